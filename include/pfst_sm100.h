@@ -1,0 +1,159 @@
+/*
+ * pfst_sm100.h — C ABI of libpfst_sm100.so: hand-written sm_100a (B200) CUDA
+ * kernels for the per-iteration self-training hot path of zhu-xlab/PFST.
+ *
+ * The reference has NO foreign-function interface (it is pure Python/PyTorch);
+ * every entry point below names the reference Python code (file:line under the
+ * reference checkout) whose arithmetic it replaces. INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers on
+ *     the current CUDA device unless the parameter comment says "host";
+ *   - tensors are dense, row-major, in the reference's layouts (NCHW logits /
+ *     features, (B,1,H,W) int64 label maps);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued
+ *     asynchronously on it; nothing here synchronises the device, allocates
+ *     device memory or throws;
+ *   - return value: PFST_OK (0) or a negative PFST_ERR_* code. A failed CUDA
+ *     launch leaves its text in pfst_last_cuda_error() (per host thread);
+ *   - there is no CPU fallback: on a machine without an sm_100 device the
+ *     compute entry points return PFST_ERR_NO_DEVICE / PFST_ERR_CUDA.
+ */
+#ifndef PFST_SM100_H_
+#define PFST_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFST_OK 0
+#define PFST_ERR_INVALID_ARG (-1)
+#define PFST_ERR_UNSUPPORTED (-2)
+#define PFST_ERR_CUDA (-3)
+#define PFST_ERR_NO_DEVICE (-4)
+
+/* dtype tags for the label-map entry points */
+#define PFST_DT_U8 0
+#define PFST_DT_I32 1
+#define PFST_DT_I64 2
+
+/* ---- library ------------------------------------------------------------ */
+const char* pfst_version(void);
+const char* pfst_error_string(int code);
+const char* pfst_last_cuda_error(void);
+/* PFST_OK iff the current device is compute capability 10.x (B200). */
+int pfst_device_check(void);
+
+/* ---- E1/E2: EMA mean-teacher update ---------------------------------------
+ * Replaces PFGST._init_ema_weights / PFGST._update_ema
+ * (rsiseg/models/uda/pfgst.py:105-114, 116-127): a Python loop of
+ * `ema[:] = a*ema + (1-a)*p` over ~214 parameter tensors (3 ATen launches
+ * each). One launch updates every tensor; arithmetic is the reference's
+ * separately-rounded fl(fl(a32*e) + fl(b32*p)) (no FMA contraction).          */
+
+/* a = min(1 - 1/(iter+1), alpha) in double; a32=(float)a, b32=(float)(1.0-a)
+ * (pfgst.py:117 + torch's python-scalar -> fp32 conversion). Host only.       */
+int pfst_ema_coeffs(int64_t iter, double alpha, float* a32_host, float* b32_host);
+
+/* mode 0: ema = a32*ema + b32*param ; mode 1: ema = param (E1, bit copy).
+ * ema_ptrs/param_ptrs/numel: device arrays of n_tensors entries.
+ * chunk_tensor/chunk_begin: device arrays of n_chunks entries; chunk i covers
+ * elements [chunk_begin[i], min(chunk_begin[i]+chunk_elems, numel[t])) of
+ * tensor t = chunk_tensor[i]. chunk_elems must be a multiple of 1024.          */
+int pfst_ema_update_multi(float* const* ema_ptrs, const float* const* param_ptrs,
+                          const int64_t* numel, const int32_t* chunk_tensor,
+                          const int64_t* chunk_begin, int64_t n_chunks,
+                          int32_t chunk_elems, float a32, float b32, int32_t mode,
+                          void* stream);
+
+/* Same arithmetic over one flat buffer (e.g. a flattened parameter bucket).   */
+int pfst_ema_update_flat(float* ema, const float* param, int64_t n, float a32,
+                         float b32, int32_t mode, void* stream);
+
+/* ---- S1/S2: pseudo-label generation ----------------------------------------
+ * Replaces pfgst.py:259-262 (softmax -> max -> ge(thr)) and the count used for
+ * the pseudo-weight at pfgst.py:264-266. One pass over NCHW fp32 logits.
+ *   label[b,p] = argmax_c softmax(logits[b,:,p])  (first index on ties, int64)
+ *   conf[b,p]  = max_c softmax(...)               (fp32, = 1/sum exp(x-max))
+ *   confident  = mode 0: conf >= thr[label]  (reference online rule; thr is one
+ *                        scalar broadcast, or a per-class vector)
+ *                mode 1: entropy(softmax) < thr[label] (offline class-wise rule,
+ *                        rsiseg/datasets/pipelines/loading.py:474-487)
+ *   *count     = number of confident pixels (zeroed here, then accumulated)
+ *   weight_part (nullable) = confident ? 1.f : 0.f   (thre_type='part', :267-268)
+ *   If reject_label >= 0, label is replaced by reject_label where not confident
+ *   (loading.py:484 writes 255).
+ * thr_per_class: device pointer to C floats, or NULL to use the scalar `thr`. */
+int pfst_pseudo_label(const float* logits, int64_t B, int32_t C, int64_t HW,
+                      float thr, const float* thr_per_class, int32_t mode,
+                      int64_t reject_label, int64_t* label, float* conf,
+                      float* weight_part, unsigned long long* count, void* stream);
+
+/* thre_type='all' (pfgst.py:264-266, 273-276): weight[b,y,x] =
+ * (float)((double)*count / (double)ps_size), rows [0,ignore_top) and
+ * [H-ignore_bottom,H) zeroed. `count` is read on the device (no host sync).    */
+int pfst_pseudo_weight_fill(float* weight, int64_t B, int64_t H, int64_t W,
+                            const unsigned long long* count, int64_t ps_size,
+                            int32_t ignore_top, int32_t ignore_bottom, void* stream);
+
+/* ---- M1/M2: ClassMix ---------------------------------------------------------
+ * Replaces get_class_masks / generate_class_mask / one_mix
+ * (rsiseg/models/utils/dacs_transforms.py:110-144) and the per-image mixing
+ * loop pfgst.py:287-300.                                                        */
+
+/* presence: device uint32[9]; words 0..7 = bitmask of label values 0..255 that
+ * occur anywhere in gt[0..n) (torch.unique of the whole batch, :113); word 8 is
+ * set non-zero if any label lies outside [0,255]. Zeroed here.                  */
+int pfst_class_presence(const int64_t* gt, int64_t n, uint32_t* presence,
+                        void* stream);
+
+/* chosen: device uint32[B*8], per-image bitmask of the classes drawn by the
+ * host RNG (np.random.choice, :115-117).
+ *   mask        = chosen[b] has bit gt[b,p]                      -> mix_mask int64
+ *   mixed_img   = mask*img + (1-mask)*trg_img  (fp32 arithmetic as one_mix)
+ *   mixed_lbl   = mask ? gt : pseudo_label                       (int64)
+ *   mixed_weight= mask*1 + (1-mask)*w, w = weight_in[b,p] if weight_in != NULL,
+ *                 else the thre_type='all' ratio (float)(count/ps_size) with the
+ *                 ignore_top/bottom rows zeroed (pfgst.py:264-277, 295-298).
+ * Any output pointer may be NULL to skip it. weight_in may alias mixed_weight.  */
+int pfst_class_mix(const int64_t* gt, const uint32_t* chosen, const float* img,
+                   const float* trg_img, const int64_t* pseudo_label,
+                   const float* weight_in, const unsigned long long* count,
+                   int64_t ps_size, int32_t ignore_top, int32_t ignore_bottom,
+                   int64_t B, int32_t img_channels, int64_t H, int64_t W,
+                   float* mixed_img, int64_t* mixed_lbl, float* mixed_weight,
+                   int64_t* mix_mask, void* stream);
+
+/* one_mix for a caller-supplied mask (dacs_transforms.py:129-144), one image:
+ * out[c,p] = mask[p]*a[c,p] + (1-mask[p])*b[c,p]; mask int64 {0,1} of HW entries;
+ * dtype 0 = fp32 operands, PFST_DT_I64 = int64 operands.                        */
+int pfst_mask_mix(const int64_t* mask, const void* a, const void* b, void* out,
+                  int32_t dtype, int64_t channels, int64_t HW, void* stream);
+
+/* ---- V1/V4: confusion matrix / area histograms -------------------------------
+ * Replaces intersect_and_union (rsiseg/core/evaluation/metrics.py:26-86, three
+ * float32 torch.histc per image on the CPU) and the integer confusion matrix of
+ * tools/confusion_matrix.py:46-65 / tests/test_metrics.py:9-28.
+ * For every image i (n_images maps of `pixels` each):
+ *   lab = lut ? lut[label] : label   (label_map, metrics.py:66-68; uint8 domain)
+ *   reduce_zero_label as metrics.py:69-72; pixels with lab == ignore_index drop.
+ *   row = lab in [0,C) ? lab : C ; col = pred in [0,C) ? pred : C
+ *   conf[slot(i)][row][col] += 1   with slot(i) = per_image ? i : 0
+ * conf is int64 [(per_image ? n_images : 1)][C+1][C+1], accumulated INTO (the
+ * caller zeroes it), so sweeps can be chained. The C x C top-left block is the
+ * confusion matrix; histc areas follow as
+ *   intersect[c]=conf[c][c], label[c]=sum_j conf[c][j], pred[c]=sum_i conf[i][c].
+ * lut: device uint8[256] or NULL.                                               */
+int pfst_confusion_accum(const void* pred, int32_t pred_dtype, const void* label,
+                         int32_t label_dtype, int64_t n_images, int64_t pixels,
+                         int32_t C, int64_t ignore_index, int32_t reduce_zero_label,
+                         const uint8_t* lut, int64_t* conf, int32_t per_image,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFST_SM100_H_ */

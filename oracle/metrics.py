@@ -1,0 +1,88 @@
+"""mIoU evaluation — restates rsiseg/core/evaluation/metrics.py:26-86, 296-395 and
+the integer confusion matrix of tools/confusion_matrix.py:46-65 /
+tests/test_metrics.py:9-28."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+
+def areas(pred: np.ndarray, label: np.ndarray, num_classes: int, ignore_index: int,
+          label_map=None, reduce_zero_label: bool = False):
+    """metrics.py:56-86 -> (intersect, union, pred_area, label_area), float32 (C,)."""
+    pred = torch.from_numpy(np.ascontiguousarray(pred))
+    label = torch.from_numpy(np.array(label))  # copy: remapping below is in place
+    if label_map:
+        for old, new in label_map.items():
+            label[label == old] = new
+    if reduce_zero_label:
+        label[label == 0] = 255
+        label = label - 1
+        label[label == 254] = 255
+    keep = label != ignore_index
+    pred, label = pred[keep], label[keep]
+    hit = pred[pred == label]
+    h = lambda v: torch.histc(v.float(), bins=num_classes, min=0, max=num_classes - 1)
+    a_i, a_p, a_l = h(hit), h(pred), h(label)
+    return a_i, a_p + a_l - a_i, a_p, a_l
+
+
+def confusion(pred: np.ndarray, label: np.ndarray, num_classes: int, ignore_index: int) -> np.ndarray:
+    """tests/test_metrics.py:9-28: bincount(n*gt+pred) over non-ignored pixels."""
+    keep = label != ignore_index
+    idx = num_classes * label[keep].astype(np.int64) + pred[keep].astype(np.int64)
+    return np.bincount(idx, minlength=num_classes ** 2).reshape(num_classes, num_classes)
+
+
+def f_score(precision, recall, beta=1):
+    # metrics.py:9-23
+    return (1 + beta ** 2) * (precision * recall) / ((beta ** 2 * precision) + recall)
+
+
+def metrics_from_areas(a_i, a_u, a_p, a_l, metrics=("mIoU",), nan_to_num=None, beta=1):
+    """metrics.py:333-395."""
+    if isinstance(metrics, str):
+        metrics = [metrics]
+    if not set(metrics) <= {"mIoU", "mDice", "mFscore"}:
+        raise KeyError(f"metrics {metrics} is not supported")
+    out = OrderedDict({"aAcc": a_i.sum() / a_l.sum()})
+    for m in metrics:
+        if m == "mIoU":
+            out["IoU"] = a_i / a_u
+            out["Acc"] = a_i / a_l
+        elif m == "mDice":
+            out["Dice"] = 2 * a_i / (a_p + a_l)
+            out["Acc"] = a_i / a_l
+        else:
+            prec, rec = a_i / a_p, a_i / a_l
+            out["Fscore"] = torch.tensor([f_score(x[0], x[1], beta) for x in zip(prec, rec)])
+            out["Precision"] = prec
+            out["Recall"] = rec
+    out = {k: v.numpy() for k, v in out.items()}
+    if nan_to_num is not None:
+        out = OrderedDict({k: np.nan_to_num(v, nan=nan_to_num) for k, v in out.items()})
+    return out
+
+
+def pre_eval_sum(per_image):
+    """metrics.py:315-323: python `sum` of the per-image float32 vectors, in order."""
+    cols = tuple(zip(*per_image))
+    return tuple(sum(c) for c in cols)
+
+
+def total_areas(preds, labels, num_classes, ignore_index, label_map=None, reduce_zero_label=False):
+    """metrics.py:89-129: float64 running totals."""
+    tot = [torch.zeros((num_classes,), dtype=torch.float64) for _ in range(4)]
+    for p, l in zip(preds, labels):
+        for t, a in zip(tot, areas(p, l, num_classes, ignore_index, label_map, reduce_zero_label)):
+            t += a
+    return tuple(tot)
+
+
+def eval_metrics(preds, labels, num_classes, ignore_index, metrics=("mIoU",), nan_to_num=None,
+                 label_map=None, reduce_zero_label=False, beta=1):
+    """metrics.py:257-293."""
+    return metrics_from_areas(*total_areas(preds, labels, num_classes, ignore_index, label_map,
+                                           reduce_zero_label), metrics, nan_to_num, beta)

@@ -1,0 +1,79 @@
+"""ctypes binding of libpfst_sm100.so (see include/pfst_sm100.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, or a
+compute entry point fails, a :class:`PfstError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libpfst_sm100.so"
+
+PFST_OK = 0
+DT_U8, DT_I32, DT_I64 = 0, 1, 2
+
+
+class PfstError(RuntimeError):
+    pass
+
+
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); mirrors include/pfst_sm100.h one to one
+SIGNATURES: dict[str, tuple] = {
+    "pfst_version": (C.c_char_p, []),
+    "pfst_error_string": (C.c_char_p, [C.c_int]),
+    "pfst_last_cuda_error": (C.c_char_p, []),
+    "pfst_device_check": (C.c_int, []),
+    "pfst_ema_coeffs": (C.c_int, [_i64, _f64, C.POINTER(_f32), C.POINTER(_f32)]),
+    "pfst_ema_update_multi": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp]),
+    "pfst_ema_update_flat": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _i32, _vp]),
+    "pfst_pseudo_label": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pfst_pseudo_weight_fill": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "pfst_class_presence": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "pfst_class_mix": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32,
+                                 _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pfst_mask_mix": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp]),
+    "pfst_confusion_accum": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _vp,
+                                       _i32, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises PfstError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise PfstError(
+                f"{LIB_PATH} not found: build it with `python -m pfst_b200.build` "
+                "(nvcc, sm_100a). pfst_b200 has no CPU/PyTorch fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code == PFST_OK:
+        return
+    lib = load()
+    msg = lib.pfst_error_string(code).decode()
+    if code == -3:
+        msg += ": " + lib.pfst_last_cuda_error().decode()
+    raise PfstError(f"{what} failed ({code}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

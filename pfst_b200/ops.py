@@ -1,0 +1,224 @@
+"""Tensor-level wrappers over the C ABI (device pointers + current CUDA stream).
+
+PyTorch is used here for device memory and streams only. Every function
+requires CUDA tensors and raises on anything else — there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PfstError
+
+_TORCH2DT = {torch.uint8: _lib.DT_U8, torch.int32: _lib.DT_I32, torch.int64: _lib.DT_I64}
+
+
+def _dev(t: torch.Tensor, name: str, dtype: Optional[torch.dtype] = None) -> int:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise PfstError(f"{name}: pfst_b200 kernels need CUDA tensors (got {t.device}); "
+                        "there is no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], name: str, dtype=None) -> Optional[int]:
+    return None if t is None else _dev(t, name, dtype)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_check() -> None:
+    _lib.call("pfst_device_check")
+
+
+# ---------------------------------------------------------------- E1/E2: EMA
+def ema_coeffs(it: int, alpha: float) -> tuple[float, float]:
+    a, b = C.c_float(), C.c_float()
+    _lib.call("pfst_ema_coeffs", int(it), float(alpha), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class EmaTable:
+    """Device-resident pointer/chunk tables for a (teacher, student) parameter list.
+
+    Built once per model (the pointers of ``nn.Parameter.data`` are stable while
+    the optimiser updates in place); ``update`` is then ONE kernel launch for all
+    tensors. ``stale()`` detects re-allocated parameters.
+    """
+
+    CHUNK = 4096  # floats per block; must be a multiple of 1024
+
+    def __init__(self, ema_params: Sequence[torch.Tensor], params: Sequence[torch.Tensor]):
+        ema_params, params = list(ema_params), list(params)
+        if len(ema_params) != len(params):
+            raise ValueError("teacher/student parameter lists differ in length")
+        self._ema = [p.data for p in ema_params]
+        self._src = [p.data for p in params]
+        eptr, pptr, numel, ctensor, cbegin = [], [], [], [], []
+        device = None
+        for i, (e, p) in enumerate(zip(self._ema, self._src)):
+            if e.shape != p.shape:
+                raise ValueError(f"parameter {i}: shape mismatch {tuple(e.shape)} vs {tuple(p.shape)}")
+            eptr.append(_dev(e, f"ema_param[{i}]", torch.float32))
+            pptr.append(_dev(p, f"param[{i}]", torch.float32))
+            device = e.device
+            n = e.numel()
+            numel.append(n)
+            for start in range(0, n, self.CHUNK):
+                ctensor.append(i)
+                cbegin.append(start)
+        self.device = device
+        self.n_tensors = len(numel)
+        self.n_chunks = len(ctensor)
+        self.total = sum(numel)
+        self._key = (tuple(eptr), tuple(pptr))
+        if self.n_chunks:
+            mk = lambda v, dt: torch.tensor(v, dtype=dt, device=device)
+            self._t_eptr = mk(eptr, torch.int64)
+            self._t_pptr = mk(pptr, torch.int64)
+            self._t_numel = mk(numel, torch.int64)
+            self._t_ctensor = mk(ctensor, torch.int32)
+            self._t_cbegin = mk(cbegin, torch.int64)
+
+    def stale(self, ema_params, params) -> bool:
+        key = (tuple(p.data.data_ptr() for p in ema_params), tuple(p.data.data_ptr() for p in params))
+        return key != self._key
+
+    def update(self, a32: float, b32: float, mode: int = 0) -> None:
+        if not self.n_chunks:
+            return
+        with torch.cuda.device(self.device):
+            _lib.call("pfst_ema_update_multi", self._t_eptr.data_ptr(), self._t_pptr.data_ptr(),
+                      self._t_numel.data_ptr(), self._t_ctensor.data_ptr(), self._t_cbegin.data_ptr(),
+                      self.n_chunks, self.CHUNK, a32, b32, mode, _stream())
+
+
+def ema_update_flat(ema: torch.Tensor, param: torch.Tensor, a32: float, b32: float, mode: int = 0):
+    if ema.shape != param.shape:
+        raise ValueError("shape mismatch")
+    _lib.call("pfst_ema_update_flat", _dev(ema, "ema", torch.float32), _dev(param, "param", torch.float32),
+              ema.numel(), a32, b32, mode, _stream())
+
+
+# ---------------------------------------------------------- S1/S2: pseudo labels
+def pseudo_label(logits: torch.Tensor, thr: float = 0.0, thr_per_class: Optional[torch.Tensor] = None,
+                 mode: int = 0, reject_label: int = -1, want_part_weight: bool = False):
+    """-> (label int64 (B,H,W), conf fp32 (B,H,W), count int64[1] on device, weight_part|None)."""
+    if logits.dim() != 4:
+        raise ValueError("logits must be (B,C,H,W)")
+    B, Cc, H, W = logits.shape
+    _dev(logits, "logits", torch.float32)
+    label = torch.empty((B, H, W), dtype=torch.int64, device=logits.device)
+    conf = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+    count = torch.empty(1, dtype=torch.int64, device=logits.device)  # written as uint64
+    wpart = torch.empty((B, H, W), dtype=torch.float32, device=logits.device) if want_part_weight else None
+    if thr_per_class is not None:
+        if thr_per_class.numel() != Cc:
+            raise ValueError("thr_per_class must have C entries")
+        _dev(thr_per_class, "thr_per_class", torch.float32)
+    _lib.call("pfst_pseudo_label", logits.data_ptr(), B, Cc, H * W, float(thr),
+              None if thr_per_class is None else thr_per_class.data_ptr(), mode, int(reject_label),
+              label.data_ptr(), conf.data_ptr(), None if wpart is None else wpart.data_ptr(),
+              count.data_ptr(), _stream())
+    return label, conf, count, wpart
+
+
+def pseudo_weight_fill(shape, count: torch.Tensor, ps_size: int, ignore_top: int = 0,
+                       ignore_bottom: int = 0) -> torch.Tensor:
+    B, H, W = shape
+    w = torch.empty((B, H, W), dtype=torch.float32, device=count.device)
+    _lib.call("pfst_pseudo_weight_fill", _dev(w, "weight"), B, H, W, _dev(count, "count", torch.int64),
+              int(ps_size), int(ignore_top), int(ignore_bottom), _stream())
+    return w
+
+
+# ------------------------------------------------------------- M1/M2: ClassMix
+def class_presence(gt: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """-> int32[9] on device: 256 presence bits + out-of-range flag."""
+    _dev(gt, "gt", torch.int64)
+    if out is None:
+        out = torch.empty(9, dtype=torch.int32, device=gt.device)
+    _lib.call("pfst_class_presence", gt.data_ptr(), gt.numel(), _dev(out, "presence", torch.int32), _stream())
+    return out
+
+
+def class_mix(gt: torch.Tensor, chosen: torch.Tensor, img: Optional[torch.Tensor],
+              trg_img: Optional[torch.Tensor], pseudo_lbl: Optional[torch.Tensor],
+              weight_in: Optional[torch.Tensor] = None, count: Optional[torch.Tensor] = None,
+              ps_size: int = 0, ignore_top: int = 0, ignore_bottom: int = 0,
+              want_weight: bool = True, want_mask: bool = True, weight_out: Optional[torch.Tensor] = None):
+    """Fused ClassMix. gt (B,1,H,W) int64; chosen int32 (B,8) bitmasks.
+    -> (mixed_img|None, mixed_lbl|None, mixed_weight|None, mix_mask|None)"""
+    _dev(gt, "gt", torch.int64)
+    B, H, W = gt.shape[0], gt.shape[-2], gt.shape[-1]
+    if gt.numel() != B * H * W:
+        raise ValueError("gt must be (B,1,H,W) or (B,H,W)")
+    _dev(chosen, "chosen", torch.int32)
+    if chosen.numel() != B * 8:
+        raise ValueError("chosen must hold 8 words per image")
+    dev = gt.device
+    channels = 0
+    mixed_img = mixed_lbl = mixed_w = mask = None
+    if img is not None:
+        _dev(img, "img", torch.float32)
+        _dev(trg_img, "trg_img", torch.float32)
+        if img.shape != trg_img.shape or img.shape[0] != B or img.shape[-2:] != gt.shape[-2:]:
+            raise ValueError("img/trg_img shape mismatch")
+        channels = img.shape[1]
+        mixed_img = torch.empty_like(img)
+    if pseudo_lbl is not None:
+        _dev(pseudo_lbl, "pseudo_label", torch.int64)
+        if pseudo_lbl.numel() != B * H * W:
+            raise ValueError("pseudo_label shape mismatch")
+        mixed_lbl = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)
+    if want_weight:
+        if weight_in is not None:
+            _dev(weight_in, "weight_in", torch.float32)
+        else:
+            _dev(count, "count", torch.int64)
+        mixed_w = weight_out if weight_out is not None else torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        _dev(mixed_w, "weight_out", torch.float32)
+    if want_mask:
+        mask = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)
+    p = lambda t: None if t is None else t.data_ptr()
+    _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), p(img), p(trg_img), p(pseudo_lbl),
+              p(weight_in) if want_weight else None, p(count), int(ps_size), int(ignore_top),
+              int(ignore_bottom), B, channels, H, W, p(mixed_img), p(mixed_lbl), p(mixed_w), p(mask),
+              _stream())
+    return mixed_img, mixed_lbl, mixed_w, mask
+
+
+# ----------------------------------------------------------- V1/V4: confusion
+def confusion_accum(pred: torch.Tensor, label: torch.Tensor, num_classes: int, ignore_index: int = 255,
+                    reduce_zero_label: bool = False, lut: Optional[torch.Tensor] = None,
+                    per_image: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pred/label: (N,H,W) or (H,W) maps (uint8/int32/int64). -> int64 (slots,C+1,C+1),
+    accumulated into ``out`` when given."""
+    if pred.shape != label.shape:
+        raise ValueError("pred/label shape mismatch")
+    if pred.dtype not in _TORCH2DT or label.dtype not in _TORCH2DT:
+        raise TypeError("pred/label must be uint8, int32 or int64")
+    _dev(pred, "pred")
+    _dev(label, "label")
+    n_images = pred.shape[0] if pred.dim() >= 3 else 1
+    pixels = pred.numel() // max(n_images, 1)
+    slots = n_images if per_image else 1
+    Cn = int(num_classes)
+    if out is None:
+        out = torch.zeros((slots, Cn + 1, Cn + 1), dtype=torch.int64, device=pred.device)
+    elif out.numel() != slots * (Cn + 1) * (Cn + 1):
+        raise ValueError("out has the wrong size")
+    _lib.call("pfst_confusion_accum", pred.data_ptr(), _TORCH2DT[pred.dtype], label.data_ptr(),
+              _TORCH2DT[label.dtype], n_images, pixels, Cn, int(ignore_index), int(bool(reduce_zero_label)),
+              _opt(lut, "lut", torch.uint8), _dev(out, "out", torch.int64), int(per_image), _stream())
+    return out

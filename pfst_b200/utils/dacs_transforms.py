@@ -1,0 +1,174 @@
+"""ClassMix utilities — drop-in for rsiseg/models/utils/dacs_transforms.py.
+
+Same function names, argument meaning and return shapes/dtypes as the reference
+(`get_class_masks`, `generate_class_mask`, `one_mix`, `strong_transform`,
+`get_mean_std`, `denorm`), computed by the sm_100a kernels in csrc/classmix.cu.
+`class_mix_batch` is the fused form the PFGST trainer uses instead of the
+reference's per-image Python loop (pfgst.py:287-300).
+
+Host RNG: the class draw stays `np.random.choice` on the global numpy stream,
+one draw per image in batch order, exactly as dacs_transforms.py:115-117 — the
+stream is observable behaviour of the reference.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import PfstError
+
+
+def _present_classes(presence_words: np.ndarray) -> np.ndarray:
+    """Sorted label values present in the batch (== torch.unique, :113)."""
+    if presence_words[8] != 0:
+        raise PfstError("gt_semantic_seg holds labels outside [0,255]; the ClassMix kernels "
+                        "address classes through a 256-bit mask")
+    bits = np.unpackbits(presence_words[:8].view(np.uint8), bitorder="little")
+    return np.nonzero(bits)[0].astype(np.int64)
+
+
+def draw_class_choice(classes: np.ndarray, batch: int, rng=np.random) -> np.ndarray:
+    """One `np.random.choice(n, int((n + n % 2) / 2), replace=False)` per image
+    (dacs_transforms.py:114-117) -> uint32 (batch, 8) bitmasks of the drawn classes."""
+    n = classes.shape[0]
+    chosen = np.zeros((batch, 8), dtype=np.uint32)
+    for b in range(batch):
+        pick = rng.choice(n, int((n + n % 2) / 2), replace=False)
+        for v in classes[pick]:
+            chosen[b, v >> 5] |= np.uint32(1) << np.uint32(v & 31)
+    return chosen
+
+
+class ClassMixPlan:
+    """Two-phase ClassMix: `start(gt)` enqueues the presence kernel and an async D2H of
+    its 36-byte result; `choose()` (called later, after other work has been enqueued)
+    waits for that copy only, draws the classes on the host and uploads the per-image
+    bitmasks. This hides the one unavoidable host round trip."""
+
+    def __init__(self, device: torch.device, max_batch: int = 256):
+        self.device = device
+        self._presence = torch.empty(9, dtype=torch.int32, device=device)
+        self._presence_host = torch.empty(9, dtype=torch.int32).pin_memory()
+        self._chosen_host = torch.empty((max_batch, 8), dtype=torch.int32).pin_memory()
+        self._chosen = torch.empty((max_batch, 8), dtype=torch.int32, device=device)
+        self._event = torch.cuda.Event()
+        self._batch = 0
+
+    def start(self, gt: torch.Tensor) -> None:
+        self._batch = gt.shape[0]
+        if self._batch > self._chosen.shape[0]:
+            raise ValueError("batch larger than the plan's capacity")
+        ops.class_presence(gt, out=self._presence)
+        self._presence_host.copy_(self._presence, non_blocking=True)
+        self._event.record()
+
+    def choose(self, rng=np.random) -> torch.Tensor:
+        self._event.synchronize()
+        classes = _present_classes(self._presence_host.numpy().view(np.uint32))
+        chosen = draw_class_choice(classes, self._batch, rng)
+        self._chosen_host[: self._batch].copy_(torch.from_numpy(chosen.view(np.int32)))
+        dst = self._chosen[: self._batch]
+        dst.copy_(self._chosen_host[: self._batch], non_blocking=True)
+        return dst
+
+
+def _chosen_for(labels: torch.Tensor, rng=np.random) -> torch.Tensor:
+    plan = ClassMixPlan(labels.device, max_batch=labels.shape[0])
+    plan.start(labels)
+    return plan.choose(rng)
+
+
+def get_class_masks(labels: torch.Tensor):
+    """dacs_transforms.py:110-119 — list of B masks, each (1,1,H,W) int64."""
+    labels = labels.contiguous()
+    chosen = _chosen_for(labels)
+    _, _, _, mask = ops.class_mix(labels, chosen, None, None, None, want_weight=False)
+    return [mask[i:i + 1] for i in range(mask.shape[0])]
+
+
+def generate_class_mask(label: torch.Tensor, classes: torch.Tensor) -> torch.Tensor:
+    """dacs_transforms.py:122-126 — label (1,H,W), classes (K,) -> (1,H,W) int64."""
+    vals = classes.detach().cpu().numpy().astype(np.int64)
+    if ((vals < 0) | (vals > 255)).any():
+        raise PfstError("classes outside [0,255]")
+    chosen = np.zeros((1, 8), dtype=np.uint32)
+    for v in vals:
+        chosen[0, v >> 5] |= np.uint32(1) << np.uint32(v & 31)
+    ch = torch.from_numpy(chosen.view(np.int32)).to(label.device)
+    H, W = label.shape[-2:]
+    _, _, _, mask = ops.class_mix(label.reshape(1, 1, H, W).contiguous(), ch, None, None, None,
+                                  want_weight=False)
+    return mask.reshape(1, H, W)
+
+
+def one_mix(mask, data=None, target=None):
+    """dacs_transforms.py:129-144 — mask (1,1,H,W); data (2,C,H,W) -> (1,C,H,W);
+    target (2,H,W) -> (1,1,H,W)."""
+    if mask is None:
+        return data, target
+    H, W = mask.shape[-2:]
+    m = mask.reshape(H * W).contiguous()
+    if m.dtype != torch.int64:
+        m = m.long()
+
+    def mix(pair, channels, out_shape):
+        a, b = pair[0].contiguous(), pair[1].contiguous()
+        out = torch.empty(out_shape, dtype=a.dtype, device=a.device)
+        if a.dtype == torch.float32:
+            dt = 0
+        elif a.dtype == torch.int64:
+            dt = 2
+        else:
+            raise TypeError(f"one_mix supports float32/int64 operands, got {a.dtype}")
+        from .. import _lib
+        _lib.call("pfst_mask_mix", ops._dev(m, "mask", torch.int64), ops._dev(a, "a"), ops._dev(b, "b"),
+                  out.data_ptr(), dt, channels, H * W, ops._stream())
+        return out
+
+    if data is not None:
+        data = mix(data, data.shape[1], (1,) + tuple(data.shape[1:]))
+    if target is not None:
+        if tuple(target.shape[-2:]) != (H, W):
+            raise PfstError("one_mix: target/mask size mismatch (resampling not supported)")
+        target = mix(target, 1, (1, 1, H, W))
+    return data, target
+
+
+def strong_transform(param, data=None, target=None):
+    """dacs_transforms.py:12-27. Colour jitter and Gaussian blur are kornia arithmetic
+    (third-party, unpinned — SURVEY.md §8c) and are NOT part of this path: requesting
+    them raises instead of silently skipping."""
+    assert (data is not None) or (target is not None)
+    if "mix" in param:
+        data, target = one_mix(mask=param["mix"], data=data, target=target)
+    if data is not None and data.shape[1] == 3:
+        if param.get("color_jitter", 0) > param.get("color_jitter_p", 1.0):
+            raise PfstError("kornia ColorJitter branch is outside the B200 hot path "
+                            "(set color_jitter_probability=1.0)")
+        if param.get("blur", 0) > 0.5:
+            raise PfstError("kornia GaussianBlur2d branch is outside the B200 hot path (set blur=False)")
+    return data, target
+
+
+def get_mean_std(img_metas, dev):
+    """dacs_transforms.py:30-41."""
+    mean = torch.stack([torch.as_tensor(m["img_norm_cfg"]["mean"], device=dev) for m in img_metas])
+    std = torch.stack([torch.as_tensor(m["img_norm_cfg"]["std"], device=dev) for m in img_metas])
+    return mean.view(-1, 3, 1, 1), std.view(-1, 3, 1, 1)
+
+
+def denorm(img, mean, std):
+    """dacs_transforms.py:44-45."""
+    return img.mul(std).add(mean) / 255.0
+
+
+def class_mix_batch(img: torch.Tensor, trg_img: torch.Tensor, gt: torch.Tensor, pseudo_lbl: torch.Tensor,
+                    chosen: torch.Tensor, count: Optional[torch.Tensor] = None, ps_size: int = 0,
+                    weight_in: Optional[torch.Tensor] = None, ignore_top: int = 0, ignore_bottom: int = 0):
+    """Fused replacement of pfgst.py:281-300 for the whole batch, one launch.
+    -> mixed_img (B,3,H,W), mixed_lbl (B,1,H,W) int64, pseudo_weight (B,H,W), mix_masks (B,1,H,W) int64."""
+    return ops.class_mix(gt, chosen, img, trg_img, pseudo_lbl, weight_in=weight_in, count=count,
+                         ps_size=ps_size, ignore_top=ignore_top, ignore_bottom=ignore_bottom)

@@ -1,0 +1,155 @@
+"""Load the reference's hot-path modules BY FILE PATH from a read-only checkout.
+
+Only usable where the reference checkout exists (the build container:
+/root/reference). Used by make_golden.py to produce the committed fixtures and by
+the `-m "not gpu"` pinning tests, which skip when the checkout is absent (it is
+absent on the GPU box). Nothing is copied: the files are executed where they lie
+with small import stubs for packages that are not installed here (mmcv,
+matplotlib, timm, the rsiseg package __init__ that asserts an mmcv version).
+SURVEY.md Appendix D is the recipe.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+from pathlib import Path
+
+REF_ROOT = Path(os.environ.get("PFST_REFERENCE", "/root/reference"))
+
+
+def available() -> bool:
+    return (REF_ROOT / "rsiseg" / "models" / "uda" / "pfgst.py").exists()
+
+
+def _load(name: str, rel: str):
+    spec = importlib.util.spec_from_file_location(name, REF_ROOT / rel)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _stub(name: str, **attrs):
+    mod = sys.modules.get(name)
+    if mod is None:
+        mod = types.ModuleType(name)
+        mod.__path__ = []  # behaves as a package for submodule imports
+        sys.modules[name] = mod
+    for k, v in attrs.items():
+        setattr(mod, k, v)
+    return mod
+
+
+class _Registry:
+    def __init__(self):
+        self.modules = {}
+
+    def register_module(self, *a, **k):
+        def deco(cls):
+            self.modules[cls.__name__] = cls
+            return cls
+        return deco
+
+
+_cache: dict = {}
+
+
+def dacs_transforms():
+    if "dacs" not in _cache:
+        _cache["dacs"] = _load("_pfst_ref_dacs_transforms", "rsiseg/models/utils/dacs_transforms.py")
+    return _cache["dacs"]
+
+
+def metrics():
+    if "metrics" not in _cache:
+        had = "mmcv" in sys.modules
+        _stub("mmcv")
+        _cache["metrics"] = _load("_pfst_ref_metrics", "rsiseg/core/evaluation/metrics.py")
+        if not had:
+            sys.modules.pop("mmcv", None)
+    return _cache["metrics"]
+
+
+def pfgst_loss():
+    """-> module with class PFGSTLoss (CPU: torch.Tensor.cuda must be patched by the caller
+    through `cpu_cuda_identity()` because pfgst_loss.py:225-226 hard-codes .cuda())."""
+    if "loss" not in _cache:
+        pkg = "_pfst_ref_models"
+        _stub(pkg)
+        _stub(pkg + ".builder", LOSSES=_Registry())
+        _stub(pkg + ".losses")
+        _stub(pkg + ".losses.utils", get_class_weight=lambda *a, **k: None,
+              weight_reduce_loss=lambda *a, **k: None)
+        _cache["loss"] = _load(pkg + ".losses.pfgst_loss", "rsiseg/models/losses/pfgst_loss.py")
+    return _cache["loss"]
+
+
+class cpu_cuda_identity:
+    """Context manager: make Tensor.cuda() the identity on a CUDA-less host."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.Tensor.cuda
+        if not torch.cuda.is_available():
+            torch.Tensor.cuda = lambda self, *a, **k: self
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._orig
+        return False
+
+
+def pfgst():
+    """-> module rsiseg/models/uda/pfgst.py with class PFGST (methods usable unbound on a
+    duck-typed object; the segmentor passes are supplied by the caller)."""
+    if "pfgst" not in _cache:
+        import torch.nn as nn
+
+        saved = {k: sys.modules.get(k) for k in (
+            "mmcv", "mmcv.parallel", "matplotlib", "matplotlib.pyplot", "timm", "timm.models",
+            "timm.models.layers", "rsiseg", "rsiseg.core", "rsiseg.models", "rsiseg.models.uda",
+            "rsiseg.models.uda.uda_decorator", "rsiseg.models.utils",
+            "rsiseg.models.utils.dacs_transforms")}
+        dacs = dacs_transforms()
+        mloss = pfgst_loss()
+
+        class _DropPath(nn.Module):
+            pass
+
+        class _MMDDP(nn.Module):
+            pass
+
+        uda_reg, loss_reg = _Registry(), _Registry()
+        _stub("mmcv", print_log=lambda *a, **k: None)
+        _stub("mmcv.parallel", MMDistributedDataParallel=_MMDDP)
+        _stub("matplotlib")
+        _stub("matplotlib.pyplot")
+        _stub("timm")
+        _stub("timm.models")
+        _stub("timm.models.layers", DropPath=_DropPath)
+
+        def add_prefix(inputs, prefix):  # rsiseg/core/utils/misc.py:2-18 (glue)
+            return {f"{prefix}.{k}": v for k, v in inputs.items()}
+
+        builder = types.SimpleNamespace(
+            build_loss=lambda cfg: mloss.PFGSTLoss(**{k: v for k, v in cfg.items() if k != "type"}))
+        _stub("rsiseg")
+        _stub("rsiseg.core", add_prefix=add_prefix)
+        _stub("rsiseg.models", UDA=uda_reg, build_segmentor=lambda cfg: cfg["_instance_factory"](),
+              builder=builder, BaseSegmentor=nn.Module)
+        _stub("rsiseg.models.uda")
+        _stub("rsiseg.models.utils")
+        sys.modules["rsiseg.models.utils.dacs_transforms"] = dacs
+        deco = _load("rsiseg.models.uda.uda_decorator", "rsiseg/models/uda/uda_decorator.py")
+        mod = _load("_pfst_ref_pfgst", "rsiseg/models/uda/pfgst.py")
+        mod._uda_decorator = deco
+        _cache["pfgst"] = mod
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return _cache["pfgst"]
