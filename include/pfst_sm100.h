@@ -92,6 +92,11 @@ int pfst_pseudo_label(const float* logits, int64_t B, int32_t C, int64_t HW,
                       int64_t reject_label, int64_t* label, float* conf,
                       float* weight_part, unsigned long long* count, void* stream);
 
+/* Self-test of the kernel's hand-scheduled exp: *mismatches = number of x[i]
+ * (x[i] <= 0) for which it differs bitwise from CUDA's expf. Must be 0.       */
+int pfst_selftest_exp(const float* x, int64_t n, unsigned long long* mismatches,
+                      void* stream);
+
 /* thre_type='all' (pfgst.py:264-266, 273-276): weight[b,y,x] =
  * (float)((double)*count / (double)ps_size), rows [0,ignore_top) and
  * [H-ignore_bottom,H) zeroed. `count` is read on the device (no host sync).    */

@@ -9,7 +9,10 @@ import ctypes as C
 import threading
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libpfst_sm100.so"
+import os
+
+# PFST_LIB overrides the library path (A/B experiments with alternative builds only)
+LIB_PATH = Path(os.environ.get("PFST_LIB") or (Path(__file__).resolve().parent / "csrc" / "libpfst_sm100.so"))
 
 PFST_OK = 0
 DT_U8, DT_I32, DT_I64 = 0, 1, 2
@@ -31,6 +34,7 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_ema_update_multi": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp]),
     "pfst_ema_update_flat": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _i32, _vp]),
     "pfst_pseudo_label": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pfst_selftest_exp": (C.c_int, [_vp, _i64, _vp, _vp]),
     "pfst_pseudo_weight_fill": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp]),
     "pfst_class_presence": (C.c_int, [_vp, _i64, _vp, _vp]),
     "pfst_class_mix": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i64, _i32,

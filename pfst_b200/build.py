@@ -48,7 +48,7 @@ def _compile(src: Path, verbose: bool) -> tuple[Path, str]:
     newest_dep = max(src.stat().st_mtime, _deps_mtime())
     if obj.exists() and obj.stat().st_mtime >= newest_dep:
         return obj, ""
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("PFST_EXTRA_NVCC", "").split(), "-c", str(src), "-o", str(obj)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")

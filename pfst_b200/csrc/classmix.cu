@@ -63,15 +63,14 @@ class_mix_kernel(const int64_t* __restrict__ gt, const uint32_t* __restrict__ ch
                  int ignore_bottom, int64_t B, int channels, int64_t H, int64_t W,
                  float* __restrict__ mixed_img, int64_t* __restrict__ mixed_lbl,
                  float* mixed_weight, int64_t* __restrict__ mix_mask) {
+  // grid = (tiles of the image plane, images): 32-bit pixel index, no 64-bit divisions
   const int64_t HW = H * W;
-  const int64_t per_img = HW / VEC;
-  const int64_t total = B * per_img;
+  const unsigned per_img = (unsigned)(HW / VEC);
   float ratio = 0.f;
   if (mixed_weight && !weight_in) ratio = (float)((double)(*count) / (double)ps_size);
-  for (int64_t i = (int64_t)blockIdx.x * kMixThreads + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * kMixThreads) {
-    const int64_t b = i / per_img;
-    const int64_t p = (i - b * per_img) * VEC;
+  const unsigned i = blockIdx.x * kMixThreads + threadIdx.x;
+  for (int64_t b = blockIdx.y; b < B && i < per_img; b += gridDim.y) {
+    const int64_t p = (int64_t)i * VEC;
     const int64_t o = b * HW + p;
     int64_t g[VEC];
     if (VEC == 4) {
@@ -135,7 +134,7 @@ class_mix_kernel(const int64_t* __restrict__ gt, const uint32_t* __restrict__ ch
       if (ignore_top > 0 || ignore_bottom > 0) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-          const int64_t y = (p + k) / W;
+          const int64_t y = (int64_t)((unsigned)(p + k) / (unsigned)W);
           if (y < ignore_top || y >= H - ignore_bottom) w[k] = 0.f;
         }
       }
@@ -236,16 +235,16 @@ int pfst_class_mix(const int64_t* gt, const uint32_t* chosen, const float* img,
                     (!mixed_weight || (aligned16(mixed_weight) && (!weight_in || aligned16(weight_in)))) &&
                     (!mix_mask || aligned16(mix_mask));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t items = vec4 ? B * (HW / 4) : B * HW;
-  int64_t g = (items + pfst::kMixThreads - 1) / pfst::kMixThreads;
-  const int64_t cap = (int64_t)pfst::kNumSMs * 8 * 32;
-  if (g > cap) g = cap;
+  if (HW > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+  const int64_t items = vec4 ? HW / 4 : HW;
+  const dim3 g((unsigned)((items + pfst::kMixThreads - 1) / pfst::kMixThreads),
+               (unsigned)(B < 65535 ? B : 65535), 1);
   if (vec4)
-    pfst::class_mix_kernel<4><<<(unsigned)g, pfst::kMixThreads, 0, s>>>(
+    pfst::class_mix_kernel<4><<<g, pfst::kMixThreads, 0, s>>>(
         gt, chosen, img, trg_img, pseudo_label, weight_in, count, ps_size, ignore_top, ignore_bottom,
         B, img_channels, H, W, mixed_img, mixed_lbl, mixed_weight, mix_mask);
   else
-    pfst::class_mix_kernel<1><<<(unsigned)g, pfst::kMixThreads, 0, s>>>(
+    pfst::class_mix_kernel<1><<<g, pfst::kMixThreads, 0, s>>>(
         gt, chosen, img, trg_img, pseudo_label, weight_in, count, ps_size, ignore_top, ignore_bottom,
         B, img_channels, H, W, mixed_img, mixed_lbl, mixed_weight, mix_mask);
   PFST_CHECK_LAUNCH("pfst_class_mix");

@@ -10,23 +10,35 @@
 // (C+1)x(C+1) int64 matrix per slot: row/col C collect out-of-range values so
 // that the histc areas (which count pred and label independently) are exact.
 //
+// Label handling (label_map LUT, reduce_zero_label, ignore_index, range check) is
+// folded into ONE 256-entry shared-memory table built per block: raw label byte
+// -> element offset of the matrix row inside the block histogram (ignored labels
+// point at a scratch row that is never flushed). Per pixel that is one LDS.
+//
 // Histogramming strategy (SURVEY.md §7 "histogram contention"):
-//   * bins=(C+1)^2 <= 96 (C <= 8: ISPRS 6 classes, Inria 2): every thread owns a
-//     private column of 32-bit counters in shared memory, hist[bin][tid] — bank
-//     = tid, so updates are conflict-free plain LDS/ADD/STS with NO atomics even
-//     for worst-case uniformly random labels;
+//   * (C+1)(C+2) <= 192 counters (C <= 12: ISPRS 6 classes, Inria 2): every thread
+//     owns a private column of 16-bit counters, hist[bin][tid] (flushed before they
+//     can wrap), so updates are plain LDS/ADD/STS with NO atomics and no dependence
+//     on the label distribution, even for worst-case uniformly random labels;
 //   * larger C: one shared histogram per block, warp-aggregated (match.any)
 //     shared atomics; beyond the shared-memory budget, warp-aggregated global
 //     atomics.
-// Blocks own a contiguous span of the pixel stream and flush their histogram
-// once per image they touch, so global atomics are O(grid * bins).
+// Blocks own a contiguous span of the pixel stream (persistent grid, one resident
+// wave), prefetch the next tile while counting the current one, and flush their
+// histogram once per image they touch, so global atomics are O(grid * bins).
 #include "common.cuh"
 
 namespace pfst {
 
 constexpr int kCfThreads = 256;
 constexpr int kCfUnroll = 4;
-constexpr int kCfPrivateMaxBins = 96;          // 96 KB of private counters per block
+#ifndef PFST_CF_PRIV_ATOMIC
+#define PFST_CF_PRIV_ATOMIC 0
+#endif
+// private counters: 16-bit LDS/ADD/STS (0) or 32-bit fire-and-forget shared atomics (1)
+constexpr bool kCfPrivAtomic = PFST_CF_PRIV_ATOMIC != 0;
+constexpr int kCfPrivWordsPerBin = kCfPrivAtomic ? 256 : 128;   // 32-bit words per bin (256 threads)
+constexpr int kCfPrivateMaxRows = 96 * 1024 / (4 * kCfPrivWordsPerBin);  // 96 KB per block
 constexpr int kCfSharedMaxBins = 40960;        // 160 KB shared histogram
 
 struct CfParams {
@@ -65,16 +77,22 @@ __device__ __forceinline__ void load_units(const T* __restrict__ p, T (&out)[N])
   }
 }
 
-// returns bin index or -1 when the pixel is ignored
-__device__ __forceinline__ int cf_bin(int64_t pred, int64_t lab, const CfParams& q,
-                                      const uint8_t* __restrict__ lut_s) {
-  if (lut_s && lab >= 0 && lab < 256) lab = lut_s[lab];
+// Row of a label value after label_map / reduce_zero_label / ignore: 0..C-1 in
+// range, C out of range, C+1 ignored (scratch row).
+__device__ __forceinline__ int cf_row(int64_t lab, const CfParams& q, const uint8_t* __restrict__ lut) {
+  if (lut && lab >= 0 && lab < 256) lab = lut[lab];
   if (q.reduce_zero_label) lab = (lab == 0 || lab == 255) ? 255 : lab - 1;
-  if (lab == q.ignore_index) return -1;
-  const int C = q.C;
-  const int row = (lab >= 0 && lab < C) ? (int)lab : C;
-  const int col = (pred >= 0 && pred < C) ? (int)pred : C;
-  return row * (C + 1) + col;
+  if (lab == q.ignore_index) return q.C + 1;
+  return (lab >= 0 && lab < q.C) ? (int)lab : q.C;
+}
+
+template <typename PT>
+__device__ __forceinline__ unsigned cf_col(PT pred, unsigned C) {
+  if constexpr (sizeof(PT) == 8) {
+    return ((unsigned long long)pred < (unsigned long long)C) ? (unsigned)pred : C;
+  } else {
+    return min((unsigned)pred, C);   // negative int32 wraps to a large unsigned -> C
+  }
 }
 
 // STRAT 0: private per-thread counters; 1: shared atomics; 2: global atomics
@@ -82,15 +100,17 @@ template <typename PT, typename LT, int UNIT, int STRAT>
 __global__ void __launch_bounds__(kCfThreads)
 confusion_kernel(const CfParams q) {
   extern __shared__ __align__(16) unsigned cf_smem[];
-  __shared__ uint8_t lut_s[256];
+  __shared__ unsigned row_off[256];   // raw label byte -> element offset of its matrix row
   const int tid = threadIdx.x;
-  const int bins = (q.C + 1) * (q.C + 1);
-  const uint8_t* lut = nullptr;
-  if (q.lut) {
-    lut_s[tid] = q.lut[tid];  // kCfThreads == 256
-    lut = lut_s;
-  }
-  const int hist_words = STRAT == 0 ? bins * kCfThreads : (STRAT == 1 ? bins : 0);
+  const unsigned C = (unsigned)q.C, C1 = C + 1;
+  const int bins = (int)(C1 * C1);            // flushed bins; the scratch row follows them
+  const int rows_total = (int)(C1 * (C1 + 1));
+  // element stride between consecutive bins: STRAT 0 interleaves the 256 private columns
+  constexpr unsigned kBinStride = STRAT == 0 ? kCfThreads : 1;
+  row_off[tid] = (unsigned)cf_row(tid, q, q.lut) * C1 * kBinStride;   // kCfThreads == 256
+  // STRAT 0 packs two 16-bit private counters per 32-bit word
+  unsigned short* priv = reinterpret_cast<unsigned short*>(cf_smem);
+  const int hist_words = STRAT == 0 ? rows_total * kCfPrivWordsPerBin : (STRAT == 1 ? rows_total : 0);
   for (int i = tid; i < hist_words; i += kCfThreads) cf_smem[i] = 0u;
   __syncthreads();
 
@@ -101,60 +121,36 @@ confusion_kernel(const CfParams q) {
   int64_t u = (int64_t)blockIdx.x * q.span_units;
   int64_t span_end = u + q.span_units;
   if (span_end > total_units) span_end = total_units;
+  constexpr int64_t kTile = (int64_t)kCfThreads * kCfUnroll;
 
-  while (u < span_end) {
-    const int64_t img = u / upi;
-    int64_t seg_end = (img + 1) * upi;
-    if (seg_end > span_end) seg_end = span_end;
-    int64_t* out = q.conf + img * bins;
-
-    for (int64_t base = u; base < seg_end; base += kCfThreads * kCfUnroll) {
-      PT pv[kCfUnroll][UNIT];
-      LT lv[kCfUnroll][UNIT];
+  PT pv[kCfUnroll][UNIT], pn[kCfUnroll][UNIT];
+  LT lv[kCfUnroll][UNIT], ln[kCfUnroll][UNIT];
+  auto load_tile = [&](int64_t base, int64_t seg_end, PT (&P)[kCfUnroll][UNIT], LT (&L)[kCfUnroll][UNIT]) {
 #pragma unroll
-      for (int j = 0; j < kCfUnroll; ++j) {
-        const int64_t unit = base + j * kCfThreads + tid;
-        if (unit < seg_end) {
-          load_units<PT, UNIT>(pred + unit * UNIT, pv[j]);
-          load_units<LT, UNIT>(label + unit * UNIT, lv[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kCfUnroll; ++j) {
-        const int64_t unit = base + j * kCfThreads + tid;
-        const bool live = unit < seg_end;
-#pragma unroll
-        for (int k = 0; k < UNIT; ++k) {
-          const int bin = live ? cf_bin((int64_t)pv[j][k], (int64_t)lv[j][k], q, lut) : -1;
-          if (STRAT == 0) {
-            if (bin >= 0) cf_smem[bin * kCfThreads + tid] += 1u;
-          } else {
-            // warp-aggregate equal bins, one atomic per distinct bin per warp
-            const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            const int leader = __ffs(peers) - 1;
-            if (bin >= 0 && (tid & 31) == leader) {
-              if (STRAT == 1) atomicAdd(&cf_smem[bin], (unsigned)__popc(peers));
-              else atomicAdd(reinterpret_cast<unsigned long long*>(out) + bin,
-                             (unsigned long long)__popc(peers));
-            }
-          }
-        }
+    for (int j = 0; j < kCfUnroll; ++j) {
+      const int64_t unit = base + j * kCfThreads + tid;
+      if (unit < seg_end) {
+        load_units<PT, UNIT>(pred + unit * UNIT, P[j]);
+        load_units<LT, UNIT>(label + unit * UNIT, L[j]);
       }
     }
+  };
 
-    // flush this image's counts
+  // add the block's counts into the image's matrix and clear them
+  auto flush = [&](int64_t* out) {
     if (STRAT == 0) {
       __syncthreads();
       const int warp = tid >> 5, lane = tid & 31;
-      for (int b = warp; b < bins; b += kCfThreads / 32) {
+      for (int b = warp; b < rows_total; b += kCfThreads / 32) {
         unsigned s = 0;
 #pragma unroll
-        for (int k = 0; k < kCfThreads / 32; ++k) {
-          s += cf_smem[b * kCfThreads + k * 32 + lane];
-          cf_smem[b * kCfThreads + k * 32 + lane] = 0u;
+        for (int k = 0; k < kCfPrivWordsPerBin / 32; ++k) {
+          const unsigned w = cf_smem[b * kCfPrivWordsPerBin + k * 32 + lane];
+          s += kCfPrivAtomic ? w : (w & 0xffffu) + (w >> 16);
+          cf_smem[b * kCfPrivWordsPerBin + k * 32 + lane] = 0u;
         }
         s = warp_sum(s);
-        if (lane == 0 && s)
+        if (lane == 0 && s && b < bins)
           atomicAdd(reinterpret_cast<unsigned long long*>(out) + b, (unsigned long long)s);
       }
       __syncthreads();
@@ -169,6 +165,71 @@ confusion_kernel(const CfParams q) {
       }
       __syncthreads();
     }
+  };
+  // a private 16-bit counter gains at most kCfUnroll*UNIT per tile
+  constexpr int kTilesPerFlush = kCfPrivAtomic ? 0x7fffffff : 65535 / (kCfUnroll * UNIT);
+
+  while (u < span_end) {
+    const int64_t img = u / upi;
+    int64_t seg_end = (img + 1) * upi;
+    if (seg_end > span_end) seg_end = span_end;
+    int64_t* out = q.conf + img * bins;
+
+    load_tile(u, seg_end, pv, lv);
+    int tiles_since_flush = 0;
+    for (int64_t base = u; base < seg_end; base += kTile) {
+      if (STRAT == 0 && ++tiles_since_flush > kTilesPerFlush) {
+        flush(out);
+        tiles_since_flush = 1;
+      }
+      // software pipeline: next tile's loads are in flight while this one is counted
+      if (base + kTile < seg_end) load_tile(base + kTile, seg_end, pn, ln);
+      // 1) all bin indices of the tile first (independent LDS lookups, batched) ...
+      unsigned idx[kCfUnroll][UNIT];
+      const unsigned scratch = C1 * C1 * kBinStride;
+#pragma unroll
+      for (int j = 0; j < kCfUnroll; ++j) {
+        const bool live = base + j * kCfThreads + tid < seg_end;
+#pragma unroll
+        for (int k = 0; k < UNIT; ++k) {
+          unsigned roff;
+          if constexpr (sizeof(LT) == 1) {
+            roff = row_off[lv[j][k]];
+          } else {
+            const int64_t lab = (int64_t)lv[j][k];
+            roff = ((unsigned long long)lab < 256ull) ? row_off[lab]
+                                                      : (unsigned)cf_row(lab, q, nullptr) * C1 * kBinStride;
+          }
+          idx[j][k] = live ? roff + cf_col<PT>(pv[j][k], C) * kBinStride + (STRAT == 0 ? tid : 0) : scratch + (STRAT == 0 ? tid : 0);
+        }
+      }
+      // 2) ... then the counter updates
+#pragma unroll
+      for (int j = 0; j < kCfUnroll; ++j) {
+#pragma unroll
+        for (int k = 0; k < UNIT; ++k) {
+          if (STRAT == 0) {
+            if (kCfPrivAtomic) atomicAdd(&cf_smem[idx[j][k]], 1u);
+            else priv[idx[j][k]] += 1;
+          } else {
+            // warp-aggregate equal bins, one atomic per distinct bin per warp
+            const unsigned peers = __match_any_sync(0xffffffffu, idx[j][k]);
+            const int leader = __ffs(peers) - 1;
+            if ((int)idx[j][k] < bins && (tid & 31) == leader) {
+              if (STRAT == 1) atomicAdd(&cf_smem[idx[j][k]], (unsigned)__popc(peers));
+              else atomicAdd(reinterpret_cast<unsigned long long*>(out) + idx[j][k],
+                             (unsigned long long)__popc(peers));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kCfUnroll; ++j)
+#pragma unroll
+        for (int k = 0; k < UNIT; ++k) { pv[j][k] = pn[j][k]; lv[j][k] = ln[j][k]; }
+    }
+
+    flush(out);
     u = seg_end;
   }
 }
@@ -176,9 +237,13 @@ confusion_kernel(const CfParams q) {
 template <typename PT, typename LT, int UNIT, int STRAT>
 static int launch_cf_strat(CfParams q, size_t smem, cudaStream_t s) {
   auto k = confusion_kernel<PT, LT, UNIT, STRAT>;
-  if (smem > 0)
+  if (smem > 0) {
     PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "pfst_confusion_accum/attr");
+    PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared),
+                  "pfst_confusion_accum/carveout");
+  }
   int occ = 0;
   PFST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kCfThreads, smem),
                 "pfst_confusion_accum/occupancy");
@@ -201,11 +266,11 @@ static int launch_cf_strat(CfParams q, size_t smem, cudaStream_t s) {
 
 template <typename PT, typename LT, int UNIT>
 static int launch_cf(const CfParams& q, cudaStream_t s) {
-  const int bins = (q.C + 1) * (q.C + 1);
-  if (bins <= kCfPrivateMaxBins)
-    return launch_cf_strat<PT, LT, UNIT, 0>(q, (size_t)bins * kCfThreads * sizeof(unsigned), s);
-  if (bins <= kCfSharedMaxBins)
-    return launch_cf_strat<PT, LT, UNIT, 1>(q, (size_t)bins * sizeof(unsigned), s);
+  const int rows_total = (q.C + 1) * (q.C + 2);   // bins + scratch row
+  if (rows_total <= kCfPrivateMaxRows)
+    return launch_cf_strat<PT, LT, UNIT, 0>(q, (size_t)rows_total * kCfPrivWordsPerBin * sizeof(unsigned), s);
+  if (rows_total <= kCfSharedMaxBins)
+    return launch_cf_strat<PT, LT, UNIT, 1>(q, (size_t)rows_total * sizeof(unsigned), s);
   return launch_cf_strat<PT, LT, UNIT, 2>(q, 0, s);
 }
 

@@ -127,3 +127,29 @@ def test_pseudo_label_against_torch_cuda(cuda):
     assert torch.allclose(conf, prob_t, rtol=0, atol=1e-6)
     safe = (prob_t - THR).abs() > 1e-6
     assert torch.equal(conf.ge(THR)[safe], large_t[safe])
+
+
+def test_exp_split_is_bit_identical(cuda):
+    """The kernel's hand-scheduled exp must equal CUDA expf bit for bit on d = x - max <= 0."""
+    from pfst_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    xs = [-torch.rand(4_000_000, generator=g) * 110.0,            # whole useful range incl. underflow
+          -torch.rand(2_000_000, generator=g) * 1e-3,              # near zero
+          -torch.logspace(-45, 2.1, 200_000),                      # denormals .. -126
+          torch.tensor([0.0, -0.0, float("-inf"), float("nan"), -87.3, -88.7, -103.9, -104.1, -126.0])]
+    x = torch.cat(xs).to(cuda)
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    _lib.call("pfst_selftest_exp", x.data_ptr(), x.numel(), bad.data_ptr(), ops._stream())
+    assert int(bad.cpu()) == 0
+
+
+def test_pseudo_label_bitwise_vs_torch_cuda_report(cuda):
+    """Informational strictness: on the GPU the confidences should equal torch's own
+    softmax->max bit for bit (same expf, same summation order); allow 1e-6 as specified."""
+    g = torch.Generator().manual_seed(77)
+    x = teacher_logits(2, 6, 256, 256, g).to(cuda)
+    _, prob_t, _ = opl.pseudo_label(x, THR)
+    _, conf, _, _ = ops.pseudo_label(x, THR)
+    frac_equal = float((conf == prob_t).float().mean())
+    print(f"bitwise-equal confidences vs torch CUDA: {frac_equal:.6f}")
+    assert frac_equal > 0.99
