@@ -138,6 +138,66 @@ int pfst_class_mix(const int64_t* gt, const uint32_t* chosen, const float* img,
 int pfst_mask_mix(const int64_t* mask, const void* a, const void* b, void* out,
                   int32_t dtype, int64_t channels, int64_t HW, void* stream);
 
+/* ---- L1-L6: PFGST auxiliary loss ----------------------------------------------
+ * Replaces PFGSTLoss.forward and its autograd backward
+ * (rsiseg/models/losses/pfgst_loss.py:44-234) for the shipped configuration:
+ * sim_type='cosine', kernel_size=3, cross_prob_type='trg', src_loss_type='mean_std',
+ * detach_unfold=True, feat_level=None. Four launches replace ~60 ATen kernels, two
+ * 604 MB im2col buffers and 3+ host syncs:
+ *   pfst_neigh_dots      x_ema, x_src  -> five dot-product maps per tensor (:181-201)
+ *   pfst_pfgst_loss_fwd  maps, logits, gt, mix masks -> six losses on the device
+ *   pfst_pfgst_loss_bwd  upstream grads -> coef maps + grad of logits_trg
+ *   pfst_neigh_grad      coef, x_src -> grad of x_src                              */
+
+/* Number of channel splits pfst_neigh_dots uses for this shape (>= 1); the caller
+ * sizes `dots` as float[splits][n_tensors][B][5][h][w]. Host only.                 */
+int32_t pfst_neigh_dots_splits(int64_t n_tensors, int64_t B, int32_t D, int32_t h,
+                               int32_t w);
+
+/* x_a, x_b: (B,D,h,w) fp32 NCHW features (x_b may be NULL: one tensor). For every
+ * pixel n: dots[...,0,n] = |x_n|^2 and dots[...,1..4,n] = x_n . x_{n+delta} for
+ * delta = (0,+d), (+d,-d), (+d,0), (+d,+d) (rows, cols), 0 outside the image.      */
+int pfst_neigh_dots(const float* x_a, const float* x_b, int64_t B, int32_t D, int32_t h,
+                    int32_t w, int32_t dilation, float* dots, void* stream);
+
+/* grad_x[b,c,n] = sum_{k=0..8} coef[b,k,n] * x[b,c,n+delta_k], delta_k =
+ * ((k/3-1)*d, (k%3-1)*d), zero outside the image. coef: (B,9,h,w).                 */
+int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int32_t h,
+                    int32_t w, int32_t dilation, float* grad_x, void* stream);
+
+/* dots: output of pfst_neigh_dots(x_ema, x_src) on the (fh,fw) feature grid with
+ * dilation `dilation/up`; the loss grid is (fh*up, fw*up) (features nearest-
+ * upsampled by the integer factor `up`, pfgst_loss.py:58-59).
+ * logits: (B,C,lh,lw), sampled at src = min(floor(dst*lscale), in-1) (nearest
+ * down-scaling by `downscale`, :57; lscale = 1/downscale).
+ * gt, mix: (B,1,gt_h,gt_w) int64 source labels / ClassMix masks, nearest-sampled
+ * to the loss grid (:62-67). weights6 (host): src_pos, src_neg, src_pos_std,
+ * src_neg_std, sim_pos, sim_neg (:110-135).
+ * stats: device double[16] workspace (zeroed here; kept for the backward).
+ * losses: device float[6] = loss_src_pos_mean, loss_src_neg_mean, loss_src_pos_std,
+ * loss_src_neg_std, loss_sim_pos, loss_sim_neg. density (nullable): (B,fh*up,fw*up)
+ * = 1 - mean_k cos_ema ('vis|density_sim_feat', :136); eroded (nullable): uint8 of
+ * the eroded target mask (:69-71).                                                 */
+int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
+                        int32_t fw, int32_t up, const float* logits, int32_t C,
+                        int32_t lh, int32_t lw, float lscale_h, float lscale_w,
+                        const int64_t* gt, const int64_t* mix, int32_t gt_h,
+                        int32_t gt_w, int32_t dilation, int32_t top_k,
+                        const float* weights6_host, double* stats, float* losses,
+                        float* density, uint8_t* eroded, void* stream);
+
+/* grad_losses: device float[6], upstream gradient of each loss. coef: (B,9,fh,fw)
+ * for pfst_neigh_grad(x_src, dilation/up). grad_logits (nullable): (B,C,lh,lw),
+ * zero-filled here, gradient of the two loss_sim terms.                            */
+int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
+                        int32_t fw, int32_t up, const float* logits, int32_t C,
+                        int32_t lh, int32_t lw, float lscale_h, float lscale_w,
+                        const int64_t* gt, const int64_t* mix, int32_t gt_h,
+                        int32_t gt_w, int32_t dilation, int32_t top_k,
+                        const float* weights6_host, const double* stats,
+                        const float* grad_losses, float* coef, float* grad_logits,
+                        void* stream);
+
 /* ---- V1/V4: confusion matrix / area histograms -------------------------------
  * Replaces intersect_and_union (rsiseg/core/evaluation/metrics.py:26-86, three
  * float32 torch.histc per image on the CPU) and the integer confusion matrix of

@@ -222,3 +222,97 @@ def confusion_accum(pred: torch.Tensor, label: torch.Tensor, num_classes: int, i
               _TORCH2DT[label.dtype], n_images, pixels, Cn, int(ignore_index), int(bool(reduce_zero_label)),
               _opt(lut, "lut", torch.uint8), _dev(out, "out", torch.int64), int(per_image), _stream())
     return out
+
+
+# ------------------------------------------------------------ L1-L6: PFGST loss
+def neigh_dots(x_a: torch.Tensor, x_b: Optional[torch.Tensor], dilation: int):
+    """-> (dots float32 (splits, T, B, 5, h, w), splits)."""
+    _dev(x_a, "x_a", torch.float32)
+    B, D, h, w = x_a.shape
+    T = 1
+    if x_b is not None:
+        _dev(x_b, "x_b", torch.float32)
+        if x_b.shape != x_a.shape:
+            raise ValueError("x_a / x_b shape mismatch")
+        T = 2
+    ks = int(_lib.load().pfst_neigh_dots_splits(T, B, D, h, w))
+    dots = torch.empty((ks, T, B, 5, h, w), dtype=torch.float32, device=x_a.device)
+    _lib.call("pfst_neigh_dots", x_a.data_ptr(), None if x_b is None else x_b.data_ptr(), B, D, h, w,
+              int(dilation), dots.data_ptr(), _stream())
+    return dots, ks
+
+
+def neigh_grad(x: torch.Tensor, coef: torch.Tensor, dilation: int) -> torch.Tensor:
+    _dev(x, "x", torch.float32)
+    _dev(coef, "coef", torch.float32)
+    B, D, h, w = x.shape
+    if tuple(coef.shape) != (B, 9, h, w):
+        raise ValueError("coef must be (B,9,h,w)")
+    grad = torch.empty_like(x)
+    _lib.call("pfst_neigh_grad", x.data_ptr(), coef.data_ptr(), B, D, h, w, int(dilation), grad.data_ptr(),
+              _stream())
+    return grad
+
+
+class LossGeometry:
+    """Shapes / resampling factors of one PFGSTLoss call, derived as the reference does
+    (pfgst_loss.py:56-67) and validated against what the kernels support."""
+
+    def __init__(self, logits_shape, feat_shape, gt_shape, downscale, dilation: int):
+        B, C, lh, lw = logits_shape
+        if downscale is not None:
+            gh, gw = int(lh * downscale), int(lw * downscale)   # F.interpolate(scale_factor): floor(in*s)
+            ls = 1.0 / downscale
+        else:
+            gh, gw, ls = lh, lw, 1.0
+        fh, fw = feat_shape[2], feat_shape[3]
+        if gh < 1 or gw < 1 or gh % fh or gw % fw or gh // fh != gw // fw:
+            raise PfstError(f"PFGSTLoss: loss grid {gh}x{gw} is not an integer up-sampling of the "
+                            f"{fh}x{fw} feature grid (unsupported resampling)")
+        up = gh // fh
+        if dilation % up:
+            raise PfstError(f"PFGSTLoss: dilation {dilation} is not a multiple of the feature up-sampling {up}")
+        self.B, self.C, self.lh, self.lw = B, C, lh, lw
+        self.fh, self.fw, self.up = fh, fw, up
+        self.gh, self.gw = gh, gw
+        self.lscale = ls
+        self.gt_h, self.gt_w = gt_shape[-2], gt_shape[-1]
+        self.dilation = int(dilation)
+
+
+def _w6(weights6):
+    arr = (C.c_float * 6)(*[float(v) for v in weights6])
+    return arr
+
+
+def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, want_vis=True):
+    """-> (losses float32[6], stats float64[16], density|None, eroded|None)."""
+    dev = logits.device
+    _dev(dots, "dots", torch.float32)
+    _dev(logits, "logits", torch.float32)
+    _dev(gt, "gt", torch.int64)
+    _dev(mix, "mix", torch.int64)
+    stats = torch.empty(16, dtype=torch.float64, device=dev)
+    losses = torch.empty(6, dtype=torch.float32, device=dev)
+    density = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.float32, device=dev) if want_vis else None
+    eroded = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.uint8, device=dev) if want_vis else None
+    _lib.call("pfst_pfgst_loss_fwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
+              geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
+              geo.dilation, int(top_k), _w6(weights6), stats.data_ptr(), losses.data_ptr(),
+              None if density is None else density.data_ptr(), None if eroded is None else eroded.data_ptr(),
+              _stream())
+    return losses, stats, density, eroded
+
+
+def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, stats, grad_losses,
+                   want_logits_grad=True):
+    """-> (coef (B,9,fh,fw), grad_logits|None)."""
+    dev = logits.device
+    _dev(grad_losses, "grad_losses", torch.float32)
+    coef = torch.empty((geo.B, 9, geo.fh, geo.fw), dtype=torch.float32, device=dev)
+    glog = torch.empty_like(logits) if want_logits_grad else None
+    _lib.call("pfst_pfgst_loss_bwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
+              geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
+              geo.dilation, int(top_k), _w6(weights6), stats.data_ptr(), grad_losses.data_ptr(),
+              coef.data_ptr(), None if glog is None else glog.data_ptr(), _stream())
+    return coef, glog

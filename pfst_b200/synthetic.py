@@ -42,8 +42,8 @@ WORKLOADS = {
     "cfg3": Workload("inria_B4_C2_1024", 4, 2, 1024, 1024),
     "cfg4": Workload("seasonnet_B64_C33_120", 64, 33, 120, 120, downscale=1.0),
     # small cases for quick parity
-    "tiny": Workload("tiny_B2_C6_64", 2, 6, 64, 64, D=32),
-    "tiny33": Workload("tiny_B3_C33_40", 3, 33, 40, 40, D=16, downscale=1.0),
+    "tiny": Workload("tiny_B2_C6_128", 2, 6, 128, 128, D=32),
+    "tiny33": Workload("tiny_B3_C33_48", 3, 33, 48, 48, D=16, downscale=1.0),
 }
 
 
