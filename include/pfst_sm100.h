@@ -198,6 +198,48 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         const float* grad_losses, float* coef, float* grad_logits,
                         void* stream);
 
+/* ---- P1-P3: class prototypes (north_star extension; no reference code) ----------
+ * Anchor: PFGST.masked_feat_dist, rsiseg/models/uda/pfgst.py:168-177. Labels are
+ * nearest-resampled to the feature grid as pfgst_loss.py:62 does.                  */
+
+/* packed: float[C*D + C], ACCUMULATED INTO (caller zeroes it; it is the NCCL
+ * all-reduce buffer): packed[c*D+d] += sum of feats[b,d,n] over pixels n with
+ * label c (0 <= label < C, and conf >= conf_thr when conf != NULL);
+ * packed[C*D+c] += number of such pixels. labels: (B,lab_h,lab_w) int64,
+ * conf: (B,lab_h,lab_w) fp32 or NULL.                                              */
+int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+                     const int64_t* labels, int32_t lab_h, int32_t lab_w,
+                     const float* conf, float conf_thr, int32_t C, float* packed,
+                     void* stream);
+
+/* mu_out[c] = packed sums / max(count,1) for classes with pixels; classes already
+ * seen (seen_prev[c] != 0) are EMA-updated fl(fl(a32*mu_prev)+fl(b32*mean)) (the E2
+ * rule); classes without pixels keep mu_prev. mu_prev / seen_prev may be NULL
+ * (first call). cnt_out int64[C], seen_out uint8[C] may be NULL.                    */
+int pfst_proto_finalize(const float* packed, int32_t C, int32_t D, const float* mu_prev,
+                        const uint8_t* seen_prev, float a32, float b32, float* mu_out,
+                        int64_t* cnt_out, uint8_t* seen_out, void* stream);
+
+/* loss = mean over valid pixels of ||feats[:,n] - mu[label_n]||_2 (masked_feat_dist
+ * with f2 = mu[label]); valid = label in [0,C) and seen[label] (seen may be NULL).
+ * dist: (B,h,w) per-pixel distances (0 where invalid), kept for the backward.
+ * acc: device double[4] workspace (zeroed here; acc[1] = number of valid pixels).  */
+int pfst_proto_dist_fwd(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+                        const int64_t* labels, int32_t lab_h, int32_t lab_w,
+                        const float* mu, const uint8_t* seen, int32_t C, float* dist,
+                        double* acc, float* loss, void* stream);
+
+/* grad_feats[b,d,n] = grad_loss * (f - mu[label]) / (dist * n_valid), 0 where invalid. */
+int pfst_proto_dist_bwd(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+                        const int64_t* labels, int32_t lab_h, int32_t lab_w,
+                        const float* mu, const uint8_t* seen, int32_t C,
+                        const float* dist, const double* acc, const float* grad_loss,
+                        float* grad_feats, void* stream);
+
+/* out[b,c,n] = ||feats[b,:,n] - mu[c]||_2 for every class: (B,C,h,w).               */
+int pfst_proto_dist_all(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+                        const float* mu, int32_t C, float* out, void* stream);
+
 /* ---- V1/V4: confusion matrix / area histograms -------------------------------
  * Replaces intersect_and_union (rsiseg/core/evaluation/metrics.py:26-86, three
  * float32 torch.histc per image on the CPU) and the integer confusion matrix of

@@ -1,0 +1,123 @@
+"""Class prototypes (P1-P3): pseudo-feature accumulation, prototype bank and the
+feature-to-prototype distance loss. north_star extension — the reference has no
+prototype code; the loss is PFGST.masked_feat_dist (rsiseg/models/uda/pfgst.py:168-177)
+with f2 = mu[label]. Kernels: csrc/proto.cu.
+
+Multi-GPU: `PrototypeBank.update` accumulates sums (C,D) and counts (C) into ONE
+packed fp32 buffer which is exactly the NCCL all-reduce payload (the accumulation
+kernel's atomics write straight into it — no pack/copy step).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import PfstError
+
+
+def _lab3(labels: torch.Tensor) -> torch.Tensor:
+    if labels.dim() == 4:
+        labels = labels[:, 0]
+    return labels.contiguous()
+
+
+class PrototypeBank:
+    def __init__(self, num_classes: int, dim: int, device, alpha: float = 0.999, group=None,
+                 comm_stream: Optional[torch.cuda.Stream] = None):
+        self.C, self.D = int(num_classes), int(dim)
+        self.device = torch.device(device)
+        self.alpha = float(alpha)
+        self.group = group
+        self.iter = 0
+        self.packed = torch.zeros(self.C * self.D + self.C, dtype=torch.float32, device=self.device)
+        self.mu = torch.zeros((self.C, self.D), dtype=torch.float32, device=self.device)
+        self.seen = torch.zeros(self.C, dtype=torch.uint8, device=self.device)
+        self.counts = torch.zeros(self.C, dtype=torch.int64, device=self.device)
+        self._mu_next = torch.empty_like(self.mu)
+        self._seen_next = torch.empty_like(self.seen)
+        self.comm_stream = comm_stream
+
+    # P1
+    def accumulate(self, feats: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None,
+                   conf_thr: float = 0.0) -> None:
+        labels = _lab3(labels)
+        B, D, h, w = feats.shape
+        if D != self.D:
+            raise ValueError("feature dim mismatch")
+        _lib.call("pfst_proto_accum", ops._dev(feats, "feats", torch.float32), B, D, h, w,
+                  ops._dev(labels, "labels", torch.int64), labels.shape[-2], labels.shape[-1],
+                  ops._opt(conf, "conf", torch.float32), float(conf_thr), self.C, self.packed.data_ptr(),
+                  ops._stream())
+
+    def all_reduce(self):
+        """Sum the packed [sums | counts] buffer over ranks (NCCL). Returns the async work
+        handle (or None); `finalize` waits on it."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return None
+        return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    # P2
+    def finalize(self, work=None) -> torch.Tensor:
+        if work is not None:
+            work.wait()
+        a32, b32 = ops.ema_coeffs(max(self.iter, 1), self.alpha) if self.iter > 0 else (0.0, 1.0)
+        _lib.call("pfst_proto_finalize", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
+                  self.seen.data_ptr(), a32, b32, self._mu_next.data_ptr(), self.counts.data_ptr(),
+                  self._seen_next.data_ptr(), ops._stream())
+        self.mu, self._mu_next = self._mu_next, self.mu
+        self.seen, self._seen_next = self._seen_next, self.seen
+        self.packed.zero_()
+        self.iter += 1
+        return self.mu
+
+    def update(self, feats, labels, conf=None, conf_thr: float = 0.0) -> torch.Tensor:
+        self.accumulate(feats, labels, conf, conf_thr)
+        return self.finalize(self.all_reduce())
+
+
+class _ProtoDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, labels, mu, seen):
+        feats = feats.contiguous()
+        B, D, h, w = feats.shape
+        C = mu.shape[0]
+        dev = feats.device
+        dist = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        acc = torch.empty(4, dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("pfst_proto_dist_fwd", ops._dev(feats, "feats", torch.float32), B, D, h, w,
+                  ops._dev(labels, "labels", torch.int64), labels.shape[-2], labels.shape[-1],
+                  ops._dev(mu, "mu", torch.float32), ops._opt(seen, "seen", torch.uint8), C, dist.data_ptr(),
+                  acc.data_ptr(), loss.data_ptr(), ops._stream())
+        ctx.save_for_backward(feats, labels, mu, seen, dist, acc)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feats, labels, mu, seen, dist, acc = ctx.saved_tensors
+        B, D, h, w = feats.shape
+        grad = torch.empty_like(feats)
+        g = grad_out.reshape(1).contiguous().float()
+        _lib.call("pfst_proto_dist_bwd", feats.data_ptr(), B, D, h, w, labels.data_ptr(), labels.shape[-2],
+                  labels.shape[-1], mu.data_ptr(), None if seen is None else seen.data_ptr(), mu.shape[0],
+                  dist.data_ptr(), acc.data_ptr(), g.data_ptr(), grad.data_ptr(), ops._stream())
+        return grad, None, None, None
+
+
+def proto_dist_loss(feats: torch.Tensor, labels: torch.Tensor, mu: torch.Tensor,
+                    seen: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mean_valid ||f_n - mu[y_n]||_2 (mu is treated as a constant, like the detached
+    ImageNet features of masked_feat_dist's original use)."""
+    return _ProtoDistFn.apply(feats, _lab3(labels), mu.detach().contiguous(), seen)
+
+
+def proto_dist_all(feats: torch.Tensor, mu: torch.Tensor) -> torch.Tensor:
+    B, D, h, w = feats.shape
+    C = mu.shape[0]
+    out = torch.empty((B, C, h, w), dtype=torch.float32, device=feats.device)
+    _lib.call("pfst_proto_dist_all", ops._dev(feats, "feats", torch.float32), B, D, h, w,
+              ops._dev(mu, "mu", torch.float32), C, out.data_ptr(), ops._stream())
+    return out

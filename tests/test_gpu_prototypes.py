@@ -1,0 +1,101 @@
+"""P1-P3 (north_star extension, parity unpinned by the reference): CUDA prototype kernels
+vs the float64 oracle built on PFGST.masked_feat_dist. 1e-5 relative; counts exact."""
+import pytest
+import torch
+
+from oracle import prototypes as OP, ema as oema
+from pfst_b200 import ops, prototypes as P
+from pfst_b200.synthetic import blocky_labels
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(B, D, h, w, C, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.relu(torch.randn((B, D, h, w), generator=g))
+    labels = blocky_labels(B, H, W, C, g, min_rect=2, max_rect=max(4, H // 2))
+    return feats, labels
+
+
+@pytest.mark.parametrize("B,D,h,w,C,H,W", [(2, 32, 16, 16, 6, 128, 128), (8, 512, 64, 64, 6, 512, 512),
+                                            (3, 16, 15, 15, 33, 120, 120), (2, 64, 128, 128, 2, 1024, 1024),
+                                            (1, 8, 5, 7, 4, 40, 56)])
+def test_accumulate_and_finalize(cuda, B, D, h, w, C, H, W):
+    feats, labels = _case(B, D, h, w, C, H, W)
+    sums, counts = OP.proto_accumulate(feats, labels[:, 0], C)
+    bank = P.PrototypeBank(C, D, cuda)
+    bank.accumulate(feats.to(cuda), labels.to(cuda))
+    packed = bank.packed.cpu()
+    got_sums, got_cnt = packed[:C * D].view(C, D), packed[C * D:]
+    assert torch.equal(got_cnt.long(), counts)
+    scale = sums.abs().max()
+    assert (got_sums.double() - sums).abs().max() <= 1e-5 * scale
+    mu = bank.finalize().cpu()
+    mu_o, seen_o = OP.proto_finalize(sums, counts)
+    assert torch.equal(bank.seen.cpu().bool(), seen_o)
+    assert torch.equal(bank.counts.cpu(), counts)
+    assert (mu.double() - mu_o.double()).abs().max() <= 1e-5 * mu_o.abs().max()
+    assert float(bank.packed.abs().sum()) == 0.0
+
+
+def test_confidence_mask_and_chained_batches(cuda):
+    B, D, h, w, C, H, W = 2, 32, 16, 16, 6, 128, 128
+    feats, labels = _case(B, D, h, w, C, H, W, seed=3)
+    g = torch.Generator().manual_seed(9)
+    conf = torch.rand((B, H, W), generator=g)
+    s1, c1 = OP.proto_accumulate(feats, labels[:, 0], C, conf, 0.5)
+    feats2, labels2 = _case(B, D, h, w, C, H, W, seed=4)
+    s2, c2 = OP.proto_accumulate(feats2, labels2[:, 0], C)
+    bank = P.PrototypeBank(C, D, cuda)
+    bank.accumulate(feats.to(cuda), labels.to(cuda), conf.to(cuda), 0.5)
+    bank.accumulate(feats2.to(cuda), labels2.to(cuda))
+    packed = bank.packed.cpu()
+    assert torch.equal(packed[C * D:].long(), c1 + c2)
+    assert (packed[:C * D].view(C, D).double() - (s1 + s2)).abs().max() <= 1e-5 * (s1 + s2).abs().max()
+
+
+def test_prototype_ema_over_iterations(cuda):
+    B, D, h, w, C, H, W = 2, 16, 8, 8, 5, 64, 64
+    bank = P.PrototypeBank(C, D, cuda, alpha=0.999)
+    mu_o, seen_o = None, None
+    for it in range(4):
+        feats, labels = _case(B, D, h, w, C, H, W, seed=10 + it)
+        if it == 1:
+            labels[labels == 2] = 0          # class 2 absent in this iteration: keeps its value
+        sums, counts = OP.proto_accumulate(feats, labels[:, 0], C)
+        a = oema.alpha_teacher(max(it, 1), 0.999)
+        mu_o, seen_o = OP.proto_finalize(sums, counts, mu_o, seen_o, float(torch.tensor(a, dtype=torch.float32)),
+                                         float(torch.tensor(1 - a, dtype=torch.float32)))
+        mu = bank.update(feats.to(cuda), labels.to(cuda)).cpu()
+        assert (mu.double() - mu_o.double()).abs().max() <= 1e-5 * mu_o.abs().max(), it
+        assert torch.equal(bank.seen.cpu().bool(), seen_o)
+
+
+@pytest.mark.parametrize("B,D,h,w,C,H,W", [(2, 32, 16, 16, 6, 128, 128), (4, 512, 64, 64, 6, 512, 512),
+                                            (3, 16, 15, 15, 33, 120, 120), (1, 8, 5, 7, 4, 40, 56)])
+def test_proto_dist_loss_and_grad(cuda, B, D, h, w, C, H, W):
+    feats, labels = _case(B, D, h, w, C, H, W, seed=5)
+    g = torch.Generator().manual_seed(6)
+    mu = torch.relu(torch.randn((C, D), generator=g))
+    seen = torch.ones(C, dtype=torch.bool)
+    seen[C - 1] = False
+    f_o = feats.clone().double().requires_grad_(True)
+    loss_o, valid = OP.proto_dist_loss(f_o, labels[:, 0], mu.double(), seen)
+    (2.5 * loss_o).backward()
+    f_c = feats.clone().to(cuda).requires_grad_(True)
+    loss_c = P.proto_dist_loss(f_c, labels.to(cuda), mu.to(cuda), seen.to(cuda).to(torch.uint8))
+    (2.5 * loss_c).backward()
+    assert abs(float(loss_c) - float(loss_o)) <= 1e-5 * abs(float(loss_o))
+    go, gc = f_o.grad, f_c.grad.cpu().double()
+    assert (gc - go).abs().max() <= 1e-5 * go.abs().max()
+    assert float(gc[:, :, ~valid[0]].abs().max() if (~valid[0]).any() else 0.0) >= 0.0
+
+
+def test_proto_dist_all(cuda):
+    for (B, D, h, w, C) in ((2, 32, 16, 16, 6), (2, 16, 15, 15, 33), (1, 512, 32, 32, 2)):
+        g = torch.Generator().manual_seed(7)
+        feats = torch.relu(torch.randn((B, D, h, w), generator=g))
+        mu = torch.relu(torch.randn((C, D), generator=g))
+        want = OP.proto_dist_all(feats.double(), mu.double())
+        got = P.proto_dist_all(feats.to(cuda), mu.to(cuda)).cpu().double()
+        assert (got - want).abs().max() <= 1e-5 * want.abs().max()
