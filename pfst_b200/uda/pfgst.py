@@ -1,0 +1,313 @@
+"""PFGST — drop-in for rsiseg/models/uda/pfgst.py:53-368 (the UDA trainer selected
+by `uda.type='PFGST'`, configs/_base_/uda/pfst.py:8).
+
+Same constructor keys, same `train_step` / `forward_train` / `_init_ema_weights` /
+`_update_ema` / `get_model` / `get_ema_model` / `get_imnet_model` API, same
+`log_vars` keys and `vis|…` states, same host RNG consumption (python `random` for
+the jitter/blur draws, the global numpy stream for ClassMix). The three segmentor
+passes are the caller's network (cuDNN); everything between them runs in the
+sm_100a kernels of this package:
+
+  reference (pfgst.py)                                   here
+  ------------------------------------------------------------------------------
+  :105-127  per-tensor Python EMA loop (~850 launches)   EmaTable.update, 1 launch
+  :259-266  softmax/max/ge/sum/.item()/.cpu()            ops.pseudo_label, 1 launch,
+                                                         count stays on the device
+  :282      torch.unique + np.random.choice + eq/sum     ClassMixPlan (presence kernel,
+                                                         36-byte D2H, host draw)
+  :287-300  2B strong_transform calls in a Python loop   ops.class_mix, 1 launch
+  :333-342  PFGSTLoss (~60 ATen kernels, 3+ syncs)       losses.PFGSTLoss, 2+2 launches
+  optional  --                                           PrototypeBank / proto_dist_loss
+                                                         (north_star P1-P3, cfg 'prototypes')
+"""
+from __future__ import annotations
+
+import random
+import warnings
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.dropout import _DropoutNd
+
+from .. import losses as _losses  # noqa: F401  (registers PFGSTLoss in LOSSES)
+from .. import ops
+from .._lib import PfstError
+from ..prototypes import PrototypeBank, proto_dist_loss
+from ..registry import UDA, build_loss
+from ..utils.dacs_transforms import ClassMixPlan, get_mean_std
+from .uda_decorator import UDADecorator, build_model, get_module
+
+
+def add_prefix(inputs, prefix):
+    """rsiseg/core/utils/misc.py:2-18."""
+    return {f'{prefix}.{name}': value for name, value in inputs.items()}
+
+
+def _params_equal(ema_model, model):
+    """pfgst.py:33-39."""
+    for ema_param, param in zip(ema_model.named_parameters(), model.named_parameters()):
+        if not torch.equal(ema_param[1].data, param[1].data):
+            return False
+    return True
+
+
+@UDA.register_module()
+class PFGST(UDADecorator):
+
+    def __init__(self, **cfg):
+        super().__init__(**cfg)
+        self.local_iter = 0
+        self.max_iters = cfg['max_iters']
+        self.alpha = cfg['alpha']
+        self.pseudo_threshold = cfg['pseudo_threshold']
+        self.psweight_ignore_top = cfg['pseudo_weight_ignore_top']
+        self.psweight_ignore_bottom = cfg['pseudo_weight_ignore_bottom']
+        self.fdist_lambda = cfg['imnet_feature_dist_lambda']
+        self.fdist_classes = cfg['imnet_feature_dist_classes']
+        self.fdist_scale_min_ratio = cfg['imnet_feature_dist_scale_min_ratio']
+        self.enable_fdist = self.fdist_lambda > 0
+        self.mix = cfg['mix']
+        self.blur = cfg['blur']
+        self.color_jitter_s = cfg['color_jitter_strength']
+        self.color_jitter_p = cfg['color_jitter_probability']
+        self.print_grad_magnitude = cfg['print_grad_magnitude']
+        self.trg_loss_weight = cfg.get('trg_loss_weight', 1.)
+        self.use_decoded_feats = cfg.get('use_decoded_feats', False)
+        self.thre_type = cfg.get('thre_type', 'all')
+        self.strong_aug_denorm_type = cfg.get('strong_aug_denorm_type', 'mean_std')
+        self.apply_no_mix = cfg.get('apply_no_mix', False)
+        assert self.mix == 'class'
+        if self.thre_type not in ('all', 'part'):
+            raise ValueError(f"thre_type {self.thre_type!r}")
+        if self.enable_fdist:
+            raise PfstError("imnet_feature_dist_lambda > 0 (ImageNet feature distance) is not part of the "
+                            "B200 hot path; every shipped config sets it to 0 (_base_/uda/pfst.py:13)")
+        # B200-path extras (absent keys = reference behaviour)
+        self.pseudo_threshold_per_class = cfg.get('pseudo_threshold_per_class', None)   # north_star S2'
+        self.kornia_aug = cfg.get('kornia_aug', 'error')       # 'error' | 'skip'
+        self.compute_vis = cfg.get('compute_vis', True)
+        proto_cfg = cfg.get('prototypes', None)
+
+        self.class_probs = {}
+        self.ema_model = build_model(cfg['model'])
+        self.imnet_model = None
+
+        aux_losses = cfg.get('aux_losses', None)
+        self.apply_aux = False
+        if aux_losses is not None:
+            self.apply_aux = True
+            if not type(aux_losses) == list:
+                aux_losses = [aux_losses]
+            aux_losses = [l if isinstance(l, nn.Module) else build_loss(l) for l in aux_losses]
+            self.aux_losses = nn.ModuleList(aux_losses)
+
+        self._ema_table = None
+        self._mix_plan = None
+        self._thr_vec = None
+        self.proto_cfg = proto_cfg
+        self.proto_bank = None
+
+    # ------------------------------------------------------------------ accessors
+    def get_ema_model(self):
+        return get_module(self.ema_model)
+
+    def get_imnet_model(self):
+        return get_module(self.imnet_model)
+
+    # ------------------------------------------------------------------------ EMA
+    def _table(self):
+        ema_p = list(self.get_ema_model().parameters())
+        stu_p = list(self.get_model().parameters())
+        if self._ema_table is None or self._ema_table.stale(ema_p, stu_p):
+            self._ema_table = ops.EmaTable(ema_p, stu_p)
+        return self._ema_table
+
+    def _init_ema_weights(self):
+        """pfgst.py:105-114 — teacher <- student, one launch."""
+        for param in self.get_ema_model().parameters():
+            param.detach_()
+        self._table().update(0.0, 1.0, mode=1)
+
+    def _update_ema(self, iter):
+        """pfgst.py:116-127 — one launch, fl(fl(a*ema)+fl((1-a)*p)) per element."""
+        a32, b32 = ops.ema_coeffs(iter, self.alpha)
+        self._table().update(a32, b32, mode=0)
+
+    # ----------------------------------------------------------------- train step
+    def train_step(self, data_batch, optimizer, **kwargs):
+        """pfgst.py:129-166."""
+        optimizer.zero_grad()
+        log_vars, vis_states = self(**data_batch)
+        optimizer.step()
+        log_vars.pop('loss', None)
+        return dict(log_vars=log_vars, num_samples=len(data_batch['img_metas']), states=vis_states)
+
+    def masked_feat_dist(self, f1, f2, mask=None):
+        """pfgst.py:168-177 (plain torch; unreachable with fdist_lambda = 0)."""
+        pw = torch.norm(f1 - f2, dim=1, p=2)
+        if mask is not None:
+            pw = pw[mask.squeeze(1)]
+        return torch.mean(pw)
+
+    def _threshold_args(self, dev):
+        if self.pseudo_threshold_per_class is None:
+            return float(self.pseudo_threshold), None
+        if self._thr_vec is None or self._thr_vec.device != dev:
+            self._thr_vec = torch.tensor(list(self.pseudo_threshold_per_class), dtype=torch.float32, device=dev)
+        return 0.0, self._thr_vec
+
+    def _check_kornia(self, color_jitter, blur):
+        wants = []
+        if color_jitter > self.color_jitter_p:
+            wants.append("ColorJitter (set color_jitter_probability=1.0)")
+        if blur > 0.5:
+            wants.append("GaussianBlur2d (set blur=False)")
+        if not wants:
+            return
+        msg = ("the kornia " + " and ".join(wants) + " branch of strong_transform is third-party arithmetic "
+               "outside the B200 hot path (SURVEY.md §8c)")
+        if self.kornia_aug == 'skip':
+            warnings.warn(msg + "; skipped (kornia_aug='skip')", stacklevel=3)
+        else:
+            raise PfstError(msg)
+
+    def forward_train(self, img, img_metas, gt_semantic_seg, target_img, target_img_metas,
+                      target_img_strong_aug):
+        """pfgst.py:179-356."""
+        log_vars = {}
+        vis_states = {}
+        total_loss = 0
+        batch_size = img.shape[0]
+        dev = img.device
+
+        # ① EMA teacher (pfgst.py:203-208)
+        if self.local_iter == 0:
+            self._init_ema_weights()
+        if self.local_iter > 0:
+            self._update_ema(self.local_iter)
+
+        # ② host RNG draws, in the reference's order (pfgst.py:212-222)
+        means, stds = get_mean_std(img_metas, dev)
+        color_jitter = random.uniform(0, 1)
+        blur = random.uniform(0, 1) if self.blur else 0
+        self._check_kornia(color_jitter, blur)
+
+        # ClassMix needs the batch's class set: start the presence kernel + 36-byte D2H now,
+        # read it after the two network passes have been enqueued
+        gt_semantic_seg = gt_semantic_seg.contiguous()
+        if self._mix_plan is None or self._mix_plan.device != dev or batch_size > self._mix_plan._chosen.shape[0]:
+            self._mix_plan = ClassMixPlan(dev, max_batch=max(batch_size, 64))
+        self._mix_plan.start(gt_semantic_seg)
+
+        # ③ student on source (pfgst.py:225-236)
+        clean_losses = self.get_model().forward_train(
+            img, img_metas, gt_semantic_seg, return_feats=True, return_logits=True,
+            return_decoded_feats=self.use_decoded_feats)
+        src_feats = clean_losses.pop('features')
+        if self.use_decoded_feats:
+            src_feats = clean_losses.pop('decoded_features')
+        src_logits = clean_losses.pop('logits')
+        clean_loss, clean_log_vars = self._parse_losses(clean_losses)
+        log_vars.update(clean_log_vars)
+        total_loss += clean_loss
+
+        # ④ teacher on target (pfgst.py:247-257)
+        for m in self.get_ema_model().modules():
+            if isinstance(m, _DropoutNd):
+                m.training = False
+            if type(m).__name__ == 'DropPath':
+                m.training = False
+        ema_logits, ema_states = self.get_ema_model().encode_decode(target_img, target_img_metas)
+        ema_feats = ema_states['feats']
+        if self.use_decoded_feats:
+            ema_feats = ema_states['decoded_features']
+
+        # ⑤ pseudo labels (pfgst.py:259-277): one kernel, count stays on the device
+        thr, thr_vec = self._threshold_args(dev)
+        pseudo_label, pseudo_prob, count, weight_part = ops.pseudo_label(
+            ema_logits.detach().contiguous(), thr, thr_vec, want_part_weight=self.thre_type == 'part')
+        ps_size = pseudo_label.numel()
+
+        # ⑥⑦ ClassMix (pfgst.py:281-300): host draw, then ONE fused launch
+        chosen = self._mix_plan.choose()
+        if self.apply_no_mix:
+            chosen = torch.zeros_like(chosen)
+        trg_img = target_img if self.apply_no_mix else target_img_strong_aug
+        mixed_img, mixed_lbl, pseudo_weight, mix_masks = ops.class_mix(
+            gt_semantic_seg, chosen, img.contiguous(), trg_img.contiguous(), pseudo_label,
+            weight_in=weight_part, count=count, ps_size=ps_size,
+            ignore_top=self.psweight_ignore_top, ignore_bottom=self.psweight_ignore_bottom)
+
+        # ⑧ student on the mixed batch (pfgst.py:303-310)
+        mix_losses = self.get_model().forward_train(
+            mixed_img, img_metas, mixed_lbl, pseudo_weight, return_feats=True, return_logits=True)
+        mixed_feats = mix_losses.pop('features')
+        mixed_logits = mix_losses.pop('logits')
+        mix_losses = add_prefix(mix_losses, 'mix')
+        mix_loss, mix_log_vars = self._parse_losses(mix_losses)
+        log_vars.update(mix_log_vars)
+        total_loss += mix_loss * self.trg_loss_weight
+
+        tensors = dict(
+            img_src=img, img_src_metas=img_metas, img_trg=mixed_img, img_mixed=mixed_img,
+            img_metas_trg=target_img_metas, gt_src=gt_semantic_seg, x_src=src_feats, x_ema=ema_feats,
+            x_trg=mixed_feats, logits_src=src_logits, logits_trg=mixed_logits, logits_ema=ema_logits,
+            mix_masks=mix_masks, pseudo_weight=pseudo_weight)
+
+        # ⑨ auxiliary losses (pfgst.py:333-342)
+        if self.apply_aux:
+            aux_losses = self._get_aux_losses(tensors=tensors)
+            vis_states.update({k: v for k, v in aux_losses.items() if k.startswith('vis|')})
+            for name in vis_states.keys():
+                aux_losses.pop(name)
+            aux_loss, aux_log_vars = self._parse_losses(aux_losses)
+            log_vars.update(aux_log_vars)
+            total_loss += aux_loss
+
+        # P1-P3 (north_star extension; off unless cfg['prototypes'] is given)
+        if self.proto_cfg is not None:
+            proto_loss = self._prototype_step(ema_feats, pseudo_label, pseudo_prob, src_feats, gt_semantic_seg)
+            p_loss, p_log_vars = self._parse_losses({'loss_proto_dist': proto_loss})
+            log_vars.update(p_log_vars)
+            total_loss += p_loss
+
+        # ⑩ backward (pfgst.py:344)
+        total_loss.backward()
+
+        # ⑪ vis states (pfgst.py:346-352)
+        if self.compute_vis:
+            vis_pseudo_weight = F.interpolate(pseudo_weight.unsqueeze(1), mixed_lbl.shape[2:])
+            vis_mask_mix = torch.where(vis_pseudo_weight > 0.0, mixed_lbl, 255)
+            vis_states.update({
+                'vis|seg_mask_src': (img, gt_semantic_seg, src_logits.max(dim=1)[1].unsqueeze(1)),
+                'vis|seg_mask_mix': (mixed_img, vis_mask_mix, mixed_logits.max(dim=1)[1].unsqueeze(1).float()),
+            })
+
+        self.local_iter += 1
+        return log_vars, vis_states
+
+    def _prototype_step(self, ema_feats, pseudo_label, pseudo_prob, src_feats, gt):
+        cfg = self.proto_cfg
+        if isinstance(ema_feats, (list, tuple)) or isinstance(src_feats, (list, tuple)):
+            raise PfstError("prototypes need use_decoded_feats=True (a single (B,D,h,w) feature map)")
+        if self.proto_bank is None:
+            self.proto_bank = PrototypeBank(self.num_classes, ema_feats.shape[1], ema_feats.device,
+                                            alpha=cfg.get('alpha', self.alpha))
+        conf_thr = cfg.get('conf_threshold', None)
+        mu = self.proto_bank.update(ema_feats.detach().contiguous(), pseudo_label,
+                                    pseudo_prob if conf_thr is not None else None,
+                                    conf_thr if conf_thr is not None else 0.0)
+        return proto_dist_loss(src_feats, gt, mu, self.proto_bank.seen) * cfg.get('weight', 0.1)
+
+    def _get_aux_losses(self, tensors):
+        """pfgst.py:358-368."""
+        aux_losses = dict()
+        for loss_module in self.aux_losses:
+            loss_ = loss_module(tensors)
+            if loss_ is None:
+                continue
+            aux_losses.update(loss_)
+        return aux_losses

@@ -1,0 +1,213 @@
+"""Generate the committed golden fixtures from the REFERENCE code itself.
+
+Run in the build container (needs /root/reference): `python tests/golden/make_golden.py`.
+Every fixture stores the (small) inputs and the outputs the reference produced for
+them, so that tests can pin (a) the oracle and (b) the CUDA path against the
+reference on machines where the reference checkout does not exist (the GPU box).
+
+  metrics.npz      rsiseg/core/evaluation/metrics.py  eval_metrics / intersect_and_union
+  ema.npz          PFGST._init_ema_weights / _update_ema      (pfgst.py:105-127)
+  pseudo_mix.npz   pseudo-label block + get_class_masks + strong_transform loop
+                   (pfgst.py:259-300, dacs_transforms.py:110-144)
+  pfgst_loss.npz   PFGSTLoss.forward + autograd backward      (pfgst_loss.py:44-234)
+  pfgst_step.npz   three PFGST.train_step iterations on a tiny segmentor
+"""
+from __future__ import annotations
+
+import random
+import sys
+import types
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+
+from tests.golden import ref_loader as R  # noqa: E402
+from tests.fake_segmentor import TinySegmentor  # noqa: E402
+from pfst_b200.synthetic import blocky_labels, teacher_logits  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+W6 = {'src_pos': 0.1, 'src_neg': 0.1, 'sim_pos': 0.1, 'sim_neg': 0.1, 'src_pos_std': 0.1, 'src_neg_std': 0.1}
+LOSS_KEYS = ("loss_src_pos_mean", "loss_src_neg_mean", "loss_src_pos_std", "loss_src_neg_std",
+             "loss_sim_pos", "loss_sim_neg")
+
+
+def gen_metrics():
+    M = R.metrics()
+    rs = np.random.RandomState(0)
+    C = 19
+    pred = rs.randint(0, C, size=(10, 30, 30))
+    label = rs.randint(0, C, size=(10, 30, 30))
+    label[:, 2, 5:10] = 255                       # the reference test's ignore stripe
+    out = {"pred": pred.astype(np.int64), "label": label.astype(np.int64), "C": C}
+    ret = M.eval_metrics(pred, label, C, 255, metrics=["mIoU", "mDice", "mFscore"])
+    for k, v in ret.items():
+        out["all_" + k] = np.asarray(v)
+    per = [M.intersect_and_union(pred[i], label[i], C, 255) for i in range(10)]
+    out["per_image"] = np.stack([np.stack([a.numpy() for a in p]) for p in per])
+    ret = M.pre_eval_to_metrics(per, ["mIoU"])
+    out["pre_eval_IoU"] = ret["IoU"]
+    # label_map + reduce_zero_label, uint8 labels
+    lab8 = rs.randint(0, 8, size=(64, 64)).astype(np.uint8)
+    lab8[:4] = 255
+    pr = rs.randint(0, 6, size=(64, 64)).astype(np.int64)
+    out["lm_pred"], out["lm_label"] = pr, lab8
+    a = M.intersect_and_union(pr, lab8.copy(), 6, 255, {7: 0, 6: 255}, True)
+    out["lm_areas"] = np.stack([t.numpy() for t in a])
+    np.savez_compressed(OUT / "metrics.npz", **out)
+
+
+def gen_ema():
+    M = R.pfgst()
+    g = torch.Generator().manual_seed(1234)
+    shapes = [(), (1,), (3,), (513,), (4097,), (8, 3, 3, 3)]
+    student = [torch.nn.Parameter(0.02 * torch.randn(s, generator=g)) for s in shapes]
+    teacher = [torch.nn.Parameter(0.02 * torch.randn(s, generator=g)) for s in shapes]
+
+    class Holder:
+        alpha = 0.999
+
+        def get_model(self):
+            return types.SimpleNamespace(parameters=lambda: iter(student))
+
+        def get_ema_model(self):
+            return types.SimpleNamespace(parameters=lambda: iter(teacher))
+
+    h = Holder()
+    out = {f"student_{i}": p.detach().numpy().copy() for i, p in enumerate(student)}
+    out.update({f"teacher0_{i}": p.detach().numpy().copy() for i, p in enumerate(teacher)})
+    its = [1, 2, 10, 999, 5000]
+    out["iters"] = np.array(its)
+    for it in its:
+        M.PFGST._update_ema(h, it)
+        for i, p in enumerate(teacher):
+            out[f"teacher_it{it}_{i}"] = p.detach().numpy().copy()
+    M.PFGST._init_ema_weights(h)
+    for i, p in enumerate(teacher):
+        out[f"teacher_init_{i}"] = p.detach().numpy().copy()
+    np.savez_compressed(OUT / "ema.npz", **out)
+
+
+def gen_pseudo_mix():
+    """pfgst.py:259-300 executed verbatim through the reference's own functions."""
+    D = R.dacs_transforms()
+    g = torch.Generator().manual_seed(77)
+    B, C, H, W = 2, 6, 64, 64
+    logits = teacher_logits(B, C, H, W, g)
+    gt = blocky_labels(B, H, W, C, g, min_rect=4, max_rect=32)
+    img = torch.randn((B, 3, H, W), generator=g)
+    trg = torch.randn((B, 3, H, W), generator=g)
+    out = dict(logits=logits.numpy(), gt=gt.numpy().astype(np.uint8), img=img.numpy(), trg=trg.numpy())
+    thr, top, bottom = 0.98, 2, 3
+    ema_softmax = torch.softmax(logits.detach(), dim=1)
+    pseudo_prob, pseudo_label = torch.max(ema_softmax, dim=1)
+    ps_large_p = pseudo_prob.ge(thr).long() == 1
+    ps_size = np.size(np.array(pseudo_label.cpu()))
+    pseudo_weight = torch.sum(ps_large_p).item() / ps_size
+    pseudo_weight = pseudo_weight * torch.ones(pseudo_prob.shape)
+    pseudo_weight[:, :top, :] = 0
+    pseudo_weight[:, -bottom:, :] = 0
+    gt_pixel_weight = torch.ones(pseudo_weight.shape)
+    np.random.seed(5)
+    mix_masks = D.get_class_masks(gt)
+    param = dict(mix=None, color_jitter=0.1, color_jitter_s=0.2, color_jitter_p=1.0, blur=0,
+                 mean=torch.zeros(1, 3, 1, 1), std=torch.ones(1, 3, 1, 1), denorm_type='mean_std')
+    mixed_img, mixed_lbl = [None] * B, [None] * B
+    for i in range(B):
+        param['mix'] = mix_masks[i]
+        mixed_img[i], mixed_lbl[i] = D.strong_transform(param, data=torch.stack((img[i], trg[i])),
+                                                        target=torch.stack((gt[i][0], pseudo_label[i])))
+        _, pseudo_weight[i] = D.strong_transform(param, target=torch.stack((gt_pixel_weight[i], pseudo_weight[i])))
+    out.update(pseudo_label=pseudo_label.numpy().astype(np.uint8), pseudo_prob=pseudo_prob.numpy(),
+               large=ps_large_p.numpy(), mixed_img=torch.cat(mixed_img).numpy(),
+               mixed_lbl=torch.cat(mixed_lbl).numpy().astype(np.uint8), mixed_weight=pseudo_weight.numpy(),
+               mix_masks=torch.cat(mix_masks).numpy().astype(np.uint8), thr=thr, top=top, bottom=bottom, seed=5)
+    np.savez_compressed(OUT / "pseudo_mix.npz", **out)
+
+
+def gen_pfgst_loss():
+    L = R.pfgst_loss()
+    D = R.dacs_transforms()
+    cases = {"a": dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=1),      # identity feature grid
+             "b": dict(B=3, C=33, H=48, D=16, dil=2, down=None, seed=2)}     # 2x up-sampled features
+    out = {}
+    for name, c in cases.items():
+        g = torch.Generator().manual_seed(c["seed"])
+        B, C, H = c["B"], c["C"], c["H"]
+        gt = blocky_labels(B, H, H, C, g, min_rect=4, max_rect=max(8, H // 2))
+        logits = 2.0 * torch.randn((B, C, H // 4, H // 4), generator=g)
+        x_src = torch.relu(torch.randn((B, c["D"], H // 8, H // 8), generator=g))
+        x_ema = torch.relu(torch.randn((B, c["D"], H // 8, H // 8), generator=g))
+        np.random.seed(3)
+        mix = torch.cat(D.get_class_masks(gt), 0)
+        mod = L.PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, sim_type='cosine',
+                          feat_level=None, detach_unfold=True, downscale=c["down"])
+        lt = logits.clone().requires_grad_(True)
+        xs = x_src.clone().requires_grad_(True)
+        with R.cpu_cuda_identity():
+            res = mod(dict(logits_trg=lt, logits_ema=None, gt_src=gt, x_ema=x_ema, x_src=xs, img_trg=None,
+                           mix_masks=mix))
+        sum(res[k] for k in LOSS_KEYS).backward()
+        out.update({f"{name}_gt": gt.numpy().astype(np.uint8), f"{name}_logits": logits.numpy(),
+                    f"{name}_x_src": x_src.numpy(), f"{name}_x_ema": x_ema.numpy(),
+                    f"{name}_mix": mix.numpy().astype(np.uint8),
+                    f"{name}_losses": np.array([float(res[k]) for k in LOSS_KEYS], dtype=np.float32),
+                    f"{name}_grad_x_src": xs.grad.numpy(), f"{name}_grad_logits": lt.grad.numpy(),
+                    f"{name}_density": res['vis|density_sim_feat'][1].numpy(),
+                    f"{name}_eroded": res['vis|density_sim_feat'][2].numpy(),
+                    f"{name}_cfg": np.array([c["dil"], -1 if c["down"] is None else c["down"]], dtype=np.float64)})
+    np.savez_compressed(OUT / "pfgst_loss.npz", **out)
+
+
+STEP_CFG = dict(max_iters=100, alpha=0.999, pseudo_threshold=0.6, pseudo_weight_ignore_top=2,
+                pseudo_weight_ignore_bottom=3, imnet_feature_dist_lambda=0, imnet_feature_dist_classes=None,
+                imnet_feature_dist_scale_min_ratio=None, mix='class', blur=False, color_jitter_strength=0.2,
+                color_jitter_probability=1.0, print_grad_magnitude=False, trg_loss_weight=1.,
+                use_decoded_feats=True, thre_type='all',
+                aux_losses=[dict(type='PFGSTLoss', kernel_size=3, dilation=2, top_k=3, weights=W6,
+                                 sim_type='cosine', feat_level=None, detach_unfold=True, downscale=0.5)])
+
+
+def step_batches(n_iters=3, B=2, H=128, C=6):
+    g = torch.Generator().manual_seed(0)
+    metas = [{'img_norm_cfg': {'mean': [1., 2., 3.], 'std': [1., 1., 1.]}}] * B
+    for _ in range(n_iters):
+        yield dict(img=torch.randn((B, 3, H, H), generator=g), img_metas=metas,
+                   gt_semantic_seg=blocky_labels(B, H, H, C, g, min_rect=4, max_rect=64),
+                   target_img=torch.randn((B, 3, H, H), generator=g), target_img_metas=metas,
+                   target_img_strong_aug=torch.randn((B, 3, H, H), generator=g))
+
+
+def gen_pfgst_step():
+    M = R.pfgst()
+    C = 6
+    cfg = dict(STEP_CFG)
+    cfg['model'] = {'_instance_factory': lambda: TinySegmentor(C, 16, seed=0), 'train_cfg': {}, 'test_cfg': {},
+                    'decode_head': {'num_classes': C}}
+    m = M.PFGST(**cfg)
+    opt = torch.optim.SGD(m.model.parameters(), lr=0.01)
+    random.seed(1); np.random.seed(1); torch.manual_seed(1)
+    out = {}
+    with R.cpu_cuda_identity():
+        for it, batch in enumerate(step_batches()):
+            res = m.train_step(batch, opt)
+            out[f"log_keys_{it}"] = np.array(list(res['log_vars'].keys()))
+            out[f"log_vals_{it}"] = np.array(list(res['log_vars'].values()), dtype=np.float64)
+    out["ema_params"] = torch.cat([p.detach().reshape(-1) for p in m.ema_model.parameters()]).numpy()
+    out["student_params"] = torch.cat([p.detach().reshape(-1) for p in m.model.parameters()]).numpy()
+    np.savez_compressed(OUT / "pfgst_step.npz", **out)
+
+
+if __name__ == "__main__":
+    warnings.filterwarnings("ignore")
+    assert R.available(), "reference checkout not found"
+    torch.set_num_threads(1)      # bit-stable reductions
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step):
+        fn()
+        print("wrote", fn.__name__)
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)

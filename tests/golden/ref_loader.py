@@ -57,6 +57,11 @@ _cache: dict = {}
 
 
 def dacs_transforms():
+    # color_jitter / gaussian_blur do `import kornia` before testing whether they are active;
+    # an empty stand-in lets the inactive branches (jitter_p=1.0, blur=False) run. Any real
+    # use of kornia fails loudly with AttributeError.
+    if "kornia" not in sys.modules:
+        sys.modules["kornia"] = types.ModuleType("kornia")
     if "dacs" not in _cache:
         _cache["dacs"] = _load("_pfst_ref_dacs_transforms", "rsiseg/models/utils/dacs_transforms.py")
     return _cache["dacs"]
@@ -102,6 +107,25 @@ class cpu_cuda_identity:
         return False
 
 
+def _extract_parse_losses():
+    """Compile BaseSegmentor._parse_losses straight from the reference source file
+    (rsiseg/models/segmentors/base.py:177-222) without importing its mmcv-bound module."""
+    import ast
+    from collections import OrderedDict
+    import torch
+    import torch.distributed as dist
+    src = (REF_ROOT / "rsiseg/models/segmentors/base.py").read_text()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "_parse_losses":
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"torch": torch, "dist": dist, "OrderedDict": OrderedDict}
+            exec(compile(mod, "ref:base.py:_parse_losses", "exec"), ns)
+            return ns["_parse_losses"]
+    raise RuntimeError("_parse_losses not found in the reference")
+
+
 def pfgst():
     """-> module rsiseg/models/uda/pfgst.py with class PFGST (methods usable unbound on a
     duck-typed object; the segmentor passes are supplied by the caller)."""
@@ -138,8 +162,16 @@ def pfgst():
             build_loss=lambda cfg: mloss.PFGSTLoss(**{k: v for k, v in cfg.items() if k != "type"}))
         _stub("rsiseg")
         _stub("rsiseg.core", add_prefix=add_prefix)
+        class BaseSegmentor(nn.Module):
+            """stand-in for rsiseg/models/segmentors/base.py (needs mmcv.runner); only
+            _parse_losses is used by PFGST and it is compiled from the reference source."""
+            _parse_losses = staticmethod(_extract_parse_losses())
+
+            def forward(self, *args, return_loss=True, **kwargs):  # base.py:101-115 (auto_fp16 no-op)
+                return self.forward_train(*args, **kwargs)
+
         _stub("rsiseg.models", UDA=uda_reg, build_segmentor=lambda cfg: cfg["_instance_factory"](),
-              builder=builder, BaseSegmentor=nn.Module)
+              builder=builder, BaseSegmentor=BaseSegmentor)
         _stub("rsiseg.models.uda")
         _stub("rsiseg.models.utils")
         sys.modules["rsiseg.models.utils.dacs_transforms"] = dacs

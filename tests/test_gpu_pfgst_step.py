@@ -1,0 +1,92 @@
+"""Whole-step integration: the PFGST drop-in (pfst_b200.uda.PFGST) against three
+train_step iterations of the REFERENCE PFGST on the same tiny segmentor and batches
+(golden: tests/golden/pfgst_step.npz). The two runs differ by cuDNN-vs-CPU convolution
+rounding in the segmentor passes, so scalars are compared at 2e-3 relative here; the
+exact parity of every hot-path op is covered by the per-op tests."""
+import random
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from pfst_b200.uda import PFGST
+from pfst_b200 import ops
+from tests.fake_segmentor import TinySegmentor
+from tests.golden.make_golden import STEP_CFG, step_batches
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+
+
+def _build(cuda, **extra):
+    cfg = dict(STEP_CFG)
+    cfg.update(extra)
+    cfg['model'] = lambda: TinySegmentor(6, 16, seed=0)
+    return PFGST(**cfg).to(cuda)
+
+
+def _to(batch, dev):
+    return {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+def test_three_train_steps_match_reference(cuda):
+    z = np.load(G / "pfgst_step.npz")
+    m = _build(cuda)
+    opt = torch.optim.SGD(m.model.parameters(), lr=0.01)
+    random.seed(1); np.random.seed(1); torch.manual_seed(1)
+    for it, batch in enumerate(step_batches()):
+        out = m.train_step(_to(batch, cuda), opt)
+        keys = list(out['log_vars'].keys())
+        assert keys == list(z[f"log_keys_{it}"]), (keys, z[f"log_keys_{it}"])
+        got = np.array(list(out['log_vars'].values()))
+        want = z[f"log_vals_{it}"]
+        assert np.all(np.abs(got - want) <= 2e-3 * np.abs(want) + 2e-4), (it, dict(zip(keys, zip(got, want))))
+        assert out['num_samples'] == 2
+        assert {'vis|density_sim_feat', 'vis|seg_mask_src', 'vis|seg_mask_mix'} <= set(out['states'])
+    ema = torch.cat([p.detach().reshape(-1) for p in m.ema_model.parameters()]).cpu().numpy()
+    stu = torch.cat([p.detach().reshape(-1) for p in m.model.parameters()]).cpu().numpy()
+    assert np.abs(stu - z["student_params"]).max() <= 2e-3
+    assert np.abs(ema - z["ema_params"]).max() <= 2e-3
+    assert m.local_iter == 3
+    assert all(not p.requires_grad for p in m.get_ema_model().parameters())
+
+
+def test_ema_of_the_module_is_bit_exact_given_identical_students(cuda):
+    from oracle import ema as oema
+    m = _build(cuda)
+    m._init_ema_weights()
+    assert all(torch.equal(a, b) for a, b in zip(m.get_ema_model().parameters(), m.get_model().parameters()))
+    teacher = [p.detach().cpu().clone() for p in m.get_ema_model().parameters()]
+    with torch.no_grad():
+        for p in m.get_model().parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    student = [p.detach().cpu().clone() for p in m.get_model().parameters()]
+    for it in (1, 2, 3, 50):
+        m._update_ema(it)
+        oema.ema_update(teacher, student, it, 0.999)
+        for a, b in zip(m.get_ema_model().parameters(), teacher):
+            assert torch.equal(a.detach().cpu(), b)
+
+
+def test_kornia_branches_fail_loudly_or_skip(cuda):
+    batch = _to(next(iter(step_batches(1))), cuda)
+    m = _build(cuda, blur=True, color_jitter_probability=0.0)
+    with pytest.raises(ops.PfstError):
+        for _ in range(8):                      # blur is active with probability 1/2 per draw
+            m.forward_train(**batch)
+    m = _build(cuda, blur=True, color_jitter_probability=0.0, kornia_aug='skip')
+    with pytest.warns(UserWarning):
+        m.forward_train(**batch)
+
+
+def test_part_threshold_and_prototype_extension(cuda):
+    batch = _to(next(iter(step_batches(1))), cuda)
+    m = _build(cuda, thre_type='part', prototypes=dict(weight=0.1, conf_threshold=0.5),
+               pseudo_threshold_per_class=[0.5, 0.6, 0.7, 0.5, 0.6, 0.7])
+    random.seed(0); np.random.seed(0)
+    log_vars, _ = m.forward_train(**batch)
+    assert 'loss_proto_dist' in log_vars and np.isfinite(log_vars['loss_proto_dist'])
+    log_vars, _ = m.forward_train(**batch)
+    assert np.isfinite(log_vars['loss'])
+    assert int(m.proto_bank.seen.sum()) >= 1 and m.proto_bank.iter == 2

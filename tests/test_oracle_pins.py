@@ -1,0 +1,148 @@
+"""Pins the CPU oracle: (1) against the committed golden fixtures, which were produced by
+the REFERENCE code itself (tests/golden/make_golden.py); (2) when the reference checkout
+is present (build container), against the reference modules loaded by path, live.
+Runs without a GPU."""
+import random
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ema as oema, metrics as om, mixing as omix, pfgst_loss as OL, pseudo as opl
+from tests.golden import ref_loader as R
+
+G = Path(__file__).resolve().parent / "golden"
+needs_ref = pytest.mark.skipif(not R.available(), reason="reference checkout not present")
+
+
+def load(name):
+    return np.load(G / name, allow_pickle=False)
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_metrics_oracle_vs_golden():
+    z = load("metrics.npz")
+    C = int(z["C"])
+    ret = om.eval_metrics(z["pred"], z["label"], C, 255, metrics=["mIoU", "mDice", "mFscore"])
+    for k, v in ret.items():
+        assert np.array_equal(np.asarray(v), z["all_" + k], equal_nan=True), k
+    per = [om.areas(z["pred"][i], z["label"][i], C, 255) for i in range(10)]
+    assert np.array_equal(np.stack([np.stack([a.numpy() for a in p]) for p in per]), z["per_image"])
+    assert np.array_equal(om.metrics_from_areas(*om.pre_eval_sum(per), ["mIoU"])["IoU"], z["pre_eval_IoU"])
+    a = om.areas(z["lm_pred"], z["lm_label"], 6, 255, {7: 0, 6: 255}, True)
+    assert np.array_equal(np.stack([t.numpy() for t in a]), z["lm_areas"])
+    # and the reference's own golden relation: histc areas == bincount confusion matrix
+    tot = sum(om.confusion(z["pred"][i], z["label"][i], C, 255) for i in range(10)).astype(np.float64)
+    d = np.diag(tot)
+    assert np.allclose(z["all_IoU"], d / (tot.sum(1) + tot.sum(0) - d))
+    assert z["all_aAcc"] == d.sum() / tot.sum()
+
+
+def test_ema_oracle_vs_golden():
+    z = load("ema.npz")
+    n = 6
+    student = [torch.from_numpy(z[f"student_{i}"].copy()) for i in range(n)]
+    teacher = [torch.from_numpy(z[f"teacher0_{i}"].copy()) for i in range(n)]
+    for it in z["iters"]:
+        oema.ema_update(teacher, student, int(it), 0.999)
+        for i in range(n):
+            assert np.array_equal(teacher[i].numpy(), z[f"teacher_it{it}_{i}"]), (it, i)
+    oema.ema_init(teacher, student)
+    for i in range(n):
+        assert np.array_equal(teacher[i].numpy(), z[f"teacher_init_{i}"])
+
+
+def test_pseudo_and_mix_oracle_vs_golden():
+    z = load("pseudo_mix.npz")
+    logits = torch.from_numpy(z["logits"])
+    gt = torch.from_numpy(z["gt"]).long()
+    img, trg = torch.from_numpy(z["img"]), torch.from_numpy(z["trg"])
+    label, prob, large = opl.pseudo_label(logits, float(z["thr"]))
+    assert np.array_equal(label.numpy(), z["pseudo_label"])
+    assert np.array_equal(prob.numpy(), z["pseudo_prob"])
+    assert np.array_equal(large.numpy(), z["large"])
+    w = opl.pseudo_weight(large, "all", int(z["top"]), int(z["bottom"]))
+    np.random.seed(int(z["seed"]))
+    masks = omix.class_masks(gt)
+    mi, ml, mw, mm = omix.mix_batch(img, trg, gt, label, w, masks)
+    assert np.array_equal(mm.numpy(), z["mix_masks"])
+    assert np.array_equal(ml.numpy(), z["mixed_lbl"])
+    assert np.array_equal(mi.numpy(), z["mixed_img"])
+    assert np.array_equal(mw.numpy(), z["mixed_weight"])
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_pfgst_loss_oracle_vs_golden(name):
+    z = load("pfgst_loss.npz")
+    dil, down = z[f"{name}_cfg"]
+    lt = torch.from_numpy(z[f"{name}_logits"]).requires_grad_(True)
+    xs = torch.from_numpy(z[f"{name}_x_src"]).requires_grad_(True)
+    res = OL.pfgst_loss(dict(logits_trg=lt, gt_src=torch.from_numpy(z[f"{name}_gt"]).long(),
+                             x_ema=torch.from_numpy(z[f"{name}_x_ema"]), x_src=xs, img_trg=None,
+                             mix_masks=torch.from_numpy(z[f"{name}_mix"]).long()),
+                        OL.LossCfg(dilation=int(dil), downscale=None if down < 0 else float(down)))
+    sum(res[k] for k in OL.LOSS_KEYS).backward()
+    got = np.array([float(res[k].detach()) for k in OL.LOSS_KEYS], dtype=np.float32)
+    assert np.allclose(got, z[f"{name}_losses"], rtol=2e-6, atol=1e-8)   # thread-count dependent sums
+    assert np.allclose(xs.grad.numpy(), z[f"{name}_grad_x_src"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(lt.grad.numpy(), z[f"{name}_grad_logits"], rtol=1e-5, atol=1e-9)
+    assert np.array_equal(res['vis|density_sim_feat'][2].numpy(), z[f"{name}_eroded"])
+    assert np.allclose(res['vis|density_sim_feat'][1].numpy(), z[f"{name}_density"], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ live reference
+@needs_ref
+def test_reference_golden_test_retargeted():
+    """The reference's only golden test (tests/test_metrics.py:86-143): eval_metrics must equal
+    the bincount confusion-matrix formulas. Checked for the reference module AND the oracle."""
+    M = R.metrics()
+    rs = np.random.RandomState(123)
+    C = 19
+    pred, label = rs.randint(0, C, (10, 30, 30)), rs.randint(0, C, (10, 30, 30))
+    label[:, 2, 5:10] = 255
+    tot = sum(om.confusion(pred[i], label[i], C, 255) for i in range(10)).astype(np.float64)
+    d = np.diag(tot)
+    for impl in (M.eval_metrics, om.eval_metrics):
+        ret = impl(pred, label, C, 255, metrics=["mIoU", "mDice"])
+        assert ret["aAcc"] == d.sum() / tot.sum()
+        assert np.allclose(ret["Acc"], d / tot.sum(1))
+        assert np.allclose(ret["IoU"], d / (tot.sum(1) + tot.sum(0) - d))
+        assert np.allclose(ret["Dice"], 2 * d / (tot.sum(1) + tot.sum(0)))
+    r59 = M.eval_metrics(np.array([np.repeat(31, 59)]), np.array([np.arange(59)]), 59, 255, metrics='mIoU')
+    o59 = om.eval_metrics(np.array([np.repeat(31, 59)]), np.array([np.arange(59)]), 59, 255, metrics='mIoU')
+    assert not np.any(np.isnan(r59["IoU"])) and np.array_equal(r59["IoU"], o59["IoU"])
+
+
+@needs_ref
+def test_oracle_bitwise_equals_reference_live():
+    from pfst_b200.synthetic import WORKLOADS, step_inputs
+    warnings.filterwarnings("ignore")
+    D, L = R.dacs_transforms(), R.pfgst_loss()
+    wl = WORKLOADS["tiny"]
+    inp = step_inputs(wl, seed=99)
+    np.random.seed(11)
+    ref_masks = D.get_class_masks(inp["gt"])
+    np.random.seed(11)
+    ora_masks = omix.class_masks(inp["gt"])
+    assert all(torch.equal(a, b) for a, b in zip(ref_masks, ora_masks))
+    mix = torch.cat(ref_masks, 0)
+    W6 = {'src_pos': 0.1, 'src_neg': 0.1, 'sim_pos': 0.1, 'sim_neg': 0.1, 'src_pos_std': 0.1, 'src_neg_std': 0.1}
+    mod = L.PFGSTLoss(top_k=3, dilation=2, kernel_size=3, weights=W6, sim_type='cosine', feat_level=None,
+                      detach_unfold=True, downscale=0.5)
+
+    def t():
+        return dict(logits_trg=inp['logits_trg'].clone().requires_grad_(True), logits_ema=None, gt_src=inp['gt'],
+                    x_ema=inp['x_ema'], x_src=inp['x_src'].clone().requires_grad_(True), img_trg=None, mix_masks=mix)
+
+    t1, t2 = t(), t()
+    with R.cpu_cuda_identity():
+        a = mod(t1)
+    b = OL.pfgst_loss(t2, OL.LossCfg())
+    sum(a[k] for k in OL.LOSS_KEYS).backward()
+    sum(b[k] for k in OL.LOSS_KEYS).backward()
+    for k in OL.LOSS_KEYS:
+        assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
+    assert torch.equal(t1['x_src'].grad, t2['x_src'].grad)
+    assert torch.equal(t1['logits_trg'].grad, t2['logits_trg'].grad)
