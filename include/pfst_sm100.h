@@ -229,12 +229,13 @@ int pfst_proto_dist_fwd(const float* feats, int64_t B, int32_t D, int32_t h, int
                         const float* mu, const uint8_t* seen, int32_t C, float* dist,
                         double* acc, float* loss, void* stream);
 
-/* grad_feats[b,d,n] = grad_loss * (f - mu[label]) / (dist * n_valid), 0 where invalid. */
+/* grad_feats[b,d,n] (+)= grad_loss * (f - mu[label]) / (dist * n_valid), 0 where
+ * invalid; accumulate != 0 adds into grad_feats (e.g. on top of pfst_neigh_grad).   */
 int pfst_proto_dist_bwd(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
                         const int64_t* labels, int32_t lab_h, int32_t lab_w,
                         const float* mu, const uint8_t* seen, int32_t C,
                         const float* dist, const double* acc, const float* grad_loss,
-                        float* grad_feats, void* stream);
+                        float* grad_feats, int32_t accumulate, void* stream);
 
 /* out[b,c,n] = ||feats[b,:,n] - mu[c]||_2 for every class: (B,C,h,w).               */
 int pfst_proto_dist_all(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,

@@ -149,7 +149,7 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
                   const int64_t* __restrict__ labels, int lab_h, int lab_w, const float* __restrict__ mu,
                   const uint8_t* __restrict__ seen, int C, float* __restrict__ dist, double* __restrict__ acc,
                   float* __restrict__ loss, const float* __restrict__ grad_loss, float* __restrict__ grad,
-                  unsigned* __restrict__ done_counter) {
+                  unsigned* __restrict__ done_counter, int accumulate) {
   extern __shared__ __align__(16) unsigned char pd_smem[];
   float* mu_s = reinterpret_cast<float*>(pd_smem);                 // [C][D+1]  (+1: bank skew)
   float* part = mu_s + (size_t)C * (D + 1);                        // [warps][128]
@@ -241,9 +241,19 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] = (p0 + lane * 4 + i < hw) ? __ldg(src + (int64_t)d * hw + i) : 0.f;
         }
-        float o[4];
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (accumulate) {   // grad += ... : the PFGST loss gradient is already in the buffer
+          if (vec) {
+            const float4 t = *reinterpret_cast<const float4*>(dst + (int64_t)d * hw);
+            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+          } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = coef[i] * (v[i] - mu_s[lab[i] * (D + 1) + d]);
+            for (int i = 0; i < 4; ++i)
+              if (p0 + lane * 4 + i < hw) o[i] = dst[(int64_t)d * hw + i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fmaf(coef[i], v[i] - mu_s[lab[i] * (D + 1) + d], o[i]);
         if (vec) {
           __stcs(reinterpret_cast<float4*>(dst + (int64_t)d * hw), make_float4(o[0], o[1], o[2], o[3]));
         } else {
@@ -327,7 +337,7 @@ int pfst_proto_finalize(const float* packed, int32_t C, int32_t D, const float* 
 static int proto_dist_common(bool bwd, const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
                              const int64_t* labels, int32_t lab_h, int32_t lab_w, const float* mu,
                              const uint8_t* seen, int32_t C, float* dist, double* acc, float* loss,
-                             const float* grad_loss, float* grad, cudaStream_t s) {
+                             const float* grad_loss, float* grad, int accumulate, cudaStream_t s) {
   if (!feats || !labels || !mu || !dist || !acc || B < 0 || D < 1 || h < 1 || w < 1 || C < 1)
     return PFST_ERR_INVALID_ARG;
   if (C > pfst::kPrMaxC) return PFST_ERR_UNSUPPORTED;
@@ -343,13 +353,13 @@ static int proto_dist_common(bool bwd, const float* feats, int64_t B, int32_t D,
     PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_proto_dist_fwd/attr");
     k<<<(unsigned)grid, pfst::kPrThreads, smem, s>>>(feats, (int)B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist,
                                                      acc, loss, nullptr, nullptr,
-                                                     reinterpret_cast<unsigned*>(acc + 3));
+                                                     reinterpret_cast<unsigned*>(acc + 3), 0);
   } else {
     if (!grad_loss || !grad) return PFST_ERR_INVALID_ARG;
     auto k = pfst::proto_dist_kernel<true>;
     PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_proto_dist_bwd/attr");
     k<<<(unsigned)grid, pfst::kPrThreads, smem, s>>>(feats, (int)B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist,
-                                                     acc, nullptr, grad_loss, grad, nullptr);
+                                                     acc, nullptr, grad_loss, grad, nullptr, accumulate);
   }
   PFST_CHECK_LAUNCH(bwd ? "pfst_proto_dist_bwd" : "pfst_proto_dist_fwd");
   return PFST_OK;
@@ -359,15 +369,15 @@ int pfst_proto_dist_fwd(const float* feats, int64_t B, int32_t D, int32_t h, int
                         const int64_t* labels, int32_t lab_h, int32_t lab_w, const float* mu,
                         const uint8_t* seen, int32_t C, float* dist, double* acc, float* loss, void* stream) {
   return proto_dist_common(false, feats, B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist, acc, loss, nullptr,
-                           nullptr, static_cast<cudaStream_t>(stream));
+                           nullptr, 0, static_cast<cudaStream_t>(stream));
 }
 
 int pfst_proto_dist_bwd(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
                         const int64_t* labels, int32_t lab_h, int32_t lab_w, const float* mu,
                         const uint8_t* seen, int32_t C, const float* dist, const double* acc,
-                        const float* grad_loss, float* grad_feats, void* stream) {
+                        const float* grad_loss, float* grad_feats, int32_t accumulate, void* stream) {
   return proto_dist_common(true, feats, B, D, h, w, labels, lab_h, lab_w, mu, seen, C, const_cast<float*>(dist),
-                           const_cast<double*>(acc), nullptr, grad_loss, grad_feats,
+                           const_cast<double*>(acc), nullptr, grad_loss, grad_feats, accumulate,
                            static_cast<cudaStream_t>(stream));
 }
 

@@ -103,7 +103,7 @@ class _ProtoDistFn(torch.autograd.Function):
         g = grad_out.reshape(1).contiguous().float()
         _lib.call("pfst_proto_dist_bwd", feats.data_ptr(), B, D, h, w, labels.data_ptr(), labels.shape[-2],
                   labels.shape[-1], mu.data_ptr(), None if seen is None else seen.data_ptr(), mu.shape[0],
-                  dist.data_ptr(), acc.data_ptr(), g.data_ptr(), grad.data_ptr(), ops._stream())
+                  dist.data_ptr(), acc.data_ptr(), g.data_ptr(), grad.data_ptr(), 0, ops._stream())
         return grad, None, None, None
 
 
