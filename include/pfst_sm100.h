@@ -165,6 +165,10 @@ int pfst_neigh_dots(const float* x_a, const float* x_b, int64_t B, int32_t D, in
 int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int32_t h,
                     int32_t w, int32_t dilation, float* grad_x, void* stream);
 
+/* Bytes of the `workspace` the two entry points below share (per-pixel maps written
+ * by the forward's prep kernel and re-read by the backward). Host only.             */
+int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up);
+
 /* dots: output of pfst_neigh_dots(x_ema, x_src) on the (fh,fw) feature grid with
  * dilation `dilation/up`; the loss grid is (fh*up, fw*up) (features nearest-
  * upsampled by the integer factor `up`, pfgst_loss.py:58-59).
@@ -173,7 +177,8 @@ int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int
  * gt, mix: (B,1,gt_h,gt_w) int64 source labels / ClassMix masks, nearest-sampled
  * to the loss grid (:62-67). weights6 (host): src_pos, src_neg, src_pos_std,
  * src_neg_std, sim_pos, sim_neg (:110-135).
- * stats: device double[16] workspace (zeroed here; kept for the backward).
+ * workspace: device buffer of pfst_pfgst_loss_ws_bytes() bytes, 16-byte aligned, kept
+ * (with stats) for the backward. stats: device double[16] (zeroed here).
  * losses: device float[6] = loss_src_pos_mean, loss_src_neg_mean, loss_src_pos_std,
  * loss_src_neg_std, loss_sim_pos, loss_sim_neg. density (nullable): (B,fh*up,fw*up)
  * = 1 - mean_k cos_ema ('vis|density_sim_feat', :136); eroded (nullable): uint8 of
@@ -183,8 +188,8 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         int32_t lh, int32_t lw, float lscale_h, float lscale_w,
                         const int64_t* gt, const int64_t* mix, int32_t gt_h,
                         int32_t gt_w, int32_t dilation, int32_t top_k,
-                        const float* weights6_host, double* stats, float* losses,
-                        float* density, uint8_t* eroded, void* stream);
+                        const float* weights6_host, void* workspace, double* stats,
+                        float* losses, float* density, uint8_t* eroded, void* stream);
 
 /* grad_losses: device float[6], upstream gradient of each loss. coef: (B,9,fh,fw)
  * for pfst_neigh_grad(x_src, dilation/up). grad_logits (nullable): (B,C,lh,lw),
@@ -194,9 +199,9 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         int32_t lh, int32_t lw, float lscale_h, float lscale_w,
                         const int64_t* gt, const int64_t* mix, int32_t gt_h,
                         int32_t gt_w, int32_t dilation, int32_t top_k,
-                        const float* weights6_host, const double* stats,
-                        const float* grad_losses, float* coef, float* grad_logits,
-                        void* stream);
+                        const float* weights6_host, const void* workspace,
+                        const double* stats, const float* grad_losses, float* coef,
+                        float* grad_logits, void* stream);
 
 /* ---- P1-P3: class prototypes (north_star extension; no reference code) ----------
  * Anchor: PFGST.masked_feat_dist, rsiseg/models/uda/pfgst.py:168-177. Labels are

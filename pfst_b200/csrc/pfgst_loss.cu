@@ -19,7 +19,7 @@
 
 namespace pfst {
 
-constexpr int kLossThreads = 128;
+constexpr int kLossThreads = 64;
 constexpr int kMaxC = 64;   // classes held in registers per pixel
 
 struct LossParams {
@@ -38,11 +38,66 @@ struct LossParams {
   int dil;                    // dilation on the loss grid (feature-grid dilation = dil / up)
   int top_k;
   float w_src_pos, w_src_neg, w_src_pos_std, w_src_neg_std, w_sim_pos, w_sim_neg;
+  // workspace written by the prep kernel, read by the statistics / backward kernels
+  float* dm;                  // (2, B, 5, fh, fw)  dots summed over the channel splits
+  float* invn;                // (2, B, fh, fw)     1 / max(|x|, 1e-8)
+  float* prob;                // (B, C, gh, gw)     softmax of the resampled logits
+  uint8_t* lab;               // (B, gh, gw)        resampled source label (0..255)
+  uint8_t* flags;             // (B, gh, gw)        bit0 = gt != 255, bit1 = target pixel (mix mask == 0)
 };
 
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
   const int s = (int)floorf((float)dst * scale);
   return s < in - 1 ? s : in - 1;
+}
+
+__host__ __device__ inline size_t ws_floats(int B, int C, int fh, int fw, int up) {
+  const size_t fplane = (size_t)fh * fw, gplane = fplane * up * up;
+  return (size_t)2 * B * 5 * fplane + (size_t)2 * B * fplane + (size_t)B * C * gplane;
+}
+
+// ---- prep: everything that is per-pixel (not per-neighbourhood), computed once --------
+__global__ void __launch_bounds__(kLossThreads)
+pfgst_loss_prep_kernel(const LossParams P) {
+  const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
+  const int64_t nfeat = (int64_t)2 * P.B * fplane, nloss = (int64_t)P.B * gplane;
+  const int64_t i = (int64_t)blockIdx.x * kLossThreads + threadIdx.x;
+  if (i < nfeat) {
+    // (tensor t, image b, pixel r): merge the channel-split partial maps in a fixed order
+    const int64_t tb = i / fplane, r = i - tb * fplane;
+    const int64_t split_stride = (int64_t)2 * P.B * 5 * fplane;
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float* src = P.dots + (tb * 5 + k) * fplane + r;
+      float a = 0.f;
+      for (int sp = 0; sp < P.ksplit; ++sp) a += src[sp * split_stride];
+      v[k] = a;
+      P.dm[(tb * 5 + k) * fplane + r] = a;
+    }
+    P.invn[i] = 1.f / fmaxf(sqrtf(v[0]), 1e-8f);
+  }
+  if (i < nloss) {
+    const int b = (int)(i / gplane);
+    const int r = (int)(i - (int64_t)b * gplane);
+    const int y = r / P.gw, x = r - y * P.gw;
+    const int sy = nearest_src(y, P.gscale_h, P.gt_h), sx = nearest_src(x, P.gscale_w, P.gt_w);
+    const int64_t go = ((int64_t)b * P.gt_h + sy) * P.gt_w + sx;
+    const int64_t g = P.gt[go];
+    P.lab[i] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+    P.flags[i] = (uint8_t)((g != 255 ? 1 : 0) | (P.mix[go] <= 0 ? 2 : 0));   // (1 - mix) > 0.5
+    // softmax of the nearest-resampled logits (pfgst_loss.py:57, 145)
+    const int ly = nearest_src(y, P.lscale_h, P.lh), lx = nearest_src(x, P.lscale_w, P.lw);
+    const float* z = P.logits + ((int64_t)b * P.C * P.lh + ly) * P.lw + lx;
+    const int64_t lplane = (int64_t)P.lh * P.lw;
+    float m = -INFINITY;
+    for (int c = 0; c < P.C; ++c) m = fmaxf(m, z[c * lplane]);
+    float s = 0.f;
+    for (int c = 0; c < P.C; ++c) s += expf(z[c * lplane] - m);
+    const float inv = 1.f / s;
+    float* po = P.prob + (int64_t)b * P.C * gplane + r;
+    for (int c = 0; c < P.C; ++c) po[c * gplane] = expf(z[c * lplane] - m) * inv;
+  }
 }
 
 // Everything one loss-grid pixel needs from its 3x3 dilated neighbourhood.
@@ -59,28 +114,20 @@ struct PixelNb {
   bool eroded;
 };
 
-__device__ __forceinline__ float dots_at(const LossParams& P, int t, int b, int k, int fy, int fx) {
-  const int64_t plane = (int64_t)P.fh * P.fw;
-  const int64_t split_stride = (int64_t)2 * P.B * 5 * plane;
-  const float* p = P.dots + (((int64_t)t * P.B + b) * 5 + k) * plane + (int64_t)fy * P.fw + fx;
-  float v = 0.f;
-  for (int s = 0; s < P.ksplit; ++s) v += p[s * split_stride];   // fixed order: deterministic
-  return v;
-}
-
-__device__ __forceinline__ int64_t label_at(const LossParams& P, const int64_t* map, int b, int y, int x) {
-  const int sy = nearest_src(y, P.gscale_h, P.gt_h), sx = nearest_src(x, P.gscale_w, P.gt_w);
-  return map[((int64_t)b * P.gt_h + sy) * P.gt_w + sx];
-}
-
 __device__ __forceinline__ void load_pixel(const LossParams& P, int b, int y, int x, PixelNb& o) {
-  const float eps = 1e-8f;
+  const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
   const int fy = y / P.up, fx = x / P.up, fd = P.dil / P.up;
-  float n2e = dots_at(P, 0, b, 0, fy, fx), n2s = dots_at(P, 1, b, 0, fy, fx);
-  const float ne = fmaxf(sqrtf(n2e), eps), ns = fmaxf(sqrtf(n2s), eps);
-  o.inv_n_src = 1.f / ns;
-  const int64_t g0 = label_at(P, P.gt, b, y, x);
-  o.valid_src = g0 != 255;
+  const int64_t fn = (int64_t)fy * P.fw + fx;
+  const float* dme = P.dm + ((int64_t)(0 * P.B + b) * 5) * fplane;
+  const float* dms = P.dm + ((int64_t)(1 * P.B + b) * 5) * fplane;
+  const float* ine = P.invn + (int64_t)(0 * P.B + b) * fplane;
+  const float* ins = P.invn + (int64_t)(1 * P.B + b) * fplane;
+  const uint8_t* lab = P.lab + (int64_t)b * gplane;
+  const uint8_t* flg = P.flags + (int64_t)b * gplane;
+  const float inv_ne = ine[fn], inv_ns = ins[fn];
+  o.inv_n_src = inv_ns;
+  const int g0 = lab[(int64_t)y * P.gw + x];
+  o.valid_src = (flg[(int64_t)y * P.gw + x] & 1) != 0;
   bool er = true;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -89,27 +136,23 @@ __device__ __forceinline__ void load_pixel(const LossParams& P, int b, int y, in
     const bool in = yy >= 0 && yy < P.gh && xx >= 0 && xx < P.gw;
     o.inb[k] = in;
     float se = 0.f, ss = 0.f, invm = 0.f;
-    int64_t gk = 0;        // zero padding of unfold(gt.float())
+    int gk = 0;        // zero padding of unfold(gt.float())
     bool trg = false, nbv = false;
     if (in) {
-      const int my = fy + oy * fd, mx = fx + ox * fd;
-      float de, ds, m2e, m2s;
-      if (k == 4) {
-        de = n2e; ds = n2s; m2e = n2e; m2s = n2s;
-      } else {
-        m2e = dots_at(P, 0, b, 0, my, mx);
-        m2s = dots_at(P, 1, b, 0, my, mx);
-        // forward taps (k > 4) are stored at n, backward taps at the neighbour (symmetry)
-        if (k > 4) { de = dots_at(P, 0, b, k - 4, fy, fx); ds = dots_at(P, 1, b, k - 4, fy, fx); }
-        else       { de = dots_at(P, 0, b, 4 - k, my, mx); ds = dots_at(P, 1, b, 4 - k, my, mx); }
-      }
-      const float me = fmaxf(sqrtf(m2e), eps), ms = fmaxf(sqrtf(m2s), eps);
-      se = de / (ne * me);
-      ss = ds / (ns * ms);
-      invm = 1.f / ms;
-      gk = label_at(P, P.gt, b, yy, xx);
-      nbv = gk != 255;
-      trg = label_at(P, P.mix, b, yy, xx) <= 0;   // (1 - mix) > 0.5
+      const int64_t fm = (int64_t)(fy + oy * fd) * P.fw + (fx + ox * fd);
+      float de, ds;
+      if (k == 4)      { de = dme[fn]; ds = dms[fn]; }
+      // forward taps (k > 4) are stored at n, backward taps at the neighbour (symmetry)
+      else if (k > 4)  { de = dme[(k - 4) * fplane + fn]; ds = dms[(k - 4) * fplane + fn]; }
+      else             { de = dme[(4 - k) * fplane + fm]; ds = dms[(4 - k) * fplane + fm]; }
+      invm = ins[fm];
+      se = de * (inv_ne * ine[fm]);
+      ss = ds * (inv_ns * invm);
+      const int64_t gm = (int64_t)yy * P.gw + xx;
+      gk = lab[gm];
+      const unsigned f = flg[gm];
+      nbv = (f & 1u) != 0;
+      trg = (f & 2u) != 0;
     }
     o.s_ema[k] = se;
     o.s_src[k] = ss;
@@ -122,17 +165,11 @@ __device__ __forceinline__ void load_pixel(const LossParams& P, int b, int y, in
   o.in_mk = er && o.valid_src;
 }
 
-// softmax of the (nearest-resampled) logits at loss-grid pixel (y,x); returns false if outside
+// softmax probabilities of loss-grid pixel (y,x), from the prep map
 __device__ __forceinline__ void softmax_at(const LossParams& P, int b, int y, int x, float* p) {
-  const int sy = nearest_src(y, P.lscale_h, P.lh), sx = nearest_src(x, P.lscale_w, P.lw);
-  const float* z = P.logits + ((int64_t)b * P.C * P.lh + sy) * P.lw + sx;
-  const int64_t plane = (int64_t)P.lh * P.lw;
-  float m = -INFINITY;
-  for (int c = 0; c < P.C; ++c) { p[c] = z[c * plane]; m = fmaxf(m, p[c]); }
-  float s = 0.f;
-  for (int c = 0; c < P.C; ++c) { p[c] = expf(p[c] - m); s += p[c]; }
-  const float inv = 1.f / s;
-  for (int c = 0; c < P.C; ++c) p[c] *= inv;
+  const int64_t gplane = (int64_t)P.gh * P.gw;
+  const float* src = P.prob + (int64_t)b * P.C * gplane + (int64_t)y * P.gw + x;
+  for (int c = 0; c < P.C; ++c) p[c] = src[c * gplane];
 }
 
 // rank of tap k among the nine similarities: number of taps strictly "before" it
@@ -340,8 +377,8 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
 
 static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, int fh, int fw, int up,
                        const float* logits, int C, int lh, int lw, float lsh, float lsw, const int64_t* gt,
-                       const int64_t* mix, int gt_h, int gt_w, int dil, int top_k, const float* w6) {
-  if (!dots || !logits || !gt || !mix || !w6) return PFST_ERR_INVALID_ARG;
+                       const int64_t* mix, int gt_h, int gt_w, int dil, int top_k, const float* w6, void* ws) {
+  if (!dots || !logits || !gt || !mix || !w6 || !ws) return PFST_ERR_INVALID_ARG;
   if (B < 0 || B > 0x7fffffff || fh < 1 || fw < 1 || up < 1 || C < 1 || lh < 1 || lw < 1 || gt_h < 1 || gt_w < 1)
     return PFST_ERR_INVALID_ARG;
   if (C > kMaxC) return PFST_ERR_UNSUPPORTED;
@@ -355,6 +392,12 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
   P.dil = dil; P.top_k = top_k;
   P.w_src_pos = w6[0]; P.w_src_neg = w6[1]; P.w_src_pos_std = w6[2]; P.w_src_neg_std = w6[3];
   P.w_sim_pos = w6[4]; P.w_sim_neg = w6[5];
+  const size_t fplane = (size_t)fh * fw, gplane = (size_t)P.gh * P.gw;
+  P.dm = static_cast<float*>(ws);
+  P.invn = P.dm + (size_t)2 * B * 5 * fplane;
+  P.prob = P.invn + (size_t)2 * B * fplane;
+  P.lab = reinterpret_cast<uint8_t*>(P.prob + (size_t)B * C * gplane);
+  P.flags = P.lab + (size_t)B * gplane;
   return PFST_OK;
 }
 
@@ -362,22 +405,36 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
 
 extern "C" {
 
+int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up) {
+  if (B < 0 || C < 1 || fh < 1 || fw < 1 || up < 1) return 0;
+  const size_t gplane = (size_t)fh * fw * up * up;
+  return (int64_t)(pfst::ws_floats((int)B, C, fh, fw, up) * sizeof(float) + 2 * (size_t)B * gplane + 16);
+}
+
 int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
                         const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
                         float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
-                        int32_t dilation, int32_t top_k, const float* weights6_host, double* stats,
-                        float* losses, float* density, uint8_t* eroded, void* stream) {
+                        int32_t dilation, int32_t top_k, const float* weights6_host, void* workspace,
+                        double* stats, float* losses, float* density, uint8_t* eroded, void* stream) {
   pfst::LossParams P;
   const int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
-                                   mix, gt_h, gt_w, dilation, top_k, weights6_host);
+                                   mix, gt_h, gt_w, dilation, top_k, weights6_host, workspace);
   if (rc != PFST_OK) return rc;
   if (!stats || !losses) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // stats[0..8] fp64 sums, stats[15] doubles as the block-completion counter
   PFST_CUDA_TRY(cudaMemsetAsync(stats, 0, 16 * sizeof(double), s), "pfst_pfgst_loss_fwd/memset");
   const int64_t total = (int64_t)P.B * P.gh * P.gw;
+  {
+    const int64_t nfeat = (int64_t)2 * P.B * fh * fw;
+    const int64_t n = nfeat > total ? nfeat : total;
+    if (n == 0) return PFST_OK;
+    pfst::pfgst_loss_prep_kernel<<<(unsigned)((n + pfst::kLossThreads - 1) / pfst::kLossThreads),
+                                   pfst::kLossThreads, 0, s>>>(P);
+    PFST_CHECK_LAUNCH("pfst_pfgst_loss_fwd/prep");
+  }
   int64_t grid = (total + pfst::kLossThreads - 1) / pfst::kLossThreads;
-  const int64_t cap = (int64_t)pfst::kNumSMs * 8;
+  const int64_t cap = (int64_t)pfst::kNumSMs * 16;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   pfst::pfgst_loss_fwd_kernel<<<(unsigned)grid, pfst::kLossThreads, 0, s>>>(
@@ -389,11 +446,12 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
 int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
                         const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
                         float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
-                        int32_t dilation, int32_t top_k, const float* weights6_host, const double* stats,
-                        const float* grad_losses, float* coef, float* grad_logits, void* stream) {
+                        int32_t dilation, int32_t top_k, const float* weights6_host, const void* workspace,
+                        const double* stats, const float* grad_losses, float* coef, float* grad_logits,
+                        void* stream) {
   pfst::LossParams P;
   const int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
-                                   mix, gt_h, gt_w, dilation, top_k, weights6_host);
+                                   mix, gt_h, gt_w, dilation, top_k, weights6_host, const_cast<void*>(workspace));
   if (rc != PFST_OK) return rc;
   if (!stats || !grad_losses || !coef) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -37,14 +37,15 @@ class _PFGSTLossFn(torch.autograd.Function):
         dots, ks = ops.neigh_dots(x_ema, x_src, geo.dilation // geo.up)
         losses, stats, density, eroded = ops.pfgst_loss_fwd(dots, ks, geo, logits_trg, gt_src, mix_masks,
                                                             cfg["top_k"], cfg["w6"])
-        ctx.save_for_backward(logits_trg, x_src, gt_src, mix_masks, dots, stats)
+        ctx.save_for_backward(logits_trg, x_src, gt_src, mix_masks, dots, stats[0], stats[1])
         ctx.geo, ctx.ks, ctx.cfg = geo, ks, cfg
         ctx.mark_non_differentiable(density, eroded)
         return losses, density, eroded
 
     @staticmethod
     def backward(ctx, grad_losses, _gd, _ge):
-        logits_trg, x_src, gt_src, mix_masks, dots, stats = ctx.saved_tensors
+        logits_trg, x_src, gt_src, mix_masks, dots, st, ws = ctx.saved_tensors
+        stats = (st, ws)
         geo, cfg = ctx.geo, ctx.cfg
         need_logits, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         coef, glog = ops.pfgst_loss_bwd(dots, ctx.ks, geo, logits_trg, gt_src, mix_masks, cfg["top_k"], cfg["w6"],

@@ -286,22 +286,24 @@ def _w6(weights6):
 
 
 def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, want_vis=True):
-    """-> (losses float32[6], stats float64[16], density|None, eroded|None)."""
+    """-> (losses float32[6], (stats float64[16], workspace), density|None, eroded|None)."""
     dev = logits.device
     _dev(dots, "dots", torch.float32)
     _dev(logits, "logits", torch.float32)
     _dev(gt, "gt", torch.int64)
     _dev(mix, "mix", torch.int64)
     stats = torch.empty(16, dtype=torch.float64, device=dev)
+    ws_bytes = int(_lib.load().pfst_pfgst_loss_ws_bytes(geo.B, geo.C, geo.fh, geo.fw, geo.up))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     losses = torch.empty(6, dtype=torch.float32, device=dev)
     density = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.float32, device=dev) if want_vis else None
     eroded = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.uint8, device=dev) if want_vis else None
     _lib.call("pfst_pfgst_loss_fwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
-              geo.dilation, int(top_k), _w6(weights6), stats.data_ptr(), losses.data_ptr(),
+              geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), losses.data_ptr(),
               None if density is None else density.data_ptr(), None if eroded is None else eroded.data_ptr(),
               _stream())
-    return losses, stats, density, eroded
+    return losses, (stats, ws), density, eroded
 
 
 def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, stats, grad_losses,
@@ -309,10 +311,11 @@ def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6
     """-> (coef (B,9,fh,fw), grad_logits|None)."""
     dev = logits.device
     _dev(grad_losses, "grad_losses", torch.float32)
+    stats, ws = stats
     coef = torch.empty((geo.B, 9, geo.fh, geo.fw), dtype=torch.float32, device=dev)
     glog = torch.empty_like(logits) if want_logits_grad else None
     _lib.call("pfst_pfgst_loss_bwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
-              geo.dilation, int(top_k), _w6(weights6), stats.data_ptr(), grad_losses.data_ptr(),
+              geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), grad_losses.data_ptr(),
               coef.data_ptr(), None if glog is None else glog.data_ptr(), _stream())
     return coef, glog
