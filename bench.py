@@ -194,7 +194,8 @@ def run_ours(args, wl, rank, world, local_rank):
     teacher = [p.to(dev) for p in model_params(wl.C, g)]
     n_params = sum(p.numel() for p in student)
     step = SelfTrainingStep(teacher, student, wl.C, wl.D, dev, dilation=wl.dilation,
-                            downscale=wl.downscale if wl.downscale != 1.0 else None, max_batch=max(wl.B, 64))
+                            downscale=wl.downscale if wl.downscale != 1.0 else None, max_batch=max(wl.B, 64),
+                            graphs=not args.no_graphs)
 
     def one(it):
         return step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], inp["ema_logits"],
@@ -294,7 +295,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "config": {"workload": wl.name, "batch_per_gpu": wl.B, "classes": wl.C, "image": [wl.H, wl.W],
                        "feature_dim": wl.D, "params": n_params,
                        "l2": "no flush: per-step working set (params 349 MB + maps 0.5 GB) exceeds the 126 MB L2",
-                       "step": "EMA + pseudo-label + ClassMix + PFGST loss fwd/bwd + prototypes fwd/bwd (+ all-reduce)"},
+                       "step": "EMA + pseudo-label + ClassMix + PFGST loss fwd/bwd + prototypes fwd/bwd (+ all-reduce)",
+                       "cuda_graphs": not args.no_graphs},
             "iters_per_s": world * args.steps / (ms * 1e-3) / world,
             "step_bytes": sum(ab.values()), "step_gbs_per_gpu": sum(ab.values()) / (ms / args.steps * 1e-3) / 1e9,
             "step_frac_of_peak": sum(ab.values()) / (ms / args.steps * 1e-3) / 1e9 / peak,
@@ -327,6 +329,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-sample-images", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no CUDA-graph segments)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

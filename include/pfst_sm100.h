@@ -165,6 +165,25 @@ int pfst_neigh_dots(const float* x_a, const float* x_b, int64_t B, int32_t D, in
 int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int32_t h,
                     int32_t w, int32_t dilation, float* grad_x, void* stream);
 
+/* pfst_neigh_dots for ONE tensor written into slot `slot` of an `n_slots`-tensor dots
+ * buffer of pfst_neigh_dots_splits(1,B,D,h,w) channel splits (the loss reads slot 0 =
+ * x_ema, slot 1 = x_src), so the two feature tensors can be processed at different
+ * points of the step (x_ema next to the prototype accumulation, x_src next to the
+ * prototype distance: the second kernel of each pair then hits the 126 MB L2).       */
+int pfst_neigh_dots_slot(const float* x, int64_t B, int32_t D, int32_t h, int32_t w,
+                         int32_t dilation, int32_t slot, int32_t n_slots, float* dots,
+                         void* stream);
+
+/* pfst_neigh_grad and pfst_proto_dist_bwd (below) in one pass over x: grad_x =
+ * neighbourhood-cosine gradient + grad_loss * (x - mu[label]) / (dist * n_valid).
+ * x is read once and grad_x written once for both losses (8*D B/pixel instead of
+ * 20*D). Same argument meaning as the two entry points it fuses.                     */
+int pfst_neigh_grad_proto(const float* x, const float* coef, int64_t B, int32_t D, int32_t h,
+                          int32_t w, int32_t dilation, const int64_t* labels,
+                          int32_t lab_h, int32_t lab_w, const float* mu, const uint8_t* seen,
+                          int32_t C, const float* dist, const double* acc,
+                          const float* grad_loss, float* grad_x, void* stream);
+
 /* Bytes of the `workspace` the two entry points below share (per-pixel maps written
  * by the forward's prep kernel and re-read by the backward). Host only.             */
 int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up);
@@ -220,10 +239,13 @@ int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_
 /* mu_out[c] = packed sums / max(count,1) for classes with pixels; classes already
  * seen (seen_prev[c] != 0) are EMA-updated fl(fl(a32*mu_prev)+fl(b32*mean)) (the E2
  * rule); classes without pixels keep mu_prev. mu_prev / seen_prev may be NULL
- * (first call). cnt_out int64[C], seen_out uint8[C] may be NULL.                    */
-int pfst_proto_finalize(const float* packed, int32_t C, int32_t D, const float* mu_prev,
+ * (first call) and may alias mu_out / seen_out (in-place bank update). cnt_out
+ * int64[C], seen_out uint8[C] may be NULL. reset_packed != 0 zeroes `packed` after it
+ * has been consumed (ready for the next step's accumulation; no separate memset).   */
+int pfst_proto_finalize(float* packed, int32_t C, int32_t D, const float* mu_prev,
                         const uint8_t* seen_prev, float a32, float b32, float* mu_out,
-                        int64_t* cnt_out, uint8_t* seen_out, void* stream);
+                        int64_t* cnt_out, uint8_t* seen_out, int32_t reset_packed,
+                        void* stream);
 
 /* loss = mean over valid pixels of ||feats[:,n] - mu[label_n]||_2 (masked_feat_dist
  * with f2 = mu[label]); valid = label in [0,C) and seen[label] (seen may be NULL).

@@ -43,13 +43,16 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_neigh_dots_splits": (_i32, [_i64, _i64, _i32, _i32, _i32]),
     "pfst_neigh_dots": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pfst_neigh_grad": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pfst_neigh_dots_slot": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pfst_neigh_grad_proto": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32,
+                                        _vp, _vp, _vp, _vp, _vp]),
     "pfst_pfgst_loss_ws_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
     "pfst_pfgst_loss_fwd": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
                                       _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "pfst_pfgst_loss_bwd": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
                                       _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "pfst_proto_accum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp]),
-    "pfst_proto_finalize": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "pfst_proto_finalize": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "pfst_proto_dist_fwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "pfst_proto_dist_bwd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "pfst_proto_dist_all": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
@@ -92,5 +95,14 @@ def check(code: int, what: str) -> None:
     raise PfstError(f"{what} failed ({code}): {msg}")
 
 
+_DEBUG_SYNC = bool(os.environ.get("PFST_DEBUG_SYNC"))
+
+
 def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args), name)
+    if _DEBUG_SYNC:                       # development aid: attribute an asynchronous fault to its launch
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as exc:
+            raise PfstError(f"{name}: device fault surfaced after this launch: {exc}") from exc

@@ -88,4 +88,22 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
   return __reduce_add_sync(0xffffffffu, v);
 }
 
+// ---- nearest-resampled label lookup (F.interpolate(mode='nearest'), pfgst_loss.py:62) ----
+__device__ __forceinline__ int pr_nearest(int dst, float scale, int in) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+
+// label of feature pixel p (0..h*w) of image b, 255 if outside [0,C) or masked out
+__device__ __forceinline__ uint8_t pr_label(const int64_t* __restrict__ labels, const float* __restrict__ conf,
+                                            float conf_thr, int b, int p, int w, int lab_h, int lab_w,
+                                            float sh, float sw, int C) {
+  const int y = p / w, x = p - y * w;
+  const int64_t o = ((int64_t)b * lab_h + pr_nearest(y, sh, lab_h)) * lab_w + pr_nearest(x, sw, lab_w);
+  const int64_t l = labels[o];
+  bool ok = l >= 0 && l < C;
+  if (conf && ok) ok = conf[o] >= conf_thr;
+  return ok ? (uint8_t)l : (uint8_t)255;
+}
+
 }  // namespace pfst

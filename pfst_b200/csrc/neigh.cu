@@ -108,7 +108,7 @@ __device__ __forceinline__ void nb_produce(const CUtensorMap* map, float* stage_
 template <int DIL>
 __global__ void __launch_bounds__(kNbThreads)
 neigh_dots_tma_kernel(const __grid_constant__ NeighMaps maps, int n_tensors, int B, int D, int h, int w,
-                      int ksplit, float* __restrict__ dots) {
+                      int ksplit, int slot0, int n_slots, float* __restrict__ dots) {
   using G = NbGeom<DIL>;
   constexpr int kStageFloats = kNbCH * G::FWD_ROWS * G::RS;
   extern __shared__ __align__(128) unsigned char nb_smem[];
@@ -123,71 +123,128 @@ neigh_dots_tma_kernel(const __grid_constant__ NeighMaps maps, int n_tensors, int
       nb_produce<G::FWD_ROWS, G::RS>(&maps.m[tl.t], stage_buf, full_bar, empty_bar, tl, tl.x0 - kNbHL, tl.y0);
     return;
   }
-  const int lx = (threadIdx.x & 7) * 4, ly = threadIdx.x >> 3;  // strip origin inside the tile
-  float acc[5][4];
+  // Each lane owns a CHAIN of four 1x4 pixel strips, rows r0 + k*DIL (k = 0..3): the row read
+  // as "row y+d" of strip k is "row y" of strip k+1, so a channel costs 14 128-bit shared
+  // loads per 16 pixels instead of 20 (the kernel is shared-memory-bandwidth bound). A warp
+  // covers the whole 32x16 tile of one channel (8 lanes per row: conflict-free); the four
+  // consumer warps take the stage's channels round-robin.
+  const int lx = (lane & 7) * 4, chain = lane >> 3;
+  const int r0 = (chain / DIL) * 4 * DIL + chain % DIL;
+  float acc[5][4][4];
 #pragma unroll
-  for (int k = 0; k < 5; ++k)
+  for (int m = 0; m < 5; ++m)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][k][i] = 0.f;
 
   int it = 0;
   for (int c = tl.c_begin; c < tl.c_end; ++c, ++it) {
     const int s = it % kNbStages;
     mbar_wait(&full_bar[s], (uint32_t)(it / kNbStages) & 1u);
-    const float* buf = stage_buf + (size_t)s * kStageFloats + ly * G::RS + lx;
+    const float* buf = stage_buf + (size_t)s * kStageFloats + r0 * G::RS + lx;
 #pragma unroll
-    for (int ch = 0; ch < kNbCH; ++ch) {
+    for (int cc = 0; cc < kNbCH / (kNbConsumers / 32); ++cc) {
+      const int ch = warp + cc * (kNbConsumers / 32);
       // smem column of image column x is (x - x0 + 4); this strip's pixels sit at lx+4+i
-      const float* ra = buf + ch * G::FWD_ROWS * G::RS;   // row y
-      const float* rb = ra + DIL * G::RS;                 // row y + d
-      float A[8], Bv[12];                                 // A[j] = col lx+4+j ; Bv[j] = col lx+j
+      const float* row = buf + ch * G::FWD_ROWS * G::RS;
+      float P[12], Q[12];                                  // P[j] = col lx+j of the current row
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const float4 fa = *reinterpret_cast<const float4*>(ra + 4 + 4 * v);
-        A[4 * v] = fa.x; A[4 * v + 1] = fa.y; A[4 * v + 2] = fa.z; A[4 * v + 3] = fa.w;
+      for (int v = 1; v < 3; ++v) {
+        const float4 f = *reinterpret_cast<const float4*>(row + 4 * v);
+        P[4 * v] = f.x; P[4 * v + 1] = f.y; P[4 * v + 2] = f.z; P[4 * v + 3] = f.w;
       }
 #pragma unroll
-      for (int v = 0; v < 3; ++v) {
-        const float4 fb = *reinterpret_cast<const float4*>(rb + 4 * v);
-        Bv[4 * v] = fb.x; Bv[4 * v + 1] = fb.y; Bv[4 * v + 2] = fb.z; Bv[4 * v + 3] = fb.w;
-      }
+      for (int k = 0; k < 4; ++k) {
+        row += DIL * G::RS;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = A[i];
-        acc[0][i] = fmaf(a, a, acc[0][i]);
-        acc[1][i] = fmaf(a, A[i + DIL], acc[1][i]);             // ( 0, +d)
-        acc[2][i] = fmaf(a, Bv[4 + i - DIL], acc[2][i]);        // (+d, -d)
-        acc[3][i] = fmaf(a, Bv[4 + i], acc[3][i]);              // (+d,  0)
-        acc[4][i] = fmaf(a, Bv[4 + i + DIL], acc[4][i]);        // (+d, +d)
+        for (int v = 0; v < 3; ++v) {
+          const float4 f = *reinterpret_cast<const float4*>(row + 4 * v);
+          Q[4 * v] = f.x; Q[4 * v + 1] = f.y; Q[4 * v + 2] = f.z; Q[4 * v + 3] = f.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = P[4 + i];
+          acc[0][k][i] = fmaf(a, a, acc[0][k][i]);
+          acc[1][k][i] = fmaf(a, P[4 + i + DIL], acc[1][k][i]);      // ( 0, +d)
+          acc[2][k][i] = fmaf(a, Q[4 + i - DIL], acc[2][k][i]);      // (+d, -d)
+          acc[3][k][i] = fmaf(a, Q[4 + i], acc[3][k][i]);            // (+d,  0)
+          acc[4][k][i] = fmaf(a, Q[4 + i + DIL], acc[4][k][i]);      // (+d, +d)
+        }
+#pragma unroll
+        for (int j = 4; j < 12; ++j) P[j] = Q[j];
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
-  const int y = tl.y0 + ly;
-  if (y < h) {
-    float* out = dots + ((((int64_t)tl.split * n_tensors + tl.t) * B + tl.b) * 5) * h * w + (int64_t)y * w;
+  // The four warps hold partial sums over disjoint channels: merge through shared memory
+  // (the stage ring is idle now) in a fixed order, then one warp-row-coalesced store per map.
+  asm volatile("bar.sync 1, %0;" ::"n"(kNbConsumers) : "memory");
+  float* red = stage_buf;                                   // [4 warps][5*16 values][32 lanes]
+  if (warp > 0) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
+    for (int m = 0; m < 5; ++m)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = tl.x0 + lx + i;
-        if (x < w) out[(int64_t)k * h * w + x] = acc[k][i];
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[((warp * 80) + (m * 16 + k * 4 + i)) * 32 + lane] = acc[m][k][i];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kNbConsumers) : "memory");
+  if (warp == 0) {
+    const int x = tl.x0 + lx;
+    float* out = dots + ((((int64_t)tl.split * n_slots + slot0 + tl.t) * B + tl.b) * 5) * h * w;
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = m * 16 + k * 4 + i;
+          o[i] = ((acc[m][k][i] + red[(80 + e) * 32 + lane]) + red[(160 + e) * 32 + lane]) + red[(240 + e) * 32 + lane];
+        }
+        const int y = tl.y0 + r0 + k * DIL;
+        if (y < h && x < w)   // w % 4 == 0: a strip is entirely inside or outside
+          *reinterpret_cast<float4*>(out + ((int64_t)m * h + y) * w + x) = make_float4(o[0], o[1], o[2], o[3]);
       }
   }
 }
 
 // --------------------------------------------------------------- backward (TMA)
-template <int DIL>
+// PROTO: the prototype-distance gradient (P3 backward, proto.cu) is added in the same pass,
+//   grad[n,c] += g * (x[n,c] - mu[y_n,c]) / (dist_n * n_valid),
+// so x_src is read once and grad_x written once for both losses.
+struct ProtoBwd {
+  const int64_t* labels;   // (B, lab_h, lab_w)
+  int lab_h, lab_w;
+  const float* mu;         // (C, D)
+  const uint8_t* seen;     // (C) or null
+  int C;
+  const float* dist;       // (B, h, w) from pfst_proto_dist_fwd
+  const double* acc;       // acc[1] = number of valid pixels
+  const float* grad_loss;  // device scalar
+  int mu_stride;           // shared-memory row stride of the staged prototypes
+};
+
+template <int DIL, bool PROTO>
 __global__ void __launch_bounds__(kNbThreads)
 neigh_grad_tma_kernel(const __grid_constant__ NeighMaps maps, const float* __restrict__ coef, int B, int D,
-                      int h, int w, int ksplit, float* __restrict__ grad) {
+                      int h, int w, int ksplit, float* __restrict__ grad, const ProtoBwd pb) {
   using G = NbGeom<DIL>;
   constexpr int kStageFloats = kNbCH * G::BWD_ROWS * G::RS;
   extern __shared__ __align__(128) unsigned char nb_smem[];
   float* stage_buf = reinterpret_cast<float*>(nb_smem);
+  float* mu_s = stage_buf + (size_t)kNbStages * kStageFloats;       // [C][mu_stride]  (PROTO only)
   __shared__ uint64_t full_bar[kNbStages], empty_bar[kNbStages];
   const NbTile tl = nb_decode(1, B, h, w, D, ksplit);
+  if (PROTO) {   // this CTA's channel slice of the prototypes
+    const int ch0 = tl.c_begin * kNbCH, nch = min(D, tl.c_end * kNbCH) - ch0;
+    for (int i = threadIdx.x; i < pb.C * nch; i += kNbThreads) {
+      const int c = i / nch, j = i - c * nch;
+      mu_s[c * pb.mu_stride + j] = pb.mu[(int64_t)c * D + ch0 + j];
+    }
+  }
   nb_init_barriers(full_bar, empty_bar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,43 +254,99 @@ neigh_grad_tma_kernel(const __grid_constant__ NeighMaps maps, const float* __res
                                      tl.y0 - DIL);
     return;
   }
-  const int lx = (threadIdx.x & 7) * 4, ly = threadIdx.x >> 3;
-  const int y = tl.y0 + ly, x = tl.x0 + lx;
-  const bool live = (y < h) && (x < w);   // w % 4 == 0: a strip is entirely inside or outside
-  float K[9][4];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) v = *reinterpret_cast<const float4*>(coef + (((int64_t)tl.b * 9 + k) * h + y) * w + x);
-    K[k][0] = v.x; K[k][1] = v.y; K[k][2] = v.z; K[k][3] = v.w;
-  }
-  float* gout = grad + (((int64_t)tl.b * D) * h + y) * w + x;
+  // Each lane owns two 1x4 output strips, rows r and r+DIL: their 3x3 dilated windows share
+  // two of the four input rows, so a channel costs 12 128-bit shared loads per 8 pixels
+  // instead of 18 (shared-memory-bandwidth bound). Two warps cover the 32x16 tile of one
+  // channel; warps {0,1} take the even channels of a stage, warps {2,3} the odd ones.
+  const int lx = (lane & 7) * 4;
+  const int pair = (warp & 1) * 4 + (lane >> 3);                 // 0..7
+  const int r = (pair / DIL) * 2 * DIL + pair % DIL;             // first output row (tile-relative)
+  const int half = warp >> 1;
+  const int x = tl.x0 + lx;
   const int64_t plane = (int64_t)h * w;
+  bool live[2];
+  float K[2][9][4];
+  // P3 backward: per-pixel coefficient and prototype row of the strips' pixels
+  float pcoef[2][4];
+  int prow[2][4];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int y = tl.y0 + r + q * DIL;
+    live[q] = (y < h) && (x < w);   // w % 4 == 0: a strip is entirely inside or outside
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[q]) v = *reinterpret_cast<const float4*>(coef + (((int64_t)tl.b * 9 + k) * h + y) * w + x);
+      K[q][k][0] = v.x; K[q][k][1] = v.y; K[q][k][2] = v.z; K[q][k][3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pcoef[q][i] = 0.f; prow[q][i] = 0; }
+    if (PROTO && live[q]) {
+      const float g = pb.grad_loss[0];
+      const float nvalid = (float)pb.acc[1];
+      const float sh = (float)pb.lab_h / (float)h, sw = (float)pb.lab_w / (float)w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pp = y * w + x + i;
+        uint8_t l = pr_label(pb.labels, nullptr, 0.f, tl.b, pp, w, pb.lab_h, pb.lab_w, sh, sw, pb.C);
+        if (l != 255 && pb.seen && !pb.seen[l]) l = 255;
+        const float dn = pb.dist[(int64_t)tl.b * plane + pp];
+        pcoef[q][i] = (l != 255 && dn > 0.f) ? g / (dn * nvalid) : 0.f;   // torch.norm backward: 0 at 0
+        prow[q][i] = (l != 255 ? (int)l : 0) * pb.mu_stride;
+      }
+    }
+  }
+  float* gout = grad + (((int64_t)tl.b * D) * h + tl.y0 + r) * w + x;
 
   int it = 0;
   for (int c = tl.c_begin; c < tl.c_end; ++c, ++it) {
     const int s = it % kNbStages;
     mbar_wait(&full_bar[s], (uint32_t)(it / kNbStages) & 1u);
-    const float* buf = stage_buf + (size_t)s * kStageFloats + ly * G::RS + lx;
+    // smem row j holds image row y0 - DIL + j: output row r reads smem rows r, r+DIL, r+2*DIL
+    const float* buf = stage_buf + (size_t)s * kStageFloats + r * G::RS + lx;
 #pragma unroll
-    for (int ch = 0; ch < kNbCH; ++ch) {
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int cc = 0; cc < kNbCH / 2; ++cc) {
+      const int ch = cc * 2 + half;
+      const float* row = buf + ch * G::BWD_ROWS * G::RS;
+      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float ctr[2][4];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const float* r = buf + (ch * G::BWD_ROWS + ky * DIL) * G::RS;
-        float R[12];                                      // R[j] = col lx+j  (pixel i at 4+i)
+      for (int j = 0; j < 4; ++j) {                         // the four input rows of the two windows
+        float R[12];                                        // R[e] = col lx+e  (pixel i at 4+i)
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-          const float4 f = *reinterpret_cast<const float4*>(r + 4 * v);
+          const float4 f = *reinterpret_cast<const float4*>(row + j * DIL * G::RS + 4 * v);
           R[4 * v] = f.x; R[4 * v + 1] = f.y; R[4 * v + 2] = f.z; R[4 * v + 3] = f.w;
         }
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
+        for (int q = 0; q < 2; ++q) {
+          const int ky = j - q;                             // tap row of window q that reads input row j
+          if (ky < 0 || ky > 2) continue;
+          if (ky == 1) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = fmaf(K[ky * 3 + kx][i], R[4 + i + (kx - 1) * DIL], o[i]);
+            for (int i = 0; i < 4; ++i) ctr[q][i] = R[4 + i];
+          }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[q][i] = fmaf(K[q][ky * 3 + kx][i], R[4 + i + (kx - 1) * DIL], o[q][i]);
+        }
       }
       const int cg = c * kNbCH + ch;
-      if (live && cg < D) __stcs(reinterpret_cast<float4*>(gout + cg * plane), make_float4(o[0], o[1], o[2], o[3]));
+      if (PROTO) {
+        const int cl = (c - tl.c_begin) * kNbCH + ch;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[q][i] = fmaf(pcoef[q][i], ctr[q][i] - mu_s[prow[q][i] + cl], o[q][i]);
+      }
+      if (cg < D) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (live[q])
+            __stcs(reinterpret_cast<float4*>(gout + cg * plane + (int64_t)q * DIL * w),
+                   make_float4(o[q][0], o[q][1], o[q][2], o[q][3]));
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -243,7 +356,8 @@ neigh_grad_tma_kernel(const __grid_constant__ NeighMaps maps, const float* __res
 // ------------------------------------------------- generic (any shape) kernels
 __global__ void __launch_bounds__(128)
 neigh_dots_generic_kernel(const float* __restrict__ xa, const float* __restrict__ xb, int n_tensors, int B,
-                          int D, int h, int w, int dil, int ksplit, float* __restrict__ dots) {
+                          int D, int h, int w, int dil, int ksplit, int slot0, int n_slots,
+                          float* __restrict__ dots) {
   const int64_t plane = (int64_t)h * w;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int z = blockIdx.y;
@@ -265,7 +379,7 @@ neigh_dots_generic_kernel(const float* __restrict__ xa, const float* __restrict_
     if (inr) a3 = fmaf(v, __ldg(q + (int64_t)dil * w), a3);
     if (in4) a4 = fmaf(v, __ldg(q + (int64_t)dil * w + dil), a4);
   }
-  float* out = dots + ((((int64_t)split * n_tensors + t) * B + b) * 5) * plane + p;
+  float* out = dots + ((((int64_t)split * n_slots + slot0 + t) * B + b) * 5) * plane + p;
   out[0] = a0; out[plane] = a1; out[2 * plane] = a2; out[3 * plane] = a3; out[4 * plane] = a4;
 }
 
@@ -314,7 +428,7 @@ static int nb_splits(int64_t units, int h, int w, int D) {
 
 template <int DIL>
 static int launch_dots_tma(const float* xa, const float* xb, int T, int B, int D, int h, int w, int ks,
-                           float* dots, cudaStream_t s) {
+                           int slot0, int n_slots, float* dots, cudaStream_t s) {
   using G = NbGeom<DIL>;
   NeighMaps maps;
   if (!make_nchw_tensor_map(&maps.m[0], xa, B, D, h, w, G::RS, G::FWD_ROWS, kNbCH)) return PFST_ERR_CUDA;
@@ -324,24 +438,55 @@ static int launch_dots_tma(const float* xa, const float* xb, int T, int B, int D
   PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_neigh_dots/attr");
   const int64_t tiles = (int64_t)((w + kNbTW - 1) / kNbTW) * ((h + kNbTH - 1) / kNbTH);
   const int64_t grid = (int64_t)T * B * tiles * ks;
-  k<<<(unsigned)grid, kNbThreads, smem, s>>>(maps, T, B, D, h, w, ks, dots);
+  k<<<(unsigned)grid, kNbThreads, smem, s>>>(maps, T, B, D, h, w, ks, slot0, n_slots, dots);
   PFST_CHECK_LAUNCH("pfst_neigh_dots");
   return PFST_OK;
 }
 
-template <int DIL>
+// bytes of shared memory the fused prototype slice needs (0 = prototypes do not fit: unfused path)
+static size_t nb_proto_smem(int C, int D, int ks, int* stride) {
+  const int chunks = (D + kNbCH - 1) / kNbCH;
+  const int nch = ((chunks + ks - 1) / ks) * kNbCH;
+  *stride = nch + 1;                                   // +1: bank skew between prototype rows
+  return (size_t)C * (nch + 1) * sizeof(float);
+}
+
+template <int DIL, bool PROTO>
 static int launch_grad_tma(const float* x, const float* coef, int B, int D, int h, int w, int ks, float* grad,
-                           cudaStream_t s) {
+                           ProtoBwd pb, cudaStream_t s) {
   using G = NbGeom<DIL>;
   NeighMaps maps;
   if (!make_nchw_tensor_map(&maps.m[0], x, B, D, h, w, G::RS, G::BWD_ROWS, kNbCH)) return PFST_ERR_CUDA;
   maps.m[1] = maps.m[0];
-  const size_t smem = (size_t)kNbStages * kNbCH * G::BWD_ROWS * G::RS * sizeof(float);
-  auto k = neigh_grad_tma_kernel<DIL>;
+  size_t smem = (size_t)kNbStages * kNbCH * G::BWD_ROWS * G::RS * sizeof(float);
+  if (PROTO) smem += nb_proto_smem(pb.C, D, ks, &pb.mu_stride);
+  auto k = neigh_grad_tma_kernel<DIL, PROTO>;
   PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_neigh_grad/attr");
   const int64_t tiles = (int64_t)((w + kNbTW - 1) / kNbTW) * ((h + kNbTH - 1) / kNbTH);
   const int64_t grid = (int64_t)B * tiles * ks;
-  k<<<(unsigned)grid, kNbThreads, smem, s>>>(maps, coef, B, D, h, w, ks, grad);
+  k<<<(unsigned)grid, kNbThreads, smem, s>>>(maps, coef, B, D, h, w, ks, grad, pb);
+  PFST_CHECK_LAUNCH("pfst_neigh_grad");
+  return PFST_OK;
+}
+
+template <bool PROTO>
+static int dispatch_grad_tma(int dilation, const float* x, const float* coef, int B, int D, int h, int w, int ks,
+                             float* grad, const ProtoBwd& pb, cudaStream_t s) {
+  switch (dilation) {
+    case 1: return launch_grad_tma<1, PROTO>(x, coef, B, D, h, w, ks, grad, pb, s);
+    case 2: return launch_grad_tma<2, PROTO>(x, coef, B, D, h, w, ks, grad, pb, s);
+    default: return launch_grad_tma<4, PROTO>(x, coef, B, D, h, w, ks, grad, pb, s);
+  }
+}
+
+static int launch_grad_generic(const float* x, const float* coef, int64_t B, int D, int h, int w, int dilation,
+                               float* grad_x, cudaStream_t s) {
+  const int64_t plane = (int64_t)h * w;
+  const unsigned gx = (unsigned)((plane + 127) / 128);
+  unsigned gz = (unsigned)(((int64_t)kNumSMs * 16) / ((int64_t)gx * B) + 1);
+  if (gz > (unsigned)D) gz = (unsigned)D;
+  if (gz > 64) gz = 64;
+  neigh_grad_generic_kernel<<<dim3(gx, (unsigned)B, gz), 128, 0, s>>>(x, coef, (int)B, D, h, w, dilation, grad_x);
   PFST_CHECK_LAUNCH("pfst_neigh_grad");
   return PFST_OK;
 }
@@ -355,27 +500,41 @@ int32_t pfst_neigh_dots_splits(int64_t n_tensors, int64_t B, int32_t D, int32_t 
   return pfst::nb_splits(n_tensors * B, h, w, D);
 }
 
-int pfst_neigh_dots(const float* x_a, const float* x_b, int64_t B, int32_t D, int32_t h, int32_t w,
-                    int32_t dilation, float* dots, void* stream) {
-  if (!x_a || !dots || B < 0 || D < 1 || h < 1 || w < 1 || dilation < 1) return PFST_ERR_INVALID_ARG;
-  if (B == 0) return PFST_OK;
-  if (B > 0x7fffffffll / 4) return PFST_ERR_UNSUPPORTED;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+static int neigh_dots_impl(const float* x_a, const float* x_b, int64_t B, int32_t D, int32_t h, int32_t w,
+                           int32_t dilation, int slot0, int n_slots, float* dots, cudaStream_t s) {
   const int T = x_b ? 2 : 1;
   const int ks = pfst::nb_splits((int64_t)T * B, h, w, D);
   if (pfst::nb_tma_ok(x_a, x_b, w, dilation)) {
     switch (dilation) {
-      case 1: return pfst::launch_dots_tma<1>(x_a, x_b, T, (int)B, D, h, w, ks, dots, s);
-      case 2: return pfst::launch_dots_tma<2>(x_a, x_b, T, (int)B, D, h, w, ks, dots, s);
-      default: return pfst::launch_dots_tma<4>(x_a, x_b, T, (int)B, D, h, w, ks, dots, s);
+      case 1: return pfst::launch_dots_tma<1>(x_a, x_b, T, (int)B, D, h, w, ks, slot0, n_slots, dots, s);
+      case 2: return pfst::launch_dots_tma<2>(x_a, x_b, T, (int)B, D, h, w, ks, slot0, n_slots, dots, s);
+      default: return pfst::launch_dots_tma<4>(x_a, x_b, T, (int)B, D, h, w, ks, slot0, n_slots, dots, s);
     }
   }
   const int64_t plane = (int64_t)h * w;
   const dim3 grid((unsigned)((plane + 127) / 128), (unsigned)(T * B * ks), 1);
   if (grid.y > 65535) return PFST_ERR_UNSUPPORTED;
-  pfst::neigh_dots_generic_kernel<<<grid, 128, 0, s>>>(x_a, x_b, T, (int)B, D, h, w, dilation, ks, dots);
+  pfst::neigh_dots_generic_kernel<<<grid, 128, 0, s>>>(x_a, x_b, T, (int)B, D, h, w, dilation, ks, slot0, n_slots,
+                                                       dots);
   PFST_CHECK_LAUNCH("pfst_neigh_dots");
   return PFST_OK;
+}
+
+int pfst_neigh_dots(const float* x_a, const float* x_b, int64_t B, int32_t D, int32_t h, int32_t w,
+                    int32_t dilation, float* dots, void* stream) {
+  if (!x_a || !dots || B < 0 || D < 1 || h < 1 || w < 1 || dilation < 1) return PFST_ERR_INVALID_ARG;
+  if (B == 0) return PFST_OK;
+  if (B > 0x7fffffffll / 4) return PFST_ERR_UNSUPPORTED;
+  return neigh_dots_impl(x_a, x_b, B, D, h, w, dilation, 0, x_b ? 2 : 1, dots, static_cast<cudaStream_t>(stream));
+}
+
+int pfst_neigh_dots_slot(const float* x, int64_t B, int32_t D, int32_t h, int32_t w, int32_t dilation,
+                         int32_t slot, int32_t n_slots, float* dots, void* stream) {
+  if (!x || !dots || B < 0 || D < 1 || h < 1 || w < 1 || dilation < 1 || n_slots < 1 || slot < 0 || slot >= n_slots)
+    return PFST_ERR_INVALID_ARG;
+  if (B == 0) return PFST_OK;
+  if (B > 0x7fffffffll / 4) return PFST_ERR_UNSUPPORTED;
+  return neigh_dots_impl(x, nullptr, B, D, h, w, dilation, slot, n_slots, dots, static_cast<cudaStream_t>(stream));
 }
 
 int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int32_t h, int32_t w,
@@ -386,21 +545,34 @@ int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (pfst::nb_tma_ok(x, grad_x, w, dilation) && pfst::aligned16(coef)) {
     const int ks = pfst::nb_splits(B, h, w, D);
-    switch (dilation) {
-      case 1: return pfst::launch_grad_tma<1>(x, coef, (int)B, D, h, w, ks, grad_x, s);
-      case 2: return pfst::launch_grad_tma<2>(x, coef, (int)B, D, h, w, ks, grad_x, s);
-      default: return pfst::launch_grad_tma<4>(x, coef, (int)B, D, h, w, ks, grad_x, s);
+    return pfst::dispatch_grad_tma<false>(dilation, x, coef, (int)B, D, h, w, ks, grad_x, pfst::ProtoBwd{}, s);
+  }
+  return pfst::launch_grad_generic(x, coef, B, D, h, w, dilation, grad_x, s);
+}
+
+int pfst_neigh_grad_proto(const float* x, const float* coef, int64_t B, int32_t D, int32_t h, int32_t w,
+                          int32_t dilation, const int64_t* labels, int32_t lab_h, int32_t lab_w,
+                          const float* mu, const uint8_t* seen, int32_t C, const float* dist,
+                          const double* acc, const float* grad_loss, float* grad_x, void* stream) {
+  if (!x || !coef || !grad_x || !labels || !mu || !dist || !acc || !grad_loss || B < 0 || D < 1 || h < 1 ||
+      w < 1 || dilation < 1 || lab_h < 1 || lab_w < 1 || C < 1)
+    return PFST_ERR_INVALID_ARG;
+  if (B == 0) return PFST_OK;
+  if (B > 65535) return PFST_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pfst::nb_tma_ok(x, grad_x, w, dilation) && pfst::aligned16(coef)) {
+    const int ks = pfst::nb_splits(B, h, w, D);
+    int stride = 0;
+    if (pfst::nb_proto_smem(C, D, ks, &stride) <= 64 * 1024) {
+      pfst::ProtoBwd pb{labels, lab_h, lab_w, mu, seen, C, dist, acc, grad_loss, stride};
+      return pfst::dispatch_grad_tma<true>(dilation, x, coef, (int)B, D, h, w, ks, grad_x, pb, s);
     }
   }
-  const int64_t plane = (int64_t)h * w;
-  const unsigned gx = (unsigned)((plane + 127) / 128);
-  unsigned gz = (unsigned)(((int64_t)pfst::kNumSMs * 16) / ((int64_t)gx * B) + 1);
-  if (gz > (unsigned)D) gz = (unsigned)D;
-  if (gz > 64) gz = 64;
-  pfst::neigh_grad_generic_kernel<<<dim3(gx, (unsigned)B, gz), 128, 0, s>>>(x, coef, (int)B, D, h, w, dilation,
-                                                                             grad_x);
-  PFST_CHECK_LAUNCH("pfst_neigh_grad");
-  return PFST_OK;
+  // shapes the fused kernel does not cover: two passes over grad_x
+  const int rc = pfst_neigh_grad(x, coef, B, D, h, w, dilation, grad_x, stream);
+  if (rc != PFST_OK) return rc;
+  return pfst_proto_dist_bwd(x, B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist, acc, grad_loss, grad_x, 1,
+                             stream);
 }
 
 }  // extern "C"

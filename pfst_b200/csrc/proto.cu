@@ -17,104 +17,240 @@
 // TF32/BF16 MMA: it stays an FFMA bandwidth kernel (north_star: tensor cores only
 // when D and C make it a real contraction).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace pfst {
 
 constexpr int kPrThreads = 256;
 constexpr int kPrWarps = kPrThreads / 32;
 constexpr int kPrMaxC = 128;
-constexpr int kPrPixTile = 8192;   // label bytes staged per pass
 
-__device__ __forceinline__ int pr_nearest(int dst, float scale, int in) {
-  const int s = (int)floorf((float)dst * scale);
-  return s < in - 1 ? s : in - 1;
+// ---- P1: accumulate ------------------------------------------------------------------
+// block = (channel group, pixel tile, image). The block first builds, ONCE, the list of its
+// tile's pixel offsets sorted by class (a stable counting sort on warp match/ballot; every
+// class segment is padded to a multiple of 32 with the offset of a zero slot). After that
+// the segment-reduce of a channel plane is a branch-free gather: for each class, lanes
+// stride over the class's segment of the list and add plane[offset] — one 16-bit and one
+// 32-bit shared load plus one FADD per element, no label test, no atomics, no divergence;
+// one warp reduction + one global RED per (class present, channel).
+// Channel planes stream through a ring of shared-memory stages filled by 1-D bulk async
+// copies (cp.async.bulk + mbarrier, one producer lane), so the HBM pipe holds
+// kPaStages x 16 KB per SM regardless of how many warps are computing.
+constexpr int kPaConsumers = 8;                       // consumer warps
+constexpr int kPaThreads = (kPaConsumers + 1) * 32;   // + 1 producer warp
+constexpr int kPaTile = 4096;                         // pixels per tile (16 KB per plane)
+constexpr int kPaMaxStages = 12;
+constexpr int kPaUnroll = 8;
+
+struct PaLayout {      // dynamic shared memory carve-up (host and device agree through this)
+  int tile, stages, plane_stride;   // plane_stride: floats per stage (tile + 4: zero slot, 16 B aligned)
+  size_t off_order, off_grp, off_seg, total;
+};
+__host__ __device__ inline PaLayout pa_layout(int tile, int stages, int C) {
+  PaLayout L;
+  L.tile = tile; L.stages = stages; L.plane_stride = ((tile + 3) / 4) * 4 + 4;
+  size_t o = (size_t)stages * L.plane_stride * sizeof(float);
+  L.off_order = o; o += ((size_t)(tile + 32 * C) * 2 + 15) / 16 * 16;       // u16 offsets
+  L.off_grp = o;   o += ((size_t)((tile + 31) / 32) * C * 2 + 15) / 16 * 16;  // u16 [groups][C]
+  L.off_seg = o;   o += (size_t)(2 * C + 2) * sizeof(int);                    // seg[C+1], tot[C]
+  L.total = o;
+  return L;
 }
 
-// label of feature pixel p (0..h*w) of image b, 255 if outside [0,C) or masked out
-__device__ __forceinline__ uint8_t pr_label(const int64_t* __restrict__ labels, const float* __restrict__ conf,
-                                            float conf_thr, int b, int p, int w, int lab_h, int lab_w,
-                                            float sh, float sw, int C) {
-  const int y = p / w, x = p - y * w;
-  const int64_t o = ((int64_t)b * lab_h + pr_nearest(y, sh, lab_h)) * lab_w + pr_nearest(x, sw, lab_w);
-  const int64_t l = labels[o];
-  bool ok = l >= 0 && l < C;
-  if (conf && ok) ok = conf[o] >= conf_thr;
-  return ok ? (uint8_t)l : (uint8_t)255;
+__device__ __forceinline__ void pa_sync_consumers() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kPaConsumers * 32) : "memory");
 }
 
-// grid = (channel groups, B). Every warp takes channels of its group round-robin;
-// lanes stride over the image plane with coalesced loads.
-__global__ void __launch_bounds__(kPrThreads)
+__global__ void __launch_bounds__(kPaThreads)
 proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
                    const int64_t* __restrict__ labels, const float* __restrict__ conf, float conf_thr,
-                   int lab_h, int lab_w, int C, int ch_per_block, float* __restrict__ packed) {
-  extern __shared__ __align__(16) unsigned char pr_smem[];
-  uint8_t* lab_s = pr_smem;                                              // [kPrPixTile]
-  float* acc = reinterpret_cast<float*>(pr_smem + kPrPixTile);           // [warps][C][32]
-  const int b = blockIdx.y;
-  const int c0 = blockIdx.x * ch_per_block;
-  const int c1 = min(D, c0 + ch_per_block);
-  const int hw = h * w;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float sh = (float)lab_h / (float)h, sw = (float)lab_w / (float)w;
-  float* my = acc + warp * C * 32;
-  for (int i = lane; i < C * 32; i += 32) my[i] = 0.f;
+                   int lab_h, int lab_w, int C, int groups, int tile, int stages, int use_bulk,
+                   float* __restrict__ packed) {
+  extern __shared__ __align__(128) unsigned char pa_smem[];
+  __shared__ uint64_t full_bar[kPaMaxStages], empty_bar[kPaMaxStages];
+  __shared__ int issued;          // number of planes the producer has issued so far
+  const PaLayout L = pa_layout(tile, stages, C);
+  float* planes = reinterpret_cast<float*>(pa_smem);
+  uint16_t* order = reinterpret_cast<uint16_t*>(pa_smem + L.off_order);
+  uint16_t* grp = reinterpret_cast<uint16_t*>(pa_smem + L.off_grp);
+  int* seg = reinterpret_cast<int*>(pa_smem + L.off_seg);
+  int* tot = seg + C + 1;
 
-  for (int p0 = 0; p0 < hw; p0 += kPrPixTile) {
-    const int np = min(kPrPixTile, hw - p0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < np; i += kPrThreads)
-      lab_s[i] = pr_label(labels, conf, conf_thr, b, p0 + i, w, lab_h, lab_w, sh, sw, C);
-    __syncthreads();
-    // class counts: once per image (channel group 0), same private-accumulator scheme
-    if (blockIdx.x == 0 && warp == 0) {
-      for (int i = lane; i < np; i += 32) {
-        const unsigned l = lab_s[i];
-        if (l != 255u) my[l * 32 + lane] += 1.f;
+  const int hw = h * w;
+  const int n_tiles = (hw + tile - 1) / tile;
+  const int grp_id = blockIdx.x % groups;
+  const int tile_id = (blockIdx.x / groups) % n_tiles;
+  const int b = blockIdx.x / (groups * n_tiles);
+  const int p0 = tile_id * tile;
+  const int np = min(tile, hw - p0);
+  const int ch0 = (int)((int64_t)grp_id * D / groups), ch1 = (int)((int64_t)(grp_id + 1) * D / groups);
+  const int n_items = ch1 - ch0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = feats + ((int64_t)b * D + ch0) * hw + p0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_fence_init();
+    issued = 0;
+  }
+  for (int s = threadIdx.x; s < stages; s += kPaThreads) planes[(size_t)s * L.plane_stride + np] = 0.f;  // zero slot
+  __syncthreads();
+
+  if (warp == kPaConsumers) {          // ---- producer: stream the channel planes
+    if (lane == 0 && use_bulk) {
+      const uint32_t bytes = (uint32_t)np * sizeof(float);
+      for (int i = 0; i < n_items; ++i) {
+        const int s = i % stages;
+        if (i >= stages) mbar_wait(&empty_bar[s], (uint32_t)((i / stages) & 1) ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_load_1d(planes + (size_t)s * L.plane_stride, base + (int64_t)i * hw, bytes, &full_bar[s]);
+        *reinterpret_cast<volatile int*>(&issued) = i + 1;
       }
-      __syncwarp();
-      for (int c = 0; c < C; ++c) {
-        const float v = warp_sum(my[c * 32 + lane]);
-        my[c * 32 + lane] = 0.f;
-        if (lane == 0 && v != 0.f) atomicAdd(&packed[(int64_t)C * D + c], v);
+    }
+    return;
+  }
+
+  // ---- consumers: class-sorted offset list of this tile (stable counting sort) ----------
+  const int ng = (np + 31) / 32;                    // 32-pixel groups, <= kPaTile / 32
+  constexpr int kGroupsPerWarp = kPaTile / 32 / kPaConsumers;
+  const float sh = (float)lab_h / (float)h, sw = (float)lab_w / (float)w;
+  for (int i = threadIdx.x; i < ng * C; i += kPaConsumers * 32) grp[i] = 0;
+  // all label gathers of this warp's groups in flight at once (one memory latency, not 16)
+  unsigned lv[kGroupsPerWarp];
+#pragma unroll
+  for (int u = 0; u < kGroupsPerWarp; ++u) {
+    const int p = (warp + u * kPaConsumers) * 32 + lane;
+    lv[u] = p < np ? (unsigned)pr_label(labels, conf, conf_thr, b, p0 + p, w, lab_h, lab_w, sh, sw, C) : 255u;
+  }
+  pa_sync_consumers();
+#pragma unroll
+  for (int u = 0; u < kGroupsPerWarp; ++u) {
+    const int g = warp + u * kPaConsumers;
+    if (g < ng) {                                    // warp-uniform
+      const unsigned m = __match_any_sync(0xffffffffu, lv[u]);
+      if (lv[u] != 255u && lane == __ffs(m) - 1) grp[g * C + lv[u]] = (uint16_t)__popc(m);
+    }
+  }
+  pa_sync_consumers();
+  // exclusive scan over the groups, one warp per class: lane owns 4 consecutive groups
+  for (int c = warp; c < C; c += kPaConsumers) {
+    int v[4], run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = lane * 4 + k;
+      v[k] = g < ng ? grp[g * C + c] : 0;
+      run += v[k];
+    }
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int excl = incl - run;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = lane * 4 + k;
+      if (g < ng) grp[g * C + c] = (uint16_t)excl;
+      excl += v[k];
+    }
+    if (lane == 31) tot[c] = incl;
+  }
+  pa_sync_consumers();
+  if (warp == 0) {                                   // padded segment offsets: scan over the classes
+    int carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      const int len = c < C ? (tot[c] + 31) & ~31 : 0;
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (c < C) seg[c] = carry + incl - len;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) seg[C] = carry;
+  }
+  pa_sync_consumers();
+#pragma unroll
+  for (int u = 0; u < kGroupsPerWarp; ++u) {
+    const int g = warp + u * kPaConsumers;
+    if (g < ng) {
+      const unsigned l = lv[u];
+      const unsigned m = __match_any_sync(0xffffffffu, l);
+      if (l != 255u) order[seg[l] + grp[g * C + l] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g * 32 + lane);
+    }
+  }
+  for (int c = warp; c < C; c += kPaConsumers) {              // pad every segment with the zero slot
+    const int j = seg[c] + tot[c] + lane;
+    if (j < seg[c + 1]) order[j] = (uint16_t)np;
+  }
+  // pixel counts: once per (image, tile), by channel group 0
+  if (grp_id == 0)
+    for (int c = threadIdx.x; c < C; c += kPaConsumers * 32)
+      if (tot[c]) atomicAdd(&packed[(int64_t)C * D + c], (float)tot[c]);
+  pa_sync_consumers();
+
+  // ---- consumers: one channel plane per warp per turn ------------------------------------
+  for (int i = warp; i < n_items; i += kPaConsumers) {
+    const int s = use_bulk ? i % stages : warp;
+    float* pl = planes + (size_t)s * L.plane_stride;
+    if (use_bulk) {
+      // A stage is consumed by a different warp on every revolution of the ring, and a parity
+      // wait is only meaningful within one phase of the barrier: this warp may get here before
+      // the PREVIOUS plane of the stage has even landed, and would then take that barrier's
+      // older phase for its own. Plane i is issued only after that previous plane was consumed,
+      // so wait for the issue first.
+      while (*reinterpret_cast<volatile int*>(&issued) <= i) {}
+      mbar_wait(&full_bar[s], (uint32_t)((i / stages) & 1));
+    } else {                             // planes a bulk copy cannot describe: the warp stages its own
+      const float* src = base + (int64_t)i * hw;
+      for (int e0 = lane; e0 < np; e0 += 32 * kPaUnroll) {
+        float v[kPaUnroll];
+#pragma unroll
+        for (int u = 0; u < kPaUnroll; ++u)
+          if (e0 + u * 32 < np) v[u] = __ldg(src + e0 + u * 32);
+#pragma unroll
+        for (int u = 0; u < kPaUnroll; ++u)
+          if (e0 + u * 32 < np) pl[e0 + u * 32] = v[u];
       }
       __syncwarp();
     }
-    for (int ch = c0 + warp; ch < c1; ch += kPrWarps) {
-      const float* src = feats + ((int64_t)b * D + ch) * hw + p0;
-      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (np % 4 == 0);
-      if (vec) {
-        for (int i = lane * 4; i < np; i += 128) {
-          const float4 v = ldg_stream_f4(src + i);
-          const uchar4 l = *reinterpret_cast<const uchar4*>(lab_s + i);
-          if (l.x != 255) my[l.x * 32 + lane] += v.x;
-          if (l.y != 255) my[l.y * 32 + lane] += v.y;
-          if (l.z != 255) my[l.z * 32 + lane] += v.z;
-          if (l.w != 255) my[l.w * 32 + lane] += v.w;
-        }
-      } else {
-        for (int i = lane; i < np; i += 32) {
-          const unsigned l = lab_s[i];
-          if (l != 255u) my[l * 32 + lane] += __ldg(src + i);
-        }
+    float* dst = packed + ch0 + i;
+    for (int c = 0; c < C; ++c) {
+      const int j1 = seg[c + 1];
+      int j = seg[c] + lane;
+      if (j >= j1) continue;             // class absent from this tile (segments are multiples of 32)
+      float a[kPaUnroll];
+#pragma unroll
+      for (int u = 0; u < kPaUnroll; ++u) a[u] = 0.f;
+      for (; j + 32 * (kPaUnroll - 1) < j1; j += 32 * kPaUnroll) {
+#pragma unroll
+        for (int u = 0; u < kPaUnroll; ++u) a[u] += pl[order[j + 32 * u]];
       }
-      __syncwarp();
-      for (int c = 0; c < C; ++c) {
-        const float v = warp_sum(my[c * 32 + lane]);
-        my[c * 32 + lane] = 0.f;
-        if (lane == 0 && v != 0.f) atomicAdd(&packed[(int64_t)c * D + ch], v);
-      }
-      __syncwarp();
+      for (; j < j1; j += 32) a[0] += pl[order[j]];
+      const float v = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
+      if (lane == 0) atomicAdd(dst + (int64_t)c * D, v);
     }
+    __syncwarp();
+    if (use_bulk && lane == 0) mbar_arrive(&empty_bar[s]);
   }
 }
 
-__global__ void proto_finalize_kernel(const float* __restrict__ packed, int C, int D,
-                                      const float* __restrict__ mu_prev, const uint8_t* __restrict__ seen_prev,
-                                      float a32, float b32, float* __restrict__ mu_out,
-                                      int64_t* __restrict__ cnt_out, uint8_t* __restrict__ seen_out) {
+__global__ void proto_finalize_kernel(float* __restrict__ packed, int C, int D,
+                                      const float* mu_prev, const uint8_t* seen_prev,
+                                      float a32, float b32, float* mu_out,
+                                      int64_t* __restrict__ cnt_out, uint8_t* seen_out, int reset) {
+  // mu_out may alias mu_prev and seen_out may alias seen_prev (in-place bank update): every
+  // element is read and written by the same thread, the per-class flags after a barrier.
   const int c = blockIdx.x;
   const float cnt = packed[(int64_t)C * D + c];
   const bool has = cnt > 0.f;
@@ -126,15 +262,32 @@ __global__ void proto_finalize_kernel(const float* __restrict__ packed, int C, i
     float out = prev;
     if (has) out = seen ? __fadd_rn(__fmul_rn(a32, prev), __fmul_rn(b32, mean)) : mean;
     mu_out[(int64_t)c * D + d] = out;
+    if (reset) packed[(int64_t)c * D + d] = 0.f;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     if (cnt_out) cnt_out[c] = (int64_t)cnt;
     if (seen_out) seen_out[c] = (has || seen) ? 1 : 0;
+    if (reset) packed[(int64_t)C * D + c] = 0.f;
   }
 }
 
 // ---- distance: block = 128 consecutive pixels of one image x all channels -------
 constexpr int kPdPix = 128;
+constexpr int kPdUnroll = 8;    // channel planes in flight per warp (backward: + grad read)
+constexpr int kPdUnrollFwd = 16;
+
+// four consecutive pixels of one channel plane (128-bit when the plane allows it)
+template <bool READ_ONLY = true>
+__device__ __forceinline__ void pd_load4(const float* p, bool vec, int pix, int hw, float (&v)[4]) {
+  if (vec) {
+    const float4 t = READ_ONLY ? ldg_stream_f4(p) : *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (pix + i < hw) ? (READ_ONLY ? __ldg(p + i) : p[i]) : 0.f;
+  }
+}
 
 struct PdCtx {
   int b, p0, hw;
@@ -179,19 +332,23 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   if (!BWD) {
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
     if (any_px)
-      for (int d = warp; d < D; d += kPrWarps) {
-        float v[4];
-        if (vec) {
-          const float4 t = ldg_stream_f4(src + (int64_t)d * hw);
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
+      for (int d0 = warp; d0 < D; d0 += kPrWarps * kPdUnrollFwd) {
+        float v[kPdUnrollFwd][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = (p0 + lane * 4 + i < hw) ? __ldg(src + (int64_t)d * hw + i) : 0.f;
+        for (int u = 0; u < kPdUnrollFwd; ++u) {
+          const int d = d0 + u * kPrWarps;
+          if (d < D) pd_load4(src + (int64_t)d * hw, vec, p0 + lane * 4, hw, v[u]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float df = v[i] - mu_s[lab[i] * (D + 1) + d];
-          ss[i] = fmaf(df, df, ss[i]);
+        for (int u = 0; u < kPdUnrollFwd; ++u) {
+          const int d = d0 + u * kPrWarps;
+          if (d < D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float df = v[u][i] - mu_s[lab[i] * (D + 1) + d];
+              ss[i] = fmaf(df, df, ss[i]);
+            }
+          }
         }
       }
 #pragma unroll
@@ -232,34 +389,35 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
     }
     float* dst = grad + (int64_t)b * D * hw + p0 + lane * 4;
     if (any_px)
-      for (int d = warp; d < D; d += kPrWarps) {
-        float v[4];
-        if (vec) {
-          const float4 t = ldg_stream_f4(src + (int64_t)d * hw);
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
+      for (int d0 = warp; d0 < D; d0 += kPrWarps * kPdUnroll) {
+        float v[kPdUnroll][4], o[kPdUnroll][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = (p0 + lane * 4 + i < hw) ? __ldg(src + (int64_t)d * hw + i) : 0.f;
-        }
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        if (accumulate) {   // grad += ... : the PFGST loss gradient is already in the buffer
-          if (vec) {
-            const float4 t = *reinterpret_cast<const float4*>(dst + (int64_t)d * hw);
-            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-          } else {
+        for (int u = 0; u < kPdUnroll; ++u) {
+          const int d = d0 + u * kPrWarps;
+          if (d < D) {
+            pd_load4(src + (int64_t)d * hw, vec, p0 + lane * 4, hw, v[u]);
+            if (accumulate) {   // grad += ... : the PFGST loss gradient is already in the buffer
+              pd_load4<false>(dst + (int64_t)d * hw, vec, p0 + lane * 4, hw, o[u]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (p0 + lane * 4 + i < hw) o[i] = dst[(int64_t)d * hw + i];
+              for (int i = 0; i < 4; ++i) o[u][i] = 0.f;
+            }
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = fmaf(coef[i], v[i] - mu_s[lab[i] * (D + 1) + d], o[i]);
-        if (vec) {
-          __stcs(reinterpret_cast<float4*>(dst + (int64_t)d * hw), make_float4(o[0], o[1], o[2], o[3]));
-        } else {
+        for (int u = 0; u < kPdUnroll; ++u) {
+          const int d = d0 + u * kPrWarps;
+          if (d < D) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (p0 + lane * 4 + i < hw) dst[(int64_t)d * hw + i] = o[i];
+            for (int i = 0; i < 4; ++i) o[u][i] = fmaf(coef[i], v[u][i] - mu_s[lab[i] * (D + 1) + d], o[u][i]);
+            if (vec) {
+              __stcs(reinterpret_cast<float4*>(dst + (int64_t)d * hw), make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (p0 + lane * 4 + i < hw) dst[(int64_t)d * hw + i] = o[u][i];
+            }
+          }
         }
       }
   }
@@ -307,29 +465,44 @@ int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_
                      float conf_thr, int32_t C, float* packed, void* stream) {
   if (!feats || !labels || !packed || B < 0 || D < 1 || h < 1 || w < 1 || lab_h < 1 || lab_w < 1 || C < 1)
     return PFST_ERR_INVALID_ARG;
-  if (C > pfst::kPrMaxC || B > 65535) return PFST_ERR_UNSUPPORTED;
+  if (C > pfst::kPrMaxC) return PFST_ERR_UNSUPPORTED;
   if (B == 0) return PFST_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = pfst::kPrPixTile + (size_t)pfst::kPrWarps * C * 32 * sizeof(float);
+  const int64_t hw = (int64_t)h * w;
+  const int tile = (int)(hw < pfst::kPaTile ? hw : pfst::kPaTile);
+  const int n_tiles = (int)((hw + tile - 1) / tile);
+  // bulk async copies need 16-byte aligned planes whose tiles are multiples of 16 bytes
+  int use_bulk = (hw % 4 == 0) && pfst::aligned16(feats) ? 1 : 0;
+  if (getenv("PFST_ACCUM_NO_BULK")) use_bulk = 0;   // debugging aid
+  // stages: as many as fit next to the sort buffers, at least one per consumer warp + 1
+  int stages = pfst::kPaMaxStages;
+  while (stages > pfst::kPaConsumers + 1 && pfst::pa_layout(tile, stages, C).total > 200 * 1024) --stages;
+  const pfst::PaLayout L = pfst::pa_layout(tile, stages, C);
+  if (L.total > 200 * 1024) return PFST_ERR_UNSUPPORTED;
   PFST_CUDA_TRY(cudaFuncSetAttribute(pfst::proto_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem), "pfst_proto_accum/attr");
-  // channel groups sized so that ~2 blocks per SM are in flight
-  int groups = (int)(((int64_t)pfst::kNumSMs * 2 + B - 1) / B);
-  int cpb = (D + groups - 1) / groups;
-  cpb = ((cpb + pfst::kPrWarps - 1) / pfst::kPrWarps) * pfst::kPrWarps;
-  groups = (D + cpb - 1) / cpb;
-  pfst::proto_accum_kernel<<<dim3((unsigned)groups, (unsigned)B), pfst::kPrThreads, smem, s>>>(
-      feats, (int)B, D, h, w, labels, conf, conf_thr, lab_h, lab_w, C, cpb, packed);
+                                     (int)L.total), "pfst_proto_accum/attr");
+  // channel groups: fill every SM's shared memory with blocks, keep >= 2 planes per consumer warp
+  int per_sm = (int)((220 * 1024) / (L.total + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
+  int64_t groups = ((int64_t)pfst::kNumSMs * per_sm) / (B * n_tiles);
+  const int64_t max_groups = (D + 2 * pfst::kPaConsumers - 1) / (2 * pfst::kPaConsumers);
+  if (groups > max_groups) groups = max_groups;
+  if (groups < 1) groups = 1;
+  const int64_t grid = B * n_tiles * groups;
+  if (grid > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+  pfst::proto_accum_kernel<<<(unsigned)grid, pfst::kPaThreads, L.total, s>>>(
+      feats, (int)B, D, h, w, labels, conf, conf_thr, lab_h, lab_w, C, (int)groups, tile, stages, use_bulk, packed);
   PFST_CHECK_LAUNCH("pfst_proto_accum");
   return PFST_OK;
 }
 
-int pfst_proto_finalize(const float* packed, int32_t C, int32_t D, const float* mu_prev,
+int pfst_proto_finalize(float* packed, int32_t C, int32_t D, const float* mu_prev,
                         const uint8_t* seen_prev, float a32, float b32, float* mu_out, int64_t* cnt_out,
-                        uint8_t* seen_out, void* stream) {
+                        uint8_t* seen_out, int32_t reset_packed, void* stream) {
   if (!packed || !mu_out || C < 1 || D < 1) return PFST_ERR_INVALID_ARG;
   pfst::proto_finalize_kernel<<<(unsigned)C, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      packed, C, D, mu_prev, seen_prev, a32, b32, mu_out, cnt_out, seen_out);
+      packed, C, D, mu_prev, seen_prev, a32, b32, mu_out, cnt_out, seen_out, reset_packed);
   PFST_CHECK_LAUNCH("pfst_proto_finalize");
   return PFST_OK;
 }

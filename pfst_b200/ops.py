@@ -242,15 +242,48 @@ def neigh_dots(x_a: torch.Tensor, x_b: Optional[torch.Tensor], dilation: int):
     return dots, ks
 
 
-def neigh_grad(x: torch.Tensor, coef: torch.Tensor, dilation: int) -> torch.Tensor:
+def neigh_dots_splits(B: int, D: int, h: int, w: int, n_tensors: int = 1) -> int:
+    return int(_lib.load().pfst_neigh_dots_splits(n_tensors, B, D, h, w))
+
+
+def neigh_dots_slot(x: torch.Tensor, dilation: int, slot: int, dots: Optional[torch.Tensor] = None,
+                    n_slots: int = 2):
+    """One feature tensor into slot `slot` of a (splits, n_slots, B, 5, h, w) dots buffer
+    (slot 0 = x_ema, slot 1 = x_src for the loss). -> (dots, splits)."""
+    _dev(x, "x", torch.float32)
+    B, D, h, w = x.shape
+    ks = neigh_dots_splits(B, D, h, w)
+    if dots is None:
+        dots = torch.empty((ks, n_slots, B, 5, h, w), dtype=torch.float32, device=x.device)
+    elif dots.numel() != ks * n_slots * B * 5 * h * w:
+        raise ValueError("dots buffer has the wrong size")
+    _lib.call("pfst_neigh_dots_slot", x.data_ptr(), B, D, h, w, int(dilation), int(slot), int(n_slots),
+              _dev(dots, "dots", torch.float32), _stream())
+    return dots, ks
+
+
+def neigh_grad(x: torch.Tensor, coef: torch.Tensor, dilation: int, out: Optional[torch.Tensor] = None,
+               proto: Optional[dict] = None) -> torch.Tensor:
+    """grad_x of the neighbourhood-cosine losses; with `proto` (labels (B,H,W) int64, mu, seen,
+    dist, acc, grad_loss — the saved state of pfst_proto_dist_fwd) the prototype-distance
+    gradient is added in the same pass over x."""
     _dev(x, "x", torch.float32)
     _dev(coef, "coef", torch.float32)
     B, D, h, w = x.shape
     if tuple(coef.shape) != (B, 9, h, w):
         raise ValueError("coef must be (B,9,h,w)")
-    grad = torch.empty_like(x)
-    _lib.call("pfst_neigh_grad", x.data_ptr(), coef.data_ptr(), B, D, h, w, int(dilation), grad.data_ptr(),
-              _stream())
+    grad = torch.empty_like(x) if out is None else out
+    _dev(grad, "grad_x", torch.float32)
+    if proto is None:
+        _lib.call("pfst_neigh_grad", x.data_ptr(), coef.data_ptr(), B, D, h, w, int(dilation), grad.data_ptr(),
+                  _stream())
+    else:
+        lab, mu, seen = proto["labels"], proto["mu"], proto.get("seen")
+        _lib.call("pfst_neigh_grad_proto", x.data_ptr(), coef.data_ptr(), B, D, h, w, int(dilation),
+                  _dev(lab, "labels", torch.int64), lab.shape[-2], lab.shape[-1], _dev(mu, "mu", torch.float32),
+                  _opt(seen, "seen", torch.uint8), mu.shape[0], _dev(proto["dist"], "dist", torch.float32),
+                  _dev(proto["acc"], "acc", torch.float64), _dev(proto["grad_loss"], "grad_loss", torch.float32),
+                  grad.data_ptr(), _stream())
     return grad
 
 

@@ -35,8 +35,6 @@ class PrototypeBank:
         self.mu = torch.zeros((self.C, self.D), dtype=torch.float32, device=self.device)
         self.seen = torch.zeros(self.C, dtype=torch.uint8, device=self.device)
         self.counts = torch.zeros(self.C, dtype=torch.int64, device=self.device)
-        self._mu_next = torch.empty_like(self.mu)
-        self._seen_next = torch.empty_like(self.seen)
         self.comm_stream = comm_stream
 
     # P1
@@ -64,12 +62,11 @@ class PrototypeBank:
         if work is not None:
             work.wait()
         a32, b32 = ops.ema_coeffs(max(self.iter, 1), self.alpha) if self.iter > 0 else (0.0, 1.0)
+        # in place (mu / seen keep their addresses: CUDA-graph friendly); the kernel also zeroes
+        # `packed` for the next step's accumulation
         _lib.call("pfst_proto_finalize", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
-                  self.seen.data_ptr(), a32, b32, self._mu_next.data_ptr(), self.counts.data_ptr(),
-                  self._seen_next.data_ptr(), ops._stream())
-        self.mu, self._mu_next = self._mu_next, self.mu
-        self.seen, self._seen_next = self._seen_next, self.seen
-        self.packed.zero_()
+                  self.seen.data_ptr(), a32, b32, self.mu.data_ptr(), self.counts.data_ptr(),
+                  self.seen.data_ptr(), 1, ops._stream())
         self.iter += 1
         return self.mu
 

@@ -129,6 +129,61 @@ def main():
         del imgs, trgs, labs
     keep.clear()
 
+    if want("feat"):
+        # the feature-tensor passes (cold: R rotating copies of each 67 MB tensor)
+        from pfst_b200 import _lib
+        from pfst_b200.prototypes import PrototypeBank
+        D, h, w = wl.D, inp["x_src"].shape[2], inp["x_src"].shape[3]
+        p = B * h * w
+        dil = wl.dilation
+        xs = [inp["x_src"].to(dev) + 0.0 for _ in range(R)]
+        gt = inp["gt"].to(dev)
+        lab3 = gt[:, 0].contiguous()
+        bank = PrototypeBank(C, D, dev)
+        report("proto_accum", 4 * D * p, lambda i: bank.accumulate(xs[i], lab3))
+        mu = bank.finalize()
+        geo = ops.LossGeometry(inp["logits_trg"].shape, inp["x_src"].shape, gt.shape,
+                               wl.downscale if wl.downscale != 1.0 else None, dil)
+        fd = geo.dilation // geo.up
+        dots, ks = ops.neigh_dots_slot(xs[0], fd, 0)
+        report("neigh_dots_slot", 4 * D * p, lambda i: ops.neigh_dots_slot(xs[i], fd, 1, dots))
+        ops.neigh_dots_slot(xs[1 % R], fd, 1, dots)
+        dist = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        acc = torch.empty(4, dtype=torch.float64, device=dev)
+        ploss = torch.empty(1, dtype=torch.float32, device=dev)
+
+        def dist_fwd(i):
+            _lib.call("pfst_proto_dist_fwd", xs[i].data_ptr(), B, D, h, w, lab3.data_ptr(), H, W, mu.data_ptr(),
+                      bank.seen.data_ptr(), C, dist.data_ptr(), acc.data_ptr(), ploss.data_ptr(), ops._stream())
+        report("proto_dist_fwd", 4 * D * p, dist_fwd)
+        logits = inp["logits_trg"].to(dev)
+        mix = (torch.rand((B, 1, H, W), generator=g) < 0.5).long().to(dev)
+        w6 = (0.1,) * 6
+        st = {}
+
+        def loss_fwd(i):
+            st["v"] = ops.pfgst_loss_fwd(dots, ks, geo, logits, gt, mix, 3, w6, want_vis=False)
+        report("pfgst_loss_fwd(prep+stats)", (2 * 5 * 4 * ks + 9 * 4 * 2) * p, loss_fwd)
+        gout = torch.ones(6, dtype=torch.float32, device=dev)
+        report("pfgst_loss_bwd", (2 * 5 * 4 + 9 * 4) * p,
+               lambda i: keep.append(ops.pfgst_loss_bwd(dots, ks, geo, logits, gt, mix, 3, w6, st["v"][1], gout)))
+        coef, _ = ops.pfgst_loss_bwd(dots, ks, geo, logits, gt, mix, 3, w6, st["v"][1], gout)
+        keep.clear()
+        grads = [torch.empty_like(xs[0]) for _ in range(R)]
+        report("neigh_grad", 8 * D * p, lambda i: ops.neigh_grad(xs[i], coef, fd, out=grads[i]))
+        dist_fwd(0)
+        gl = torch.full((1,), 0.1, dtype=torch.float32, device=dev)
+        pr = dict(labels=lab3, mu=mu, seen=bank.seen, dist=dist, acc=acc, grad_loss=gl)
+        report("neigh_grad_proto", 8 * D * p, lambda i: ops.neigh_grad(xs[i], coef, fd, out=grads[i], proto=pr))
+
+        def dist_bwd(i):
+            _lib.call("pfst_proto_dist_bwd", xs[i].data_ptr(), B, D, h, w, lab3.data_ptr(), H, W, mu.data_ptr(),
+                      bank.seen.data_ptr(), C, dist.data_ptr(), acc.data_ptr(), gl.data_ptr(),
+                      grads[i].data_ptr(), 0, ops._stream())
+        report("proto_dist_bwd", 8 * D * p, dist_bwd)
+        del xs, grads
+    keep.clear()
+
     if want("conf"):
         n = 16
         pred, gt = eval_maps(n, 1024, 1024, 6, seed=1)

@@ -20,7 +20,7 @@ inp = {k: v.to(dev) for k, v in step_inputs(wl, 1234).items()}
 student = [p.to(dev) for p in model_params(wl.C, g)]
 teacher = [p.to(dev) for p in model_params(wl.C, g)]
 step = SelfTrainingStep(teacher, student, wl.C, wl.D, dev, dilation=wl.dilation,
-                        downscale=wl.downscale if wl.downscale != 1.0 else None, max_batch=max(wl.B, 64))
+                        downscale=wl.downscale if wl.downscale != 1.0 else None, max_batch=max(wl.B, 64), graphs="--graphs" in sys.argv)
 
 
 def run(it):
