@@ -19,7 +19,6 @@
 
 namespace pfst {
 
-constexpr int kLossThreads = 64;
 constexpr int kMaxC = 64;   // classes held in registers per pixel
 
 struct LossParams {
@@ -57,136 +56,130 @@ __host__ __device__ inline size_t ws_floats(int B, int C, int fh, int fw, int up
 }
 
 // ---- prep: everything that is per-pixel (not per-neighbourhood), computed once --------
-__global__ void __launch_bounds__(kLossThreads)
-pfgst_loss_prep_kernel(const LossParams P) {
+// Two independent block ranges in one launch: [0, blocks_a) merge the channel-split dot
+// maps (one thread per (tensor, image, map, pixel); map 0 also yields the inverse norm),
+// the rest resample labels / masks and take the softmax (one thread per loss-grid pixel).
+constexpr int kPrepThreads = 128;
+
+__global__ void __launch_bounds__(kPrepThreads)
+pfgst_loss_prep_kernel(const LossParams P, int blocks_a) {
   const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
-  const int64_t nfeat = (int64_t)2 * P.B * fplane, nloss = (int64_t)P.B * gplane;
-  const int64_t i = (int64_t)blockIdx.x * kLossThreads + threadIdx.x;
-  if (i < nfeat) {
-    // (tensor t, image b, pixel r): merge the channel-split partial maps in a fixed order
-    const int64_t tb = i / fplane, r = i - tb * fplane;
-    const int64_t split_stride = (int64_t)2 * P.B * 5 * fplane;
-    float v[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const float* src = P.dots + (tb * 5 + k) * fplane + r;
-      float a = 0.f;
-      for (int sp = 0; sp < P.ksplit; ++sp) a += src[sp * split_stride];
-      v[k] = a;
-      P.dm[(tb * 5 + k) * fplane + r] = a;
-    }
-    P.invn[i] = 1.f / fmaxf(sqrtf(v[0]), 1e-8f);
+  if ((int)blockIdx.x < blocks_a) {
+    const int64_t n_a = (int64_t)2 * P.B * 5 * fplane;
+    const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    if (i >= n_a) return;
+    // i = ((tensor*B + image)*5 + map)*fplane + pixel: the same offset in every split
+    const int64_t split_stride = n_a;
+    const float* src = P.dots + i;
+    float a = 0.f;
+    for (int sp = 0; sp < P.ksplit; ++sp) a += src[sp * split_stride];   // fixed order: deterministic
+    P.dm[i] = a;
+    const int64_t tbk = i / fplane;
+    if (tbk % 5 == 0) P.invn[(tbk / 5) * fplane + (i - tbk * fplane)] = 1.f / fmaxf(sqrtf(a), 1e-8f);
+    return;
   }
-  if (i < nloss) {
-    const int b = (int)(i / gplane);
-    const int r = (int)(i - (int64_t)b * gplane);
-    const int y = r / P.gw, x = r - y * P.gw;
-    const int sy = nearest_src(y, P.gscale_h, P.gt_h), sx = nearest_src(x, P.gscale_w, P.gt_w);
-    const int64_t go = ((int64_t)b * P.gt_h + sy) * P.gt_w + sx;
-    const int64_t g = P.gt[go];
-    P.lab[i] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
-    P.flags[i] = (uint8_t)((g != 255 ? 1 : 0) | (P.mix[go] <= 0 ? 2 : 0));   // (1 - mix) > 0.5
-    // softmax of the nearest-resampled logits (pfgst_loss.py:57, 145)
-    const int ly = nearest_src(y, P.lscale_h, P.lh), lx = nearest_src(x, P.lscale_w, P.lw);
-    const float* z = P.logits + ((int64_t)b * P.C * P.lh + ly) * P.lw + lx;
-    const int64_t lplane = (int64_t)P.lh * P.lw;
-    float m = -INFINITY;
-    for (int c = 0; c < P.C; ++c) m = fmaxf(m, z[c * lplane]);
-    float s = 0.f;
-    for (int c = 0; c < P.C; ++c) s += expf(z[c * lplane] - m);
-    const float inv = 1.f / s;
-    float* po = P.prob + (int64_t)b * P.C * gplane + r;
-    for (int c = 0; c < P.C; ++c) po[c * gplane] = expf(z[c * lplane] - m) * inv;
-  }
+  const int64_t i = (int64_t)(blockIdx.x - blocks_a) * kPrepThreads + threadIdx.x;
+  if (i >= (int64_t)P.B * gplane) return;
+  const int b = (int)(i / gplane);
+  const int r = (int)(i - (int64_t)b * gplane);
+  const int y = r / P.gw, x = r - y * P.gw;
+  const int sy = nearest_src(y, P.gscale_h, P.gt_h), sx = nearest_src(x, P.gscale_w, P.gt_w);
+  const int64_t go = ((int64_t)b * P.gt_h + sy) * P.gt_w + sx;
+  const int64_t g = P.gt[go];
+  const int64_t mx = P.mix[go];
+  // softmax of the nearest-resampled logits (pfgst_loss.py:57, 145)
+  const int ly = nearest_src(y, P.lscale_h, P.lh), lx = nearest_src(x, P.lscale_w, P.lw);
+  const float* z = P.logits + ((int64_t)b * P.C * P.lh + ly) * P.lw + lx;
+  const int64_t lplane = (int64_t)P.lh * P.lw;
+  float m = -INFINITY;
+  for (int c = 0; c < P.C; ++c) m = fmaxf(m, z[c * lplane]);
+  float s = 0.f;
+  for (int c = 0; c < P.C; ++c) s += expf(z[c * lplane] - m);
+  const float inv = 1.f / s;
+  float* po = P.prob + (int64_t)b * P.C * gplane + r;
+  for (int c = 0; c < P.C; ++c) po[c * gplane] = expf(z[c * lplane] - m) * inv;
+  P.lab[i] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
+  P.flags[i] = (uint8_t)((g != 255 ? 1 : 0) | (mx <= 0 ? 2 : 0));   // (1 - mix) > 0.5
 }
 
-// Everything one loss-grid pixel needs from its 3x3 dilated neighbourhood.
-struct PixelNb {
-  bool inb[9];        // tap inside the loss grid
-  float s_ema[9];     // cos(x_ema[n], x_ema[n+delta_k]), 0 outside
-  float s_src[9];
-  float inv_n_src;    // 1 / max(|x_src[n]|, eps)
-  float inv_m_src[9]; // 1 / max(|x_src[n+delta_k]|, eps)
-  bool valid_src;     // gt != 255
-  bool pos_pair[9];   // unfold(gt)[k] == gt  (zero padding reads as class 0)
-  bool nb_valid[9];   // valid_src of the in-bounds neighbour
-  bool in_mk;         // valid_src && eroded target mask
-  bool eroded;
+// ---- one (tap, pixel) thread: warp = tap k (0..8), lane = pixel of the block's 32 ---------
+// The maps are tiny (a few MB); with one thread per pixel the GPU holds ~7 warps per SM and
+// the kernels are pure latency. Spreading the nine taps of a pixel over nine warps gives 9x
+// the parallelism, coalesced map reads along x, warp-uniform tap branches and no per-thread
+// arrays; the taps of a pixel meet in shared memory ([tap][pixel], bank = pixel).
+constexpr int kLpPix = 32;                 // pixels per block
+constexpr int kLpThreads = 9 * kLpPix;     // nine tap-warps
+
+struct Tap {
+  bool in;            // tap inside the loss grid
+  float s_ema, s_src; // cos(x[n], x[n+delta_k]) of the teacher / source features, 0 outside
+  float inv_m_src;    // 1 / max(|x_src[n+delta_k]|, eps), 0 outside
+  bool pos_pair;      // unfold(gt)[k] == gt[n]  (zero padding reads as class 0)
+  bool nb_valid;      // gt != 255 at the in-bounds neighbour
+  bool trg;           // neighbour is a target pixel (mix mask == 0)
+  int gm;             // loss-grid offset of the neighbour inside the image plane
 };
 
-__device__ __forceinline__ void load_pixel(const LossParams& P, int b, int y, int x, PixelNb& o) {
+struct Center {
+  int b, y, x;
+  bool valid_src;     // gt != 255
+  float inv_n_src;
+};
+
+__device__ __forceinline__ void load_tap(const LossParams& P, int k, int b, int y, int x, Center& c, Tap& t) {
   const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
-  const int fy = y / P.up, fx = x / P.up, fd = P.dil / P.up;
-  const int64_t fn = (int64_t)fy * P.fw + fx;
+  const int fy = P.up == 1 ? y : y / P.up, fx = P.up == 1 ? x : x / P.up, fd = P.up == 1 ? P.dil : P.dil / P.up;
+  const int fn = fy * P.fw + fx;
   const float* dme = P.dm + ((int64_t)(0 * P.B + b) * 5) * fplane;
   const float* dms = P.dm + ((int64_t)(1 * P.B + b) * 5) * fplane;
   const float* ine = P.invn + (int64_t)(0 * P.B + b) * fplane;
   const float* ins = P.invn + (int64_t)(1 * P.B + b) * fplane;
   const uint8_t* lab = P.lab + (int64_t)b * gplane;
   const uint8_t* flg = P.flags + (int64_t)b * gplane;
-  const float inv_ne = ine[fn], inv_ns = ins[fn];
-  o.inv_n_src = inv_ns;
-  const int g0 = lab[(int64_t)y * P.gw + x];
-  o.valid_src = (flg[(int64_t)y * P.gw + x] & 1) != 0;
-  bool er = true;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int oy = (k / 3 - 1), ox = (k % 3 - 1);
-    const int yy = y + oy * P.dil, xx = x + ox * P.dil;
-    const bool in = yy >= 0 && yy < P.gh && xx >= 0 && xx < P.gw;
-    o.inb[k] = in;
-    float se = 0.f, ss = 0.f, invm = 0.f;
-    int gk = 0;        // zero padding of unfold(gt.float())
-    bool trg = false, nbv = false;
-    if (in) {
-      const int64_t fm = (int64_t)(fy + oy * fd) * P.fw + (fx + ox * fd);
-      float de, ds;
-      if (k == 4)      { de = dme[fn]; ds = dms[fn]; }
-      // forward taps (k > 4) are stored at n, backward taps at the neighbour (symmetry)
-      else if (k > 4)  { de = dme[(k - 4) * fplane + fn]; ds = dms[(k - 4) * fplane + fn]; }
-      else             { de = dme[(4 - k) * fplane + fm]; ds = dms[(4 - k) * fplane + fm]; }
-      invm = ins[fm];
-      se = de * (inv_ne * ine[fm]);
-      ss = ds * (inv_ns * invm);
-      const int64_t gm = (int64_t)yy * P.gw + xx;
-      gk = lab[gm];
-      const unsigned f = flg[gm];
-      nbv = (f & 1u) != 0;
-      trg = (f & 2u) != 0;
-    }
-    o.s_ema[k] = se;
-    o.s_src[k] = ss;
-    o.inv_m_src[k] = invm;
-    o.pos_pair[k] = gk == g0;
-    o.nb_valid[k] = nbv;
-    er = er && in && trg;
+  const int gn = y * P.gw + x;
+  c.b = b; c.y = y; c.x = x;
+  c.valid_src = (flg[gn] & 1) != 0;
+  c.inv_n_src = ins[fn];
+  const int g0 = lab[gn];
+  const int oy = k / 3 - 1, ox = k % 3 - 1;
+  const int yy = y + oy * P.dil, xx = x + ox * P.dil;
+  t.in = yy >= 0 && yy < P.gh && xx >= 0 && xx < P.gw;
+  t.s_ema = 0.f; t.s_src = 0.f; t.inv_m_src = 0.f;
+  t.nb_valid = false; t.trg = false; t.gm = 0;
+  int gk = 0;          // zero padding of unfold(gt.float())
+  if (t.in) {
+    const int fm = (fy + oy * fd) * P.fw + (fx + ox * fd);
+    float de, ds;
+    if (k == 4)      { de = dme[fn]; ds = dms[fn]; }
+    // forward taps (k > 4) are stored at n, backward taps at the neighbour (symmetry)
+    else if (k > 4)  { de = dme[(k - 4) * fplane + fn]; ds = dms[(k - 4) * fplane + fn]; }
+    else             { de = dme[(4 - k) * fplane + fm]; ds = dms[(4 - k) * fplane + fm]; }
+    t.inv_m_src = ins[fm];
+    t.s_ema = de * (ine[fn] * ine[fm]);
+    t.s_src = ds * (c.inv_n_src * t.inv_m_src);
+    t.gm = yy * P.gw + xx;
+    gk = lab[t.gm];
+    const unsigned f = flg[t.gm];
+    t.nb_valid = (f & 1u) != 0;
+    t.trg = (f & 2u) != 0;
   }
-  o.eroded = er;
-  o.in_mk = er && o.valid_src;
+  t.pos_pair = gk == g0;
 }
 
-// softmax probabilities of loss-grid pixel (y,x), from the prep map
-__device__ __forceinline__ void softmax_at(const LossParams& P, int b, int y, int x, float* p) {
-  const int64_t gplane = (int64_t)P.gh * P.gw;
-  const float* src = P.prob + (int64_t)b * P.C * gplane + (int64_t)y * P.gw + x;
-  for (int c = 0; c < P.C; ++c) p[c] = src[c * gplane];
-}
-
-// rank of tap k among the nine similarities: number of taps strictly "before" it
-// in descending order, ties broken by the lower index.
-__device__ __forceinline__ void tap_ranks(const float (&s)[9], int (&rank_desc)[9], int (&rank_asc)[9]) {
+// rank of tap k among the nine similarities of pixel p (column p of s[9][kLpPix]): number of
+// taps strictly "before" it in descending / ascending order, ties broken by the lower index.
+__device__ __forceinline__ void tap_rank(const float (*s)[kLpPix], int p, int k, int& rank_desc, int& rank_asc) {
+  const float sk = s[k][p];
+  int rd = 0, ra = 0;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    int rd = 0, ra = 0;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      if (j == k) continue;
-      rd += (s[j] > s[k] || (s[j] == s[k] && j < k)) ? 1 : 0;
-      ra += (s[j] < s[k] || (s[j] == s[k] && j < k)) ? 1 : 0;
-    }
-    rank_desc[k] = rd;
-    rank_asc[k] = ra;
+  for (int j = 0; j < 9; ++j) {
+    const float sj = s[j][p];
+    const bool first = j < k;
+    rd += (j != k && (sj > sk || (sj == sk && first))) ? 1 : 0;
+    ra += (j != k && (sj < sk || (sj == sk && first))) ? 1 : 0;
   }
+  rank_desc = rd;
+  rank_asc = ra;
 }
 
 // stats layout (fp64): 0 n_pos, 1 sum_pos, 2 sumsq_pos, 3 n_neg, 4 sum_neg, 5 sumsq_neg,
@@ -207,82 +200,86 @@ __device__ __forceinline__ void finalize_losses(const LossParams& P, const doubl
   losses[5] = any ? (float)(st[8] / (mk * (double)P.top_k)) * P.w_sim_neg : 0.f;
 }
 
-__global__ void __launch_bounds__(kLossThreads)
+__global__ void __launch_bounds__(kLpThreads)
 pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __restrict__ losses,
                       float* __restrict__ density, uint8_t* __restrict__ eroded_out,
                       unsigned* __restrict__ done_counter) {
-  __shared__ double red[kNumStats][kLossThreads / 32];
+  __shared__ float s_se[9][kLpPix];
+  __shared__ uint8_t s_ok[9][kLpPix];        // tap in bounds and on a target pixel (erosion)
+  __shared__ double red[kNumStats][9];
+  const int k = threadIdx.x >> 5, p = threadIdx.x & 31;     // warp = tap, lane = pixel
   const int64_t plane = (int64_t)P.gh * P.gw;
-  const int64_t total = (int64_t)P.B * plane;
+  // grid = (row segments of 32 pixels, rows, images): no index divisions
+  const int b = blockIdx.z, y = blockIdx.y, x = blockIdx.x * kLpPix + p;
+  const bool live = x < P.gw;
+  const int64_t n = (int64_t)b * plane + (int64_t)y * P.gw + x;
   double acc[kNumStats];
 #pragma unroll
   for (int i = 0; i < kNumStats; ++i) acc[i] = 0.0;
 
-  for (int64_t n = (int64_t)blockIdx.x * kLossThreads + threadIdx.x; n < total;
-       n += (int64_t)gridDim.x * kLossThreads) {
-    const int b = (int)(n / plane);
-    const int r = (int)(n - (int64_t)b * plane);
-    const int y = r / P.gw, x = r - y * P.gw;
-    PixelNb px;
-    load_pixel(P, b, y, x, px);
-
+  Center c;
+  Tap t;
+  if (live) {
+    load_tap(P, k, b, y, x, c, t);
     // L4: source pair statistics (pfgst_loss.py:85-113)
-    if (px.valid_src) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double s = (double)px.s_src[k];
-        if (px.pos_pair[k]) { acc[0] += 1.0; acc[1] += s; acc[2] += s * s; }
-        else                { acc[3] += 1.0; acc[4] += s; acc[5] += s * s; }
-      }
+    if (c.valid_src) {
+      const double s = (double)t.s_src;
+      if (t.pos_pair) { acc[0] = 1.0; acc[1] = s; acc[2] = s * s; }
+      else            { acc[3] = 1.0; acc[4] = s; acc[5] = s * s; }
     }
-    float mean_e = 0.f;
+    s_se[k][p] = t.s_ema;
+    s_ok[k][p] = (t.in && t.trg) ? 1 : 0;
+  } else {
+    s_se[k][p] = 0.f;
+    s_ok[k][p] = 0;
+  }
+  __syncthreads();
+  if (live) {
+    bool er = true;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) mean_e += px.s_ema[k];
-    if (density) density[n] = 1.f - mean_e / 9.f;
-    if (eroded_out) eroded_out[n] = px.eroded ? 1 : 0;
-
-    // L3 + L5: target consistency terms on Mk
-    if (px.in_mk) {
-      float p[kMaxC], q[kMaxC];
-      softmax_at(P, b, y, x, p);
-      int rd[9], ra[9];
-      tap_ranks(px.s_ema, rd, ra);
-      float lp = 0.f, ln = 0.f;
+    for (int j = 0; j < 9; ++j) er = er && s_ok[j][p] != 0;
+    if (k == 0) {
+      float mean_e = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const bool top = rd[k] < P.top_k + 1, bot = ra[k] < P.top_k;
-        if (!top && !bot) continue;
-        // every tap of an Mk pixel is in bounds (eroded mask)
-        softmax_at(P, b, y + (k / 3 - 1) * P.dil, x + (k % 3 - 1) * P.dil, q);
+      for (int j = 0; j < 9; ++j) mean_e += s_se[j][p];
+      if (density) density[n] = 1.f - mean_e / 9.f;
+      if (eroded_out) eroded_out[n] = er ? 1 : 0;
+    }
+    // L3 + L5: target consistency terms on Mk (every tap of an Mk pixel is in bounds)
+    if (er && c.valid_src) {
+      int rd, ra;
+      tap_rank(s_se, p, k, rd, ra);
+      const bool top = rd < P.top_k + 1, bot = ra < P.top_k;
+      if (top || bot) {
+        const float* pn = P.prob + (int64_t)c.b * P.C * plane + (int64_t)c.y * P.gw + c.x;
+        const float* pm = P.prob + (int64_t)c.b * P.C * plane + t.gm;
         float cp = 0.f;
-        for (int c = 0; c < P.C; ++c) cp = fmaf(p[c], q[c], cp);
-        if (top) lp += px.s_ema[k] * (-cp);
-        if (bot) ln += (1.f - px.s_ema[k]) * (-(1.f - cp));
+        for (int cc = 0; cc < P.C; ++cc) cp = fmaf(pn[cc * plane], pm[cc * plane], cp);
+        if (top) acc[7] = (double)(t.s_ema * (-cp));
+        if (bot) acc[8] = (double)((1.f - t.s_ema) * (-(1.f - cp)));
       }
-      acc[6] += 1.0;
-      acc[7] += (double)lp;
-      acc[8] += (double)ln;
+      if (k == 4) acc[6] = 1.0;
     }
   }
 
   // block reduction -> one fp64 atomic per statistic per block
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < kNumStats; ++i) {
     const double v = warp_sum(acc[i]);
-    if (lane == 0) red[i][warp] = v;
+    if (p == 0) red[i][k] = v;
   }
   __syncthreads();
   if (threadIdx.x < kNumStats) {
     double v = 0.0;
-    for (int wv = 0; wv < kLossThreads / 32; ++wv) v += red[threadIdx.x][wv];
+    for (int wv = 0; wv < 9; ++wv) v += red[threadIdx.x][wv];
     if (v != 0.0) atomicAdd(&stats[threadIdx.x], v);
+    __threadfence();
   }
   // last block finalises the six losses on the device (no host round trip)
   __shared__ bool is_last;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0)
+    is_last = atomicAdd(done_counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
     __threadfence();
@@ -292,87 +289,147 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
   }
 }
 
-// One thread per FEATURE-grid pixel (loops over its up x up loss-grid pixels).
-__global__ void __launch_bounds__(kLossThreads)
+// Block = 32 FEATURE-grid pixels x nine taps; loops over the up x up loss-grid pixels of a
+// feature pixel (up = 1 unless the features are coarser than the loss grid).
+constexpr int kLpMaxOwn = (kMaxC + 8) / 9;     // classes a tap-thread owns in the logits gradient
+
+__global__ void __launch_bounds__(kLpThreads)
 pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, const float* __restrict__ gout,
                       float* __restrict__ coef, float* __restrict__ grad_logits) {
-  const int64_t fplane = (int64_t)P.fh * P.fw;
-  const int64_t total = (int64_t)P.B * fplane;
-  const int64_t n = (int64_t)blockIdx.x * kLossThreads + threadIdx.x;
-  if (n >= total) return;
-  const int b = (int)(n / fplane);
-  const int r = (int)(n - (int64_t)b * fplane);
-  const int fy = r / P.fw, fx = r - fy * P.fw;
+  __shared__ float s_se[9][kLpPix];
+  __shared__ uint8_t s_ok[9][kLpPix];
+  __shared__ float s_bs[9][kLpPix];           // W * S of every tap (centre-tap coefficient)
+  __shared__ float s_dcp[9][kLpPix];          // d loss / d cross-prob of every tap
+  __shared__ int s_gm[9][kLpPix];             // neighbour offsets (for the class-parallel pass)
+  __shared__ float s_dot[9][kLpPix];
+  const int k = threadIdx.x >> 5, p = threadIdx.x & 31;
+  const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
+  // grid = (row segments of 32 feature pixels, feature rows, images)
+  const int b = blockIdx.z, fy = blockIdx.y, fx = blockIdx.x * kLpPix + p;
+  const bool live = fx < P.fw;
+  const int r = fy * P.fw + fx;
 
-  const double n_pos = stats[0], n_neg = stats[3], mk = stats[6];
-  const double mean_pos = stats[1] / n_pos, mean_neg = stats[4] / n_neg;
-  const double std_pos = sqrt(fmax((stats[2] - n_pos * mean_pos * mean_pos) / (n_pos - 1.0), 0.0));
-  const double std_neg = sqrt(fmax((stats[5] - n_neg * mean_neg * mean_neg) / (n_neg - 1.0), 0.0));
-  // d loss / d S for a positive / negative source pair:  a + c * (S - mean)
-  const float a_pos = (float)(-(double)gout[0] * P.w_src_pos / n_pos);
-  const float c_pos = (float)((double)gout[2] * P.w_src_pos_std / ((n_pos - 1.0) * std_pos));
-  const float a_neg = (float)((double)gout[1] * P.w_src_neg / n_neg);
-  const float c_neg = (float)((double)gout[3] * P.w_src_neg_std / ((n_neg - 1.0) * std_neg));
-  const float fmean_pos = (float)mean_pos, fmean_neg = (float)mean_neg;
-  const bool any = mk > 1.0;
-  const float g_pos = any ? (float)((double)gout[4] * P.w_sim_pos / (mk * (double)(P.top_k + 1))) : 0.f;
-  const float g_neg = any ? (float)((double)gout[5] * P.w_sim_neg / (mk * (double)P.top_k)) : 0.f;
+  // the backward constants (fp64 divisions and square roots) once per block, not per thread
+  __shared__ float s_k[8];
+  __shared__ int s_any;
+  if (threadIdx.x == 0) {
+    const double n_pos = stats[0], n_neg = stats[3], mk = stats[6];
+    const double mean_pos = stats[1] / n_pos, mean_neg = stats[4] / n_neg;
+    const double std_pos = sqrt(fmax((stats[2] - n_pos * mean_pos * mean_pos) / (n_pos - 1.0), 0.0));
+    const double std_neg = sqrt(fmax((stats[5] - n_neg * mean_neg * mean_neg) / (n_neg - 1.0), 0.0));
+    const bool any_ = mk > 1.0;
+    // d loss / d S for a positive / negative source pair:  a + c * (S - mean)
+    s_k[0] = (float)(-(double)gout[0] * P.w_src_pos / n_pos);
+    s_k[1] = (float)((double)gout[2] * P.w_src_pos_std / ((n_pos - 1.0) * std_pos));
+    s_k[2] = (float)((double)gout[1] * P.w_src_neg / n_neg);
+    s_k[3] = (float)((double)gout[3] * P.w_src_neg_std / ((n_neg - 1.0) * std_neg));
+    s_k[4] = (float)mean_pos;
+    s_k[5] = (float)mean_neg;
+    s_k[6] = any_ ? (float)((double)gout[4] * P.w_sim_pos / (mk * (double)(P.top_k + 1))) : 0.f;
+    s_k[7] = any_ ? (float)((double)gout[5] * P.w_sim_neg / (mk * (double)P.top_k)) : 0.f;
+    s_any = any_ ? 1 : 0;
+  }
+  __syncthreads();
+  const float a_pos = s_k[0], c_pos = s_k[1], a_neg = s_k[2], c_neg = s_k[3];
+  const float fmean_pos = s_k[4], fmean_neg = s_k[5], g_pos = s_k[6], g_neg = s_k[7];
+  const bool any = s_any != 0;
+  const bool want_logits = grad_logits != nullptr && any;     // block-uniform
 
-  float cf[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) cf[k] = 0.f;
-
+  float cf = 0.f;
   for (int uy = 0; uy < P.up; ++uy)
     for (int ux = 0; ux < P.up; ++ux) {
       const int y = fy * P.up + uy, x = fx * P.up + ux;
-      PixelNb px;
-      load_pixel(P, b, y, x, px);
-      // --- x_src: gather-form coefficients ---
-      float bsum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        if (k == 4 || !px.inb[k]) continue;
-        const float S = px.s_src[k];
-        const float g = px.pos_pair[k] ? a_pos + c_pos * (S - fmean_pos) : a_neg + c_neg * (S - fmean_neg);
-        // the pair (n, m) is counted once from n (if n is valid) and once from m (if m is valid)
-        const float W = g * ((px.valid_src ? 1.f : 0.f) + (px.nb_valid[k] ? 1.f : 0.f));
-        cf[k] += W * px.inv_n_src * px.inv_m_src[k];
-        bsum += W * S;
+      Center c;
+      Tap t;
+      float bs = 0.f;
+      c.valid_src = false; c.inv_n_src = 0.f; c.b = b; c.y = y; c.x = x;
+      t.in = false; t.s_ema = 0.f; t.trg = false; t.gm = 0;
+      if (live) {
+        load_tap(P, k, b, y, x, c, t);
+        // --- x_src: gather-form coefficients ---
+        if (k != 4 && t.in) {
+          const float S = t.s_src;
+          const float g = t.pos_pair ? a_pos + c_pos * (S - fmean_pos) : a_neg + c_neg * (S - fmean_neg);
+          // the pair (n, m) is counted once from n (if n is valid) and once from m (if m is valid)
+          const float W = g * ((c.valid_src ? 1.f : 0.f) + (t.nb_valid ? 1.f : 0.f));
+          cf += W * c.inv_n_src * t.inv_m_src;
+          bs = W * S;
+        }
       }
-      cf[4] -= bsum * px.inv_n_src * px.inv_n_src;
-
-      // --- logits_trg: through p only (q detached) ---
-      if (grad_logits && px.in_mk && any) {
-        float p[kMaxC], q[kMaxC], dp[kMaxC];
-        softmax_at(P, b, y, x, p);
-        for (int c = 0; c < P.C; ++c) dp[c] = 0.f;
-        int rd[9], ra[9];
-        tap_ranks(px.s_ema, rd, ra);
+      s_bs[k][p] = bs;
+      s_se[k][p] = t.s_ema;
+      s_ok[k][p] = (live && t.in && t.trg) ? 1 : 0;
+      s_gm[k][p] = t.gm;
+      __syncthreads();
+      if (live && k == 4) {
+        float bsum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const bool top = rd[k] < P.top_k + 1, bot = ra[k] < P.top_k;
-          if (!top && !bot) continue;
+        for (int j = 0; j < 9; ++j) bsum += s_bs[j][p];
+        cf -= bsum * c.inv_n_src * c.inv_n_src;
+      }
+      if (want_logits) {
+        // --- logits_trg: through p only (q detached) ---
+        bool er = live;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) er = er && s_ok[j][p] != 0;
+        const bool in_mk = er && c.valid_src;
+        float dcp = 0.f;
+        if (in_mk) {
+          int rd, ra;
+          tap_rank(s_se, p, k, rd, ra);
+          const bool top = rd < P.top_k + 1, bot = ra < P.top_k;
           // d/dcp of  -S*cp  and of  -(1-S)*(1-cp)
-          const float dcp = (top ? -px.s_ema[k] * g_pos : 0.f) + (bot ? (1.f - px.s_ema[k]) * g_neg : 0.f);
-          softmax_at(P, b, y + (k / 3 - 1) * P.dil, x + (k % 3 - 1) * P.dil, q);
-          for (int c = 0; c < P.C; ++c) dp[c] = fmaf(dcp, q[c], dp[c]);
+          dcp = (top ? -t.s_ema * g_pos : 0.f) + (bot ? (1.f - t.s_ema) * g_neg : 0.f);
         }
-        float dot = 0.f;
-        for (int c = 0; c < P.C; ++c) dot = fmaf(p[c], dp[c], dot);
-        const int sy = nearest_src(y, P.lscale_h, P.lh), sx = nearest_src(x, P.lscale_w, P.lw);
-        float* gz = grad_logits + ((int64_t)b * P.C * P.lh + sy) * P.lw + sx;
-        const int64_t lplane = (int64_t)P.lh * P.lw;
-        // several loss pixels can map to one logit only when the logits are UP-sampled
-        // (lscale < 1); accumulate then, plain store otherwise
-        const bool shared_src = P.lscale_h < 1.f || P.lscale_w < 1.f;
-        for (int c = 0; c < P.C; ++c) {
-          const float v = p[c] * (dp[c] - dot);
-          if (shared_src) atomicAdd(gz + c * lplane, v); else gz[c * lplane] = v;
+        s_dcp[k][p] = dcp;
+        __syncthreads();
+        // class-parallel: this thread owns classes k, k+9, ... of pixel p
+        float dp[kLpMaxOwn], pc[kLpMaxOwn];
+        float part = 0.f;
+        const float* pb = P.prob + (int64_t)b * P.C * gplane;
+        if (in_mk) {
+#pragma unroll
+          for (int j = 0; j < kLpMaxOwn; ++j) {
+            const int cc = k + 9 * j;
+            dp[j] = 0.f; pc[j] = 0.f;
+            if (cc < P.C) {
+              float d = 0.f;
+#pragma unroll
+              for (int kk = 0; kk < 9; ++kk) {
+                const float w = s_dcp[kk][p];
+                if (w != 0.f) d = fmaf(w, pb[cc * gplane + s_gm[kk][p]], d);
+              }
+              dp[j] = d;
+              pc[j] = pb[cc * gplane + (int64_t)y * P.gw + x];
+              part = fmaf(pc[j], d, part);
+            }
+          }
+        }
+        s_dot[k][p] = part;
+        __syncthreads();
+        if (in_mk) {
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) dot += s_dot[j][p];
+          const int sy = nearest_src(y, P.lscale_h, P.lh), sx = nearest_src(x, P.lscale_w, P.lw);
+          float* gz = grad_logits + ((int64_t)b * P.C * P.lh + sy) * P.lw + sx;
+          const int64_t lplane = (int64_t)P.lh * P.lw;
+          // several loss pixels can map to one logit only when the logits are UP-sampled
+          // (lscale < 1); accumulate then, plain store otherwise
+          const bool shared_src = P.lscale_h < 1.f || P.lscale_w < 1.f;
+#pragma unroll
+          for (int j = 0; j < kLpMaxOwn; ++j) {
+            const int cc = k + 9 * j;
+            if (cc < P.C) {
+              const float v = pc[j] * (dp[j] - dot);
+              if (shared_src) atomicAdd(gz + cc * lplane, v); else gz[cc * lplane] = v;
+            }
+          }
         }
       }
+      __syncthreads();     // the shared arrays are rewritten by the next loss pixel
     }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) coef[((int64_t)b * 9 + k) * fplane + r] = cf[k];
+  if (live) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
 }
 
 static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, int fh, int fw, int up,
@@ -425,19 +482,18 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
   // stats[0..8] fp64 sums, stats[15] doubles as the block-completion counter
   PFST_CUDA_TRY(cudaMemsetAsync(stats, 0, 16 * sizeof(double), s), "pfst_pfgst_loss_fwd/memset");
   const int64_t total = (int64_t)P.B * P.gh * P.gw;
+  if (total == 0) return PFST_OK;
   {
-    const int64_t nfeat = (int64_t)2 * P.B * fh * fw;
-    const int64_t n = nfeat > total ? nfeat : total;
-    if (n == 0) return PFST_OK;
-    pfst::pfgst_loss_prep_kernel<<<(unsigned)((n + pfst::kLossThreads - 1) / pfst::kLossThreads),
-                                   pfst::kLossThreads, 0, s>>>(P);
+    const int64_t n_a = (int64_t)2 * P.B * 5 * fh * fw;
+    const int64_t blocks_a = (n_a + pfst::kPrepThreads - 1) / pfst::kPrepThreads;
+    const int64_t blocks_b = (total + pfst::kPrepThreads - 1) / pfst::kPrepThreads;
+    if (blocks_a + blocks_b > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+    pfst::pfgst_loss_prep_kernel<<<(unsigned)(blocks_a + blocks_b), pfst::kPrepThreads, 0, s>>>(P, (int)blocks_a);
     PFST_CHECK_LAUNCH("pfst_pfgst_loss_fwd/prep");
   }
-  int64_t grid = (total + pfst::kLossThreads - 1) / pfst::kLossThreads;
-  const int64_t cap = (int64_t)pfst::kNumSMs * 16;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  pfst::pfgst_loss_fwd_kernel<<<(unsigned)grid, pfst::kLossThreads, 0, s>>>(
+  if (P.gh > 65535 || P.B > 65535) return PFST_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)((P.gw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)P.gh, (unsigned)P.B);
+  pfst::pfgst_loss_fwd_kernel<<<grid, pfst::kLpThreads, 0, s>>>(
       P, stats, losses, density, eroded, reinterpret_cast<unsigned*>(stats + 15));
   PFST_CHECK_LAUNCH("pfst_pfgst_loss_fwd");
   return PFST_OK;
@@ -460,9 +516,9 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                   "pfst_pfgst_loss_bwd/memset");
   const int64_t total = (int64_t)P.B * fh * fw;
   if (total == 0) return PFST_OK;
-  const int64_t grid = (total + pfst::kLossThreads - 1) / pfst::kLossThreads;
-  pfst::pfgst_loss_bwd_kernel<<<(unsigned)grid, pfst::kLossThreads, 0, s>>>(P, stats, grad_losses, coef,
-                                                                           grad_logits);
+  if (fh > 65535 || P.B > 65535) return PFST_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)((fw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)fh, (unsigned)P.B);
+  pfst::pfgst_loss_bwd_kernel<<<grid, pfst::kLpThreads, 0, s>>>(P, stats, grad_losses, coef, grad_logits);
   PFST_CHECK_LAUNCH("pfst_pfgst_loss_bwd");
   return PFST_OK;
 }

@@ -47,14 +47,15 @@ constexpr int kPaUnroll = 8;
 
 struct PaLayout {      // dynamic shared memory carve-up (host and device agree through this)
   int tile, stages, plane_stride;   // plane_stride: floats per stage (tile + 4: zero slot, 16 B aligned)
-  size_t off_order, off_grp, off_seg, total;
+  size_t off_order, off_grp, off_rows, off_seg, total;
 };
 __host__ __device__ inline PaLayout pa_layout(int tile, int stages, int C) {
   PaLayout L;
   L.tile = tile; L.stages = stages; L.plane_stride = ((tile + 3) / 4) * 4 + 4;
   size_t o = (size_t)stages * L.plane_stride * sizeof(float);
-  L.off_order = o; o += ((size_t)(tile + 32 * C) * 2 + 15) / 16 * 16;       // u16 offsets
+  L.off_order = o; o += ((size_t)(tile + 32 * C + 256) * 2 + 15) / 16 * 16;  // u16 offsets (+ a padding block of rows)
   L.off_grp = o;   o += ((size_t)((tile + 31) / 32) * C * 2 + 15) / 16 * 16;  // u16 [groups][C]
+  L.off_rows = o;  o += ((size_t)((tile + 31) / 32 + C + 8) + 15) / 16 * 16;   // u8 class of every 32-entry row
   L.off_seg = o;   o += (size_t)(2 * C + 2) * sizeof(int);                    // seg[C+1], tot[C]
   L.total = o;
   return L;
@@ -76,6 +77,7 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   float* planes = reinterpret_cast<float*>(pa_smem);
   uint16_t* order = reinterpret_cast<uint16_t*>(pa_smem + L.off_order);
   uint16_t* grp = reinterpret_cast<uint16_t*>(pa_smem + L.off_grp);
+  uint8_t* rowcls = pa_smem + L.off_rows;
   int* seg = reinterpret_cast<int*>(pa_smem + L.off_seg);
   int* tot = seg + C + 1;
 
@@ -123,10 +125,23 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   for (int i = threadIdx.x; i < ng * C; i += kPaConsumers * 32) grp[i] = 0;
   // all label gathers of this warp's groups in flight at once (one memory latency, not 16)
   unsigned lv[kGroupsPerWarp];
+  {
+    int64_t off[kGroupsPerWarp], raw[kGroupsPerWarp];
 #pragma unroll
-  for (int u = 0; u < kGroupsPerWarp; ++u) {
-    const int p = (warp + u * kPaConsumers) * 32 + lane;
-    lv[u] = p < np ? (unsigned)pr_label(labels, conf, conf_thr, b, p0 + p, w, lab_h, lab_w, sh, sw, C) : 255u;
+    for (int u = 0; u < kGroupsPerWarp; ++u) {           // addresses first ...
+      const int p = p0 + (warp + u * kPaConsumers) * 32 + lane;
+      const int y = p / w, x = p - y * w;
+      off[u] = ((int64_t)b * lab_h + pr_nearest(y, sh, lab_h)) * lab_w + pr_nearest(x, sw, lab_w);
+    }
+#pragma unroll
+    for (int u = 0; u < kGroupsPerWarp; ++u)             // ... then every load back to back
+      raw[u] = (warp + u * kPaConsumers) * 32 + lane < np ? __ldg(labels + off[u]) : (int64_t)-1;
+#pragma unroll
+    for (int u = 0; u < kGroupsPerWarp; ++u) {
+      bool ok = raw[u] >= 0 && raw[u] < C;
+      if (conf && ok) ok = __ldg(conf + off[u]) >= conf_thr;
+      lv[u] = ok ? (unsigned)raw[u] : 255u;
+    }
   }
   pa_sync_consumers();
 #pragma unroll
@@ -192,6 +207,12 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   for (int c = warp; c < C; c += kPaConsumers) {              // pad every segment with the zero slot
     const int j = seg[c] + tot[c] + lane;
     if (j < seg[c + 1]) order[j] = (uint16_t)np;
+    for (int r = seg[c] / 32 + lane; r < seg[c + 1] / 32; r += 32) rowcls[r] = (uint8_t)c;
+  }
+  {   // rows are consumed eight at a time: pad the list to a multiple of 8 rows (class 255, zero slot)
+    const int n_rows = seg[C] / 32, n_pad = ((n_rows + 7) & ~7) - n_rows;
+    for (int i = threadIdx.x; i < n_pad * 32; i += kPaConsumers * 32) order[n_rows * 32 + i] = (uint16_t)np;
+    if (threadIdx.x < n_pad) rowcls[n_rows + threadIdx.x] = 255;
   }
   // pixel counts: once per (image, tile), by channel group 0
   if (grp_id == 0)
@@ -225,20 +246,39 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
       __syncwarp();
     }
     float* dst = packed + ch0 + i;
-    for (int c = 0; c < C; ++c) {
-      const int j1 = seg[c + 1];
-      int j = seg[c] + lane;
-      if (j >= j1) continue;             // class absent from this tile (segments are multiples of 32)
-      float a[kPaUnroll];
+    // walk the class-sorted list 8 rows (256 offsets) at a time: 16 independent shared loads in
+    // flight per lane, the class of a row is warp-uniform, a class boundary costs one reduction
+    const int n_rows8 = (seg[C] / 32 + 7) / 8;
+    unsigned cur = 255u;
+    float run = 0.f;
+    for (int r8 = 0; r8 < n_rows8; ++r8) {
+      const uint2 cls = *reinterpret_cast<const uint2*>(rowcls + r8 * 8);
+      const uint16_t* op = order + r8 * 256 + lane;
+      float v[8];
 #pragma unroll
-      for (int u = 0; u < kPaUnroll; ++u) a[u] = 0.f;
-      for (; j + 32 * (kPaUnroll - 1) < j1; j += 32 * kPaUnroll) {
+      for (int u = 0; u < 8; ++u) v[u] = pl[op[32 * u]];
+      const unsigned same = cur * 0x01010101u;
+      if (cls.x == same && cls.y == same) {
+        run += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      } else {
 #pragma unroll
-        for (int u = 0; u < kPaUnroll; ++u) a[u] += pl[order[j + 32 * u]];
+        for (int u = 0; u < 8; ++u) {
+          const unsigned c = ((u < 4 ? cls.x : cls.y) >> (8 * (u & 3))) & 0xffu;
+          if (c != cur) {                                  // warp-uniform
+            if (cur != 255u) {
+              const float t = warp_sum(run);
+              if (lane == 0) atomicAdd(dst + (int64_t)cur * D, t);
+            }
+            cur = c;
+            run = 0.f;
+          }
+          run += v[u];
+        }
       }
-      for (; j < j1; j += 32) a[0] += pl[order[j]];
-      const float v = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
-      if (lane == 0) atomicAdd(dst + (int64_t)c * D, v);
+    }
+    if (cur != 255u) {
+      const float t = warp_sum(run);
+      if (lane == 0) atomicAdd(dst + (int64_t)cur * D, t);
     }
     __syncwarp();
     if (use_bulk && lane == 0) mbar_arrive(&empty_bar[s]);

@@ -28,4 +28,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(10):
         run(10 + i)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+rows = [(e.key, e.device_time_total / max(e.count, 1), e.count) for e in prof.key_averages() if e.device_time_total > 0]
+tot = sum(t * c for _, t, c in rows) / 10
+for name, t, c in sorted(rows, key=lambda r: -r[1] * r[2]):
+    print(f"{t:9.2f} us x{c // 10 if c >= 10 else c:<3d} {name[:90]}")
+print(f"{tot:9.2f} us  device time per step (sum over kernels, memsets and copies)")
