@@ -70,6 +70,16 @@ int pfst_ema_update_multi(float* const* ema_ptrs, const float* const* param_ptrs
                           void* stream);
 
 /* Same arithmetic over one flat buffer (e.g. a flattened parameter bucket).   */
+/* pfst_ema_update_multi with a bounded, persistent grid: blocks_per_sm > 0 launches
+ * 148 * blocks_per_sm blocks that stride over the chunk table (0 = one block per chunk).
+ * A small grid leaves registers and issue slots for kernels of other streams: the EMA
+ * update is independent of the rest of the step and overlaps its latency-bound kernels. */
+int pfst_ema_update_multi_ex(float* const* ema_ptrs, const float* const* param_ptrs,
+                             const int64_t* numel, const int32_t* chunk_tensor,
+                             const int64_t* chunk_begin, int64_t n_chunks,
+                             int32_t chunk_elems, float a32, float b32, int32_t mode,
+                             int32_t blocks_per_sm, void* stream);
+
 int pfst_ema_update_flat(float* ema, const float* param, int64_t n, float a32,
                          float b32, int32_t mode, void* stream);
 

@@ -109,6 +109,14 @@ int pfst_ema_update_multi(float* const* ema_ptrs, const float* const* param_ptrs
                           const int64_t* numel, const int32_t* chunk_tensor,
                           const int64_t* chunk_begin, int64_t n_chunks, int32_t chunk_elems,
                           float a32, float b32, int32_t mode, void* stream) {
+  return pfst_ema_update_multi_ex(ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems,
+                                  a32, b32, mode, 0, stream);
+}
+
+int pfst_ema_update_multi_ex(float* const* ema_ptrs, const float* const* param_ptrs,
+                             const int64_t* numel, const int32_t* chunk_tensor,
+                             const int64_t* chunk_begin, int64_t n_chunks, int32_t chunk_elems,
+                             float a32, float b32, int32_t mode, int32_t blocks_per_sm, void* stream) {
   if (n_chunks == 0) return PFST_OK;
   if (!ema_ptrs || !param_ptrs || !numel || !chunk_tensor || !chunk_begin || n_chunks < 0)
     return PFST_ERR_INVALID_ARG;
@@ -117,7 +125,10 @@ int pfst_ema_update_multi(float* const* ema_ptrs, const float* const* param_ptrs
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // One block per chunk; capped so a pathological table still launches (the
   // kernel grid-strides over chunks). 148 SMs x 8 resident blocks = 1184 per wave.
-  const int64_t max_grid = (int64_t)pfst::kNumSMs * 8 * 64;
+  // blocks_per_sm > 0: a persistent grid of that many blocks per SM, so that the update can share
+  // the SMs with kernels of other streams (it is independent of the rest of the step).
+  if (blocks_per_sm < 0) return PFST_ERR_INVALID_ARG;
+  const int64_t max_grid = blocks_per_sm > 0 ? (int64_t)pfst::kNumSMs * blocks_per_sm : (int64_t)pfst::kNumSMs * 8 * 64;
   const unsigned grid = (unsigned)(n_chunks < max_grid ? n_chunks : max_grid);
   if (mode == 0)
     pfst::ema_multi_kernel<0><<<grid, pfst::kEmaThreads, 0, s>>>(

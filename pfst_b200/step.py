@@ -9,8 +9,8 @@ call sits between them:
   segment A pseudo_label(ema_logits)                                   S1/S2
             neigh_dots(x_ema)            -> dots slot 0                L2
             proto_accum(x_ema, label)    (x_ema re-read from L2)       P1
-  eager     NCCL all-reduce(packed sums|counts), async                 (N > 1)
-            EMA update (1 launch, all tensors; hides the all-reduce)   E2
+  eager     EMA update (1 launch, all tensors) on its own stream       E2
+            NCCL all-reduce(packed sums|counts), async                 (N > 1)
             proto_finalize (in place, re-zeroes packed)                P2
             [host: wait event, np.random.choice per image, H2D 256 B]  M1 part 2
   segment B class_mix                                                  M2
@@ -20,15 +20,20 @@ call sits between them:
             pfgst_loss_bwd                                             backward
             neigh_grad + proto_dist_bwd  (one pass: read x_src, write grad_x)
 
-The only host round trip is the 36-byte class-presence read, hidden behind segment A and
-the EMA kernel. With ``graphs=True`` segments A and B are captured once per set of input
-addresses into CUDA graphs and replayed (the launch-bound part of the step: 10 kernels and
+Independent kernels run on forked streams so that the latency-bound ones (label sort,
+loss statistics, tiny maps) overlap the bandwidth-bound ones: the EMA update (independent
+of everything else in the step) runs on its own stream across the whole step, the
+pseudo-label kernel next to neigh_dots(x_ema), ClassMix next to neigh_dots(x_src), and the
+prototype distance next to the loss statistics; everything is joined before run() returns.
+The only host round trip is the 36-byte class-presence read, hidden behind segment A.
+With ``graphs=True`` segments A and B are captured once per set of input addresses into CUDA graphs and replayed (the launch-bound part of the step: 10 kernels and
 3 memsets become two graph launches). Used by bench.py and __graft_entry__.smoke(); a
 trainer that owns its autograd graph can call it in place of the aux-loss section of
 forward_train.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -83,28 +88,49 @@ class SelfTrainingStep:
         self.gproto = torch.full((1,), self.proto_weight, dtype=torch.float32, device=self.device)
         self.ema_events = None    # optional (start, end) CUDA events around the EMA launch
         self.graphs = bool(graphs)
+        self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
+        # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ema_stream = torch.cuda.Stream(device=self.device)
+        self._ev = [torch.cuda.Event() for _ in range(7)]
 
     # ------------------------------------------------------------------ segments
     def _segment_a(self, b: _Buffers, ema_logits, x_ema, geo):
         B, C, H, W = ema_logits.shape
+        main = torch.cuda.current_stream()
+        fork, join = self._ev[0], self._ev[1]
+        fork.record(main)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):                       # branch 2: L2 on x_ema
+            ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
+            join.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), ops._stream())
-        ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
-        self.bank.accumulate(x_ema, b.label)
+        main.wait_event(join)
+        self.bank.accumulate(x_ema, b.label)                      # x_ema again: L2 hits
 
     def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo):
-        s = ops._stream()
+        main = torch.cuda.current_stream()
+        s = main.cuda_stream
         B, H, W = gt.shape[0], gt.shape[-2], gt.shape[-1]
+        Bf, D, h, w = x_src.shape
+        bank = self.bank
+        fork, dots_done, join = self._ev[2], self._ev[3], self._ev[4]
+        fork.record(main)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):                       # branch 2: the x_src passes
+            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
+            dots_done.record(self._side)
+            _lib.call("pfst_proto_dist_fwd", x_src.data_ptr(), Bf, D, h, w, gt.data_ptr(), H, W,
+                      bank.mu.data_ptr(), bank.seen.data_ptr(), self.C, b.dist.data_ptr(), b.acc.data_ptr(),
+                      b.ploss.data_ptr(), ops._stream())
+            join.record(self._side)
         _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), img.data_ptr(), trg_img.data_ptr(),
                   b.label.data_ptr(), None, b.count.data_ptr(), b.label.numel(), 0, 0, B, img.shape[1], H, W,
                   b.mixed_img.data_ptr(), b.mixed_lbl.data_ptr(), b.weight.data_ptr(), b.mix_mask.data_ptr(), s)
-        ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
-        Bf, D, h, w = x_src.shape
-        bank = self.bank
-        _lib.call("pfst_proto_dist_fwd", x_src.data_ptr(), Bf, D, h, w, gt.data_ptr(), H, W, bank.mu.data_ptr(),
-                  bank.seen.data_ptr(), self.C, b.dist.data_ptr(), b.acc.data_ptr(), b.ploss.data_ptr(), s)
+        main.wait_event(dots_done)
         w6 = ops._w6(self.w6)
         common = (b.dots.data_ptr(), b.ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C, geo.lh,
                   geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h, geo.gt_w,
@@ -113,6 +139,7 @@ class SelfTrainingStep:
         # backward of (sum of the six losses + proto_weight * proto loss)
         _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
                   b.grad_logits.data_ptr(), s)
+        main.wait_event(join)
         _lib.call("pfst_neigh_grad_proto", x_src.data_ptr(), b.coef.data_ptr(), Bf, D, h, w,
                   geo.dilation // geo.up, gt.data_ptr(), H, W, bank.mu.data_ptr(), bank.seen.data_ptr(), self.C,
                   b.dist.data_ptr(), b.acc.data_ptr(), self.gproto.data_ptr(), b.grad_x.data_ptr(), s)
@@ -162,21 +189,27 @@ class SelfTrainingStep:
         if self.graphs:
             pkey = skey + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
             graphs = self._captured(pkey, b, args_a, args_b)
+        # E2 on its own stream: independent of everything below, joined at the end of the step
+        main = torch.cuda.current_stream()
+        ema_fork, ema_done = self._ev[5], self._ev[6]
+        ema_fork.record(main)
+        self._ema_stream.wait_event(ema_fork)
+        with torch.cuda.stream(self._ema_stream):
+            if self.ema_events is not None:
+                self.ema_events[0].record()
+            if it == 0:
+                self.table.update(0.0, 1.0, mode=1, blocks_per_sm=self.ema_blocks_per_sm)
+            else:
+                self.table.update(*ops.ema_coeffs(it, self.alpha), blocks_per_sm=self.ema_blocks_per_sm)
+            if self.ema_events is not None:
+                self.ema_events[1].record()
+            ema_done.record(self._ema_stream)
         # S1/S2, L2(x_ema), P1
         if graphs:
             graphs[0].replay()
         else:
             self._segment_a(b, *args_a)
         work = self.bank.all_reduce()
-        # E2
-        if self.ema_events is not None:
-            self.ema_events[0].record()
-        if it == 0:
-            self.table.update(0.0, 1.0, mode=1)
-        else:
-            self.table.update(*ops.ema_coeffs(it, self.alpha))
-        if self.ema_events is not None:
-            self.ema_events[1].record()
         # P2
         mu = self.bank.finalize(work)
         # M1 part 2 (host) -> M2, L2(x_src), P3, L1/L3-L6, backward
@@ -185,6 +218,7 @@ class SelfTrainingStep:
             graphs[1].replay()
         else:
             self._segment_b(b, *args_b)
+        main.wait_event(ema_done)
         return dict(losses=b.losses, proto_loss=b.ploss, pseudo_label=b.label, pseudo_conf=b.conf, count=b.count,
                     mixed_img=b.mixed_img, mixed_lbl=b.mixed_lbl, pseudo_weight=b.weight, mix_masks=b.mix_mask,
                     grad_x_src=b.grad_x, grad_logits_trg=b.grad_logits, mu=mu)
