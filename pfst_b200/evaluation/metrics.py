@@ -183,6 +183,14 @@ def mean_fscore(results, gt_seg_maps, num_classes, ignore_index, nan_to_num=None
                         label_map, reduce_zero_label, beta)
 
 
+def shard_range(n_items: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of an evaluation sweep for `rank` (sizes differ by at most one);
+    the confusion matrix is the only quantity reduced across ranks afterwards."""
+    base, rem = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class ConfusionMeter:
     """Running (C+1)x(C+1) int64 confusion matrix kept on the device; `all_reduce()`
     sums it across ranks (NCCL) — the only cross-image quantity of evaluation."""
