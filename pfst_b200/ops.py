@@ -89,20 +89,24 @@ class EmaTable:
             self._t_numel = mk(numel, torch.int64)
             self._t_ctensor = mk(ctensor, torch.int32)
             self._t_cbegin = mk(cbegin, torch.int64)
+            self._ptrs = (self._t_eptr.data_ptr(), self._t_pptr.data_ptr(), self._t_numel.data_ptr(),
+                          self._t_ctensor.data_ptr(), self._t_cbegin.data_ptr())
 
     def stale(self, ema_params, params) -> bool:
         key = (tuple(p.data.data_ptr() for p in ema_params), tuple(p.data.data_ptr() for p in params))
         return key != self._key
 
-    def update(self, a32: float, b32: float, mode: int = 0, blocks_per_sm: int = 0) -> None:
+    def update(self, a32: float, b32: float, mode: int = 0, blocks_per_sm: int = 0,
+               stream: Optional[int] = None) -> None:
         """blocks_per_sm > 0: bounded persistent grid (lets the update share the SMs with
-        kernels of other streams)."""
+        kernels of other streams). stream: raw cudaStream_t handle (default: the current
+        stream of the table's device)."""
         if not self.n_chunks:
             return
-        with torch.cuda.device(self.device):
-            _lib.call("pfst_ema_update_multi_ex", self._t_eptr.data_ptr(), self._t_pptr.data_ptr(),
-                      self._t_numel.data_ptr(), self._t_ctensor.data_ptr(), self._t_cbegin.data_ptr(),
-                      self.n_chunks, self.CHUNK, a32, b32, mode, int(blocks_per_sm), _stream())
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("pfst_ema_update_multi_ex", *self._ptrs, self.n_chunks, self.CHUNK, a32, b32, mode,
+                  int(blocks_per_sm), stream)
 
 
 def ema_update_flat(ema: torch.Tensor, param: torch.Tensor, a32: float, b32: float, mode: int = 0):

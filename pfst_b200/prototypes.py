@@ -58,7 +58,7 @@ class PrototypeBank:
         return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     # P2
-    def finalize(self, work=None) -> torch.Tensor:
+    def finalize(self, work=None, stream: Optional[int] = None) -> torch.Tensor:
         if work is not None:
             work.wait()
         a32, b32 = ops.ema_coeffs(max(self.iter, 1), self.alpha) if self.iter > 0 else (0.0, 1.0)
@@ -66,7 +66,7 @@ class PrototypeBank:
         # `packed` for the next step's accumulation
         _lib.call("pfst_proto_finalize", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
                   self.seen.data_ptr(), a32, b32, self.mu.data_ptr(), self.counts.data_ptr(),
-                  self.seen.data_ptr(), 1, ops._stream())
+                  self.seen.data_ptr(), 1, ops._stream() if stream is None else stream)
         self.iter += 1
         return self.mu
 

@@ -10,8 +10,7 @@ call sits between them:
             neigh_dots(x_ema)            -> dots slot 0                L2
             proto_accum(x_ema, label)    (x_ema re-read from L2)       P1
   eager     EMA update (1 launch, all tensors) on its own stream       E2
-            NCCL all-reduce(packed sums|counts), async                 (N > 1)
-            proto_finalize (in place, re-zeroes packed)                P2
+            proto_finalize (in place, re-zeroes packed)                P2   (single rank)
             [host: wait event, np.random.choice per image, H2D 256 B]  M1 part 2
   segment B class_mix                                                  M2
             neigh_dots(x_src)            -> dots slot 1                L2
@@ -19,6 +18,12 @@ call sits between them:
             pfgst_loss_fwd (prep + statistics)                         L1,L3-L6
             pfgst_loss_bwd                                             backward
             neigh_grad + proto_dist_bwd  (one pass: read x_src, write grad_x)
+
+With more than one rank the NCCL all-reduce of the packed [sums|counts] buffer is issued
+(async) right after segment A and segment B is split around it: B1 = everything that does not
+need the prototypes (ClassMix, neigh_dots(x_src), the loss statistics and their backward
+maps), then proto_finalize — the only place that waits for the all-reduce — then B2 =
+prototype distance + the fused backward pass. The collective's latency is hidden behind B1.
 
 Independent kernels run on forked streams so that the latency-bound ones (label sort,
 loss statistics, tiny maps) overlap the bandwidth-bound ones: the EMA update (independent
@@ -74,7 +79,8 @@ class SelfTrainingStep:
     def __init__(self, teacher_params, student_params, num_classes: int, feat_dim: int, device,
                  alpha: float = 0.999, pseudo_threshold: float = 0.98, dilation: int = 2, top_k: int = 3,
                  downscale: Optional[float] = 0.5, weights6=W6_DEFAULT, proto_weight: float = 0.1,
-                 max_batch: int = 64, group=None, graphs: bool = False):
+                 max_batch: int = 64, group=None, graphs: bool = False,
+                 split_for_allreduce: Optional[bool] = None):
         self.device = torch.device(device)
         self.alpha, self.thr = alpha, pseudo_threshold
         self.dilation, self.top_k, self.downscale = dilation, top_k, downscale
@@ -88,6 +94,7 @@ class SelfTrainingStep:
         self.gproto = torch.full((1,), self.proto_weight, dtype=torch.float32, device=self.device)
         self.ema_events = None    # optional (start, end) CUDA events around the EMA launch
         self.graphs = bool(graphs)
+        self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
         self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
@@ -95,6 +102,7 @@ class SelfTrainingStep:
         self._side = torch.cuda.Stream(device=self.device)
         self._ema_stream = torch.cuda.Stream(device=self.device)
         self._ev = [torch.cuda.Event() for _ in range(7)]
+        self._world = None        # world size, resolved on first use
 
     # ------------------------------------------------------------------ segments
     def _segment_a(self, b: _Buffers, ema_logits, x_ema, geo):
@@ -111,42 +119,62 @@ class SelfTrainingStep:
         main.wait_event(join)
         self.bank.accumulate(x_ema, b.label)                      # x_ema again: L2 hits
 
-    def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo):
+    def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo, part="all"):
+        """part 'all': the whole segment (single rank: the prototypes are final before it starts).
+        Multi-rank: 'b1' = everything that does not need the prototypes (runs while the NCCL
+        all-reduce is in flight), then proto_finalize, then 'b2' = distance forward + fused backward."""
         main = torch.cuda.current_stream()
         s = main.cuda_stream
         B, H, W = gt.shape[0], gt.shape[-2], gt.shape[-1]
         Bf, D, h, w = x_src.shape
         bank = self.bank
         fork, dots_done, join = self._ev[2], self._ev[3], self._ev[4]
-        fork.record(main)
-        self._side.wait_event(fork)
-        with torch.cuda.stream(self._side):                       # branch 2: the x_src passes
-            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
-            dots_done.record(self._side)
+
+        def dist_fwd():
             _lib.call("pfst_proto_dist_fwd", x_src.data_ptr(), Bf, D, h, w, gt.data_ptr(), H, W,
                       bank.mu.data_ptr(), bank.seen.data_ptr(), self.C, b.dist.data_ptr(), b.acc.data_ptr(),
                       b.ploss.data_ptr(), ops._stream())
-            join.record(self._side)
-        _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), img.data_ptr(), trg_img.data_ptr(),
-                  b.label.data_ptr(), None, b.count.data_ptr(), b.label.numel(), 0, 0, B, img.shape[1], H, W,
-                  b.mixed_img.data_ptr(), b.mixed_lbl.data_ptr(), b.weight.data_ptr(), b.mix_mask.data_ptr(), s)
-        main.wait_event(dots_done)
-        w6 = ops._w6(self.w6)
-        common = (b.dots.data_ptr(), b.ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C, geo.lh,
-                  geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h, geo.gt_w,
-                  geo.dilation, int(self.top_k), w6, b.ws.data_ptr(), b.stats.data_ptr())
-        _lib.call("pfst_pfgst_loss_fwd", *common, b.losses.data_ptr(), None, None, s)
-        # backward of (sum of the six losses + proto_weight * proto loss)
-        _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
-                  b.grad_logits.data_ptr(), s)
-        main.wait_event(join)
-        _lib.call("pfst_neigh_grad_proto", x_src.data_ptr(), b.coef.data_ptr(), Bf, D, h, w,
-                  geo.dilation // geo.up, gt.data_ptr(), H, W, bank.mu.data_ptr(), bank.seen.data_ptr(), self.C,
-                  b.dist.data_ptr(), b.acc.data_ptr(), self.gproto.data_ptr(), b.grad_x.data_ptr(), s)
 
-    def _captured(self, key, b, args_a, args_b):
-        """CUDA graphs of the two segments for one set of input addresses (captured after a
-        warm-up pass on a side stream, as CUDA requires for first-use initialisation)."""
+        if part in ("all", "b1"):
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):                   # branch 2: the x_src passes
+                ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
+                dots_done.record(self._side)
+                if part == "all":
+                    dist_fwd()
+                    join.record(self._side)
+            _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), img.data_ptr(), trg_img.data_ptr(),
+                      b.label.data_ptr(), None, b.count.data_ptr(), b.label.numel(), 0, 0, B, img.shape[1], H, W,
+                      b.mixed_img.data_ptr(), b.mixed_lbl.data_ptr(), b.weight.data_ptr(), b.mix_mask.data_ptr(),
+                      s)
+            main.wait_event(dots_done)
+            w6 = ops._w6(self.w6)
+            common = (b.dots.data_ptr(), b.ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C,
+                      geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h,
+                      geo.gt_w, geo.dilation, int(self.top_k), w6, b.ws.data_ptr(), b.stats.data_ptr())
+            _lib.call("pfst_pfgst_loss_fwd", *common, b.losses.data_ptr(), None, None, s)
+            # backward of (sum of the six losses + proto_weight * proto loss)
+            _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
+                      b.grad_logits.data_ptr(), s)
+            if part == "all":
+                main.wait_event(join)
+        if part == "b2":
+            dist_fwd()
+        if part in ("all", "b2"):
+            _lib.call("pfst_neigh_grad_proto", x_src.data_ptr(), b.coef.data_ptr(), Bf, D, h, w,
+                      geo.dilation // geo.up, gt.data_ptr(), H, W, bank.mu.data_ptr(), bank.seen.data_ptr(),
+                      self.C, b.dist.data_ptr(), b.acc.data_ptr(), self.gproto.data_ptr(), b.grad_x.data_ptr(), s)
+
+    def _multi_rank(self) -> bool:
+        if self._world is None:
+            import torch.distributed as dist
+            self._world = dist.get_world_size(self.bank.group) if dist.is_available() and dist.is_initialized() else 1
+        return self._world > 1
+
+    def _captured(self, key, b, args_a, args_b, parts):
+        """CUDA graphs of the segments for one set of input addresses (captured after a warm-up
+        pass on a side stream, as CUDA requires for first-use initialisation)."""
         if key in self._graphs:
             return self._graphs[key]
         side = torch.cuda.Stream(device=self.device)
@@ -154,16 +182,18 @@ class SelfTrainingStep:
         snap = self.bank.packed.clone()
         with torch.cuda.stream(side):              # warm-up: module load, cudaFuncSetAttribute
             self._segment_a(b, *args_a)
-            self._segment_b(b, *args_b)
+            for part in parts:
+                self._segment_b(b, *args_b, part=part)
         torch.cuda.current_stream().wait_stream(side)
         self.bank.packed.copy_(snap)               # the warm-up accumulated into the all-reduce buffer
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga):
+        graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
+        with torch.cuda.graph(graphs[0]):
             self._segment_a(b, *args_a)
-        with torch.cuda.graph(gb):
-            self._segment_b(b, *args_b)
-        self._graphs[key] = (ga, gb)
-        return ga, gb
+        for g, part in zip(graphs[1:], parts):
+            with torch.cuda.graph(g):
+                self._segment_b(b, *args_b, part=part)
+        self._graphs[key] = graphs
+        return graphs
 
     # ----------------------------------------------------------------------- run
     def run(self, it: int, img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema, rng=np.random):
@@ -180,44 +210,49 @@ class SelfTrainingStep:
             ent = (_Buffers(self.device, B, self.C, H, W, img.shape, logits_trg.shape, x_src.shape, geo), geo)
             self._bufs[skey] = ent
         b, geo = ent
+        main = torch.cuda.current_stream()
         # M1 part 1: presence bits + tiny D2H, overlapped with the kernels below
-        self.plan.start(gt)
+        self.plan.start(gt, main)
         args_a = (ema_logits, x_ema, geo)
         chosen_buf = self.plan._chosen[:B]
         args_b = (img, trg_img, gt, chosen_buf, logits_trg, x_src, geo)
+        split = self._multi_rank() if self.split_for_allreduce is None else bool(self.split_for_allreduce)
+        parts = ("b1", "b2") if split else ("all",)
         graphs = None
         if self.graphs:
-            pkey = skey + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
-            graphs = self._captured(pkey, b, args_a, args_b)
+            pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
+            graphs = self._captured(pkey, b, args_a, args_b, parts)
         # E2 on its own stream: independent of everything below, joined at the end of the step
-        main = torch.cuda.current_stream()
         ema_fork, ema_done = self._ev[5], self._ev[6]
         ema_fork.record(main)
-        self._ema_stream.wait_event(ema_fork)
-        with torch.cuda.stream(self._ema_stream):
-            if self.ema_events is not None:
-                self.ema_events[0].record()
-            if it == 0:
-                self.table.update(0.0, 1.0, mode=1, blocks_per_sm=self.ema_blocks_per_sm)
-            else:
-                self.table.update(*ops.ema_coeffs(it, self.alpha), blocks_per_sm=self.ema_blocks_per_sm)
-            if self.ema_events is not None:
-                self.ema_events[1].record()
-            ema_done.record(self._ema_stream)
+        es = self._ema_stream
+        es.wait_event(ema_fork)
+        if self.ema_events is not None:
+            self.ema_events[0].record(es)
+        if it == 0:
+            self.table.update(0.0, 1.0, mode=1, blocks_per_sm=self.ema_blocks_per_sm, stream=es.cuda_stream)
+        else:
+            self.table.update(*ops.ema_coeffs(it, self.alpha), blocks_per_sm=self.ema_blocks_per_sm, stream=es.cuda_stream)
+        if self.ema_events is not None:
+            self.ema_events[1].record(es)
+        ema_done.record(es)
         # S1/S2, L2(x_ema), P1
         if graphs:
             graphs[0].replay()
         else:
             self._segment_a(b, *args_a)
-        work = self.bank.all_reduce()
-        # P2
-        mu = self.bank.finalize(work)
-        # M1 part 2 (host) -> M2, L2(x_src), P3, L1/L3-L6, backward
+        work = self.bank.all_reduce()                 # async; None on a single rank
+        if len(parts) == 1:
+            mu = self.bank.finalize(work, main.cuda_stream)             # P2
+        # M1 part 2 (host) -> M2, L2(x_src), L1/L3-L6 (+ P3 and the fused backward on a single rank)
         self.plan.choose(rng)
-        if graphs:
-            graphs[1].replay()
-        else:
-            self._segment_b(b, *args_b)
+        for i, part in enumerate(parts):
+            if part == "b2":
+                mu = self.bank.finalize(work, main.cuda_stream)         # P2: waits for the all-reduce only here
+            if graphs:
+                graphs[1 + i].replay()
+            else:
+                self._segment_b(b, *args_b, part=part)
         main.wait_event(ema_done)
         return dict(losses=b.losses, proto_loss=b.ploss, pseudo_label=b.label, pseudo_conf=b.conf, count=b.count,
                     mixed_img=b.mixed_img, mixed_lbl=b.mixed_lbl, pseudo_weight=b.weight, mix_masks=b.mix_mask,

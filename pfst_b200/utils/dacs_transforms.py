@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from .._lib import PfstError
 
 
@@ -32,14 +32,22 @@ def _present_classes(presence_words: np.ndarray) -> np.ndarray:
 
 def draw_class_choice(classes: np.ndarray, batch: int, rng=np.random) -> np.ndarray:
     """One `np.random.choice(n, int((n + n % 2) / 2), replace=False)` per image
-    (dacs_transforms.py:114-117) -> uint32 (batch, 8) bitmasks of the drawn classes."""
-    n = classes.shape[0]
-    chosen = np.zeros((batch, 8), dtype=np.uint32)
-    for b in range(batch):
-        pick = rng.choice(n, int((n + n % 2) / 2), replace=False)
-        for v in classes[pick]:
-            chosen[b, v >> 5] |= np.uint32(1) << np.uint32(v & 31)
-    return chosen
+    (dacs_transforms.py:114-117) -> uint32 (batch, 8) bitmasks of the drawn classes.
+
+    Legacy `RandomState.choice(n, k, replace=False)` IS `permutation(n)[:k]` (numpy
+    mtrand: `idx = self.permutation(pop_size)[:size]`), i.e. the same values from the same
+    stream state; `permutation` skips choice's argument checking and is 3x cheaper, which
+    matters because this draw sits on the step's only host round trip."""
+    n = int(classes.shape[0])
+    k = int((n + n % 2) / 2)
+    vals = classes.tolist()
+    words = []
+    for _ in range(batch):
+        mask = 0
+        for i in rng.permutation(n)[:k].tolist():
+            mask |= 1 << vals[i]
+        words.append([(mask >> (32 * w)) & 0xffffffff for w in range(8)])
+    return np.array(words, dtype=np.uint32).reshape(batch, 8)
 
 
 class ClassMixPlan:
@@ -54,22 +62,27 @@ class ClassMixPlan:
         self._presence_host = torch.empty(9, dtype=torch.int32).pin_memory()
         self._chosen_host = torch.empty((max_batch, 8), dtype=torch.int32).pin_memory()
         self._chosen = torch.empty((max_batch, 8), dtype=torch.int32, device=device)
+        self._presence_np = self._presence_host.numpy().view(np.uint32)     # views of the pinned buffers
+        self._chosen_np = self._chosen_host.numpy()
         self._event = torch.cuda.Event()
         self._batch = 0
 
-    def start(self, gt: torch.Tensor) -> None:
+    def start(self, gt: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
         self._batch = gt.shape[0]
         if self._batch > self._chosen.shape[0]:
             raise ValueError("batch larger than the plan's capacity")
-        ops.class_presence(gt, out=self._presence)
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        _lib.call("pfst_class_presence", ops._dev(gt, "gt", torch.int64), gt.numel(), self._presence.data_ptr(),
+                  stream.cuda_stream)
         self._presence_host.copy_(self._presence, non_blocking=True)
-        self._event.record()
+        self._event.record(stream)
 
     def choose(self, rng=np.random) -> torch.Tensor:
         self._event.synchronize()
-        classes = _present_classes(self._presence_host.numpy().view(np.uint32))
+        classes = _present_classes(self._presence_np)
         chosen = draw_class_choice(classes, self._batch, rng)
-        self._chosen_host[: self._batch].copy_(torch.from_numpy(chosen.view(np.int32)))
+        self._chosen_np[: self._batch] = chosen.view(np.int32)
         dst = self._chosen[: self._batch]
         dst.copy_(self._chosen_host[: self._batch], non_blocking=True)
         return dst

@@ -65,7 +65,7 @@ def test_finalize_in_place_resets_packed(cuda):
         assert float(bank.packed.abs().sum()) == 0.0           # re-zeroed by the finalize kernel
 
 
-def _check_step(cuda, wl_name, graphs, iters=(0, 1, 2)):
+def _check_step(cuda, wl_name, graphs, iters=(0, 1, 2), split=None):
     wl = WORKLOADS[wl_name]
     host = step_inputs(wl, 1234)
     g = torch.Generator().manual_seed(7)
@@ -75,7 +75,8 @@ def _check_step(cuda, wl_name, graphs, iters=(0, 1, 2)):
     d_student, d_teacher = [p.to(cuda) for p in student], [p.to(cuda) for p in teacher]
     inp = {k: v.to(cuda) for k, v in host.items()}
     step = SelfTrainingStep(d_teacher, d_student, wl.C, wl.D, cuda, dilation=wl.dilation,
-                            downscale=wl.downscale if wl.downscale != 1.0 else None, graphs=graphs)
+                            downscale=wl.downscale if wl.downscale != 1.0 else None, graphs=graphs,
+                            split_for_allreduce=split)
     from oracle import pfgst_loss as OL
     cfg = OL.LossCfg(dilation=wl.dilation, downscale=wl.downscale if wl.downscale != 1.0 else None)
     proto_state = None
@@ -114,6 +115,12 @@ def _check_step(cuda, wl_name, graphs, iters=(0, 1, 2)):
 @pytest.mark.parametrize("wl_name", ["tiny", "tiny33"])
 def test_selftraining_step_matches_oracle(cuda, wl_name, graphs):
     _check_step(cuda, wl_name, graphs)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_step_split_around_the_allreduce_matches_oracle(cuda, graphs):
+    """The multi-rank schedule (segment B split around proto_finalize) on one rank."""
+    _check_step(cuda, "tiny", graphs, split=True)
 
 
 def test_graph_replay_is_bit_identical_to_eager(cuda):
