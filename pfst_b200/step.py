@@ -96,6 +96,7 @@ class SelfTrainingStep:
         self.graphs = bool(graphs)
         self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
         self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
+        self.ema_at = os.environ.get("PFST_EMA_AT", "start")   # 'start': with segment A; 'b': with segment B
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
@@ -195,6 +196,24 @@ class SelfTrainingStep:
         self._graphs[key] = graphs
         return graphs
 
+    def _launch_ema(self, it: int, main) -> None:
+        """E2 on its own stream (bounded persistent grid): independent of everything else in the
+        step, forked from `main` here and joined at the end of run()."""
+        ema_fork, ema_done = self._ev[5], self._ev[6]
+        ema_fork.record(main)
+        es = self._ema_stream
+        es.wait_event(ema_fork)
+        if self.ema_events is not None:
+            self.ema_events[0].record(es)
+        if it == 0:
+            self.table.update(0.0, 1.0, mode=1, blocks_per_sm=self.ema_blocks_per_sm, stream=es.cuda_stream)
+        else:
+            self.table.update(*ops.ema_coeffs(it, self.alpha), blocks_per_sm=self.ema_blocks_per_sm,
+                              stream=es.cuda_stream)
+        if self.ema_events is not None:
+            self.ema_events[1].record(es)
+        ema_done.record(es)
+
     # ----------------------------------------------------------------------- run
     def run(self, it: int, img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema, rng=np.random):
         B, H, W = gt.shape[0], gt.shape[-2], gt.shape[-1]
@@ -222,20 +241,8 @@ class SelfTrainingStep:
         if self.graphs:
             pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
             graphs = self._captured(pkey, b, args_a, args_b, parts)
-        # E2 on its own stream: independent of everything below, joined at the end of the step
-        ema_fork, ema_done = self._ev[5], self._ev[6]
-        ema_fork.record(main)
-        es = self._ema_stream
-        es.wait_event(ema_fork)
-        if self.ema_events is not None:
-            self.ema_events[0].record(es)
-        if it == 0:
-            self.table.update(0.0, 1.0, mode=1, blocks_per_sm=self.ema_blocks_per_sm, stream=es.cuda_stream)
-        else:
-            self.table.update(*ops.ema_coeffs(it, self.alpha), blocks_per_sm=self.ema_blocks_per_sm, stream=es.cuda_stream)
-        if self.ema_events is not None:
-            self.ema_events[1].record(es)
-        ema_done.record(es)
+        if self.ema_at == "start":
+            self._launch_ema(it, main)
         # S1/S2, L2(x_ema), P1
         if graphs:
             graphs[0].replay()
@@ -246,6 +253,8 @@ class SelfTrainingStep:
             mu = self.bank.finalize(work, main.cuda_stream)             # P2
         # M1 part 2 (host) -> M2, L2(x_src), L1/L3-L6 (+ P3 and the fused backward on a single rank)
         self.plan.choose(rng)
+        if self.ema_at != "start":
+            self._launch_ema(it, main)
         for i, part in enumerate(parts):
             if part == "b2":
                 mu = self.bank.finalize(work, main.cuda_stream)         # P2: waits for the all-reduce only here
@@ -253,7 +262,7 @@ class SelfTrainingStep:
                 graphs[1 + i].replay()
             else:
                 self._segment_b(b, *args_b, part=part)
-        main.wait_event(ema_done)
+        main.wait_event(self._ev[6])
         return dict(losses=b.losses, proto_loss=b.ploss, pseudo_label=b.label, pseudo_conf=b.conf, count=b.count,
                     mixed_img=b.mixed_img, mixed_lbl=b.mixed_lbl, pseudo_weight=b.weight, mix_masks=b.mix_mask,
                     grad_x_src=b.grad_x, grad_logits_trg=b.grad_logits, mu=mu)

@@ -63,7 +63,7 @@ if rep.exists():
             mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             t = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * mult.get(unit_r, 1) + \
                 float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * mult.get(unit_w, 1)
-            traffic[name.split("::")[-1].split("<")[0]] = t
+            traffic[name.replace("void ", "").split("::")[-1].split("<")[0].strip()] = t
         except (KeyError, ValueError):
             pass
     (dst / f"{out}_full_summary.json").write_text(json.dumps({"units": dict(zip(hdr, rows[1])), "kernels": table}, indent=1))
