@@ -5,7 +5,7 @@ three network passes. It issues the same kernels as the PFGST drop-in
 through autograd, into buffers allocated once, so that no PyTorch kernel and no allocator
 call sits between them:
 
-  eager     presence(gt) -> D2H 36 B -> [event]                        M1 part 1
+  aux       presence(gt) -> D2H 36 B -> [event]   (own stream)         M1 part 1
   segment A pseudo_label(ema_logits)                                   S1/S2
             neigh_dots(x_ema)            -> dots slot 0                L2
             proto_accum(x_ema, label)    (x_ema re-read from L2)       P1
@@ -102,7 +102,8 @@ class SelfTrainingStep:
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
         self._side = torch.cuda.Stream(device=self.device)
         self._ema_stream = torch.cuda.Stream(device=self.device)
-        self._ev = [torch.cuda.Event() for _ in range(7)]
+        self._aux = torch.cuda.Stream(device=self.device)
+        self._ev = [torch.cuda.Event() for _ in range(8)]
         self._world = None        # world size, resolved on first use
 
     # ------------------------------------------------------------------ segments
@@ -230,8 +231,11 @@ class SelfTrainingStep:
             self._bufs[skey] = ent
         b, geo = ent
         main = torch.cuda.current_stream()
-        # M1 part 1: presence bits + tiny D2H, overlapped with the kernels below
-        self.plan.start(gt, main)
+        # M1 part 1: presence bits + tiny D2H on an auxiliary stream — only the HOST waits for it
+        # (in choose()); segment A does not
+        self._ev[7].record(main)
+        self._aux.wait_event(self._ev[7])
+        self.plan.start(gt, self._aux)
         args_a = (ema_logits, x_ema, geo)
         chosen_buf = self.plan._chosen[:B]
         args_b = (img, trg_img, gt, chosen_buf, logits_trg, x_src, geo)

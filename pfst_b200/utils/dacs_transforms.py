@@ -75,7 +75,8 @@ class ClassMixPlan:
             stream = torch.cuda.current_stream()
         _lib.call("pfst_class_presence", ops._dev(gt, "gt", torch.int64), gt.numel(), self._presence.data_ptr(),
                   stream.cuda_stream)
-        self._presence_host.copy_(self._presence, non_blocking=True)
+        with torch.cuda.stream(stream):
+            self._presence_host.copy_(self._presence, non_blocking=True)
         self._event.record(stream)
 
     def choose(self, rng=np.random) -> torch.Tensor:
