@@ -198,8 +198,12 @@ def run_ours(args, wl, rank, world, local_rank):
                             graphs=not args.no_graphs)
 
     def one(it):
-        return step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], inp["ema_logits"],
-                        inp["logits_trg"], inp["x_src"], inp["x_ema"])
+        out = step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], inp["ema_logits"],
+                       inp["logits_trg"], inp["x_src"], inp["x_ema"])
+        # the next batch's labels are known before its network passes: their class-presence bits
+        # (M1 part 1, one kernel + a 36-byte D2H) are prefetched so the host never waits for them
+        step.prefetch(inp["gt"])
+        return out
 
     def barrier():
         if world > 1:

@@ -257,6 +257,16 @@ int pfst_proto_finalize(float* packed, int32_t C, int32_t D, const float* mu_pre
                         int64_t* cnt_out, uint8_t* seen_out, int32_t reset_packed,
                         void* stream);
 
+/* pfst_proto_finalize with the bank iteration kept ON THE DEVICE: iter_state = int64[2]
+ * {iteration (0 on the first call), internal block counter (0)}. The kernel derives
+ * a = min(1 - 1/(iter+1), alpha), b = 1 - a in fp64 exactly as pfst_ema_coeffs does (iter 0:
+ * plain mean) and advances the iteration itself, so the launch carries no per-step host
+ * argument and can be captured in a CUDA graph.                                        */
+int pfst_proto_finalize_dev(float* packed, int32_t C, int32_t D, const float* mu_prev,
+                            const uint8_t* seen_prev, double alpha, int64_t* iter_state,
+                            float* mu_out, int64_t* cnt_out, uint8_t* seen_out,
+                            int32_t reset_packed, void* stream);
+
 /* loss = mean over valid pixels of ||feats[:,n] - mu[label_n]||_2 (masked_feat_dist
  * with f2 = mu[label]); valid = label in [0,C) and seen[label] (seen may be NULL).
  * dist: (B,h,w) per-pixel distances (0 where invalid), kept for the backward.

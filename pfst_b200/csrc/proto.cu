@@ -285,13 +285,31 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   }
 }
 
+// iter_state (nullable): device int64[2] = {prototype-bank iteration, block-completion counter}.
+// When given, the EMA coefficients are derived from the device-resident iteration with the
+// E2 rule (pfgst.py:117, in fp64 like the host) and the last block to finish advances it —
+// the launch then has no per-step host argument and can live inside a CUDA graph.
 __global__ void proto_finalize_kernel(float* __restrict__ packed, int C, int D,
                                       const float* mu_prev, const uint8_t* seen_prev,
-                                      float a32, float b32, float* mu_out,
-                                      int64_t* __restrict__ cnt_out, uint8_t* seen_out, int reset) {
+                                      float a32, float b32, double alpha, long long* iter_state,
+                                      float* mu_out, int64_t* __restrict__ cnt_out, uint8_t* seen_out,
+                                      int reset) {
   // mu_out may alias mu_prev and seen_out may alias seen_prev (in-place bank update): every
   // element is read and written by the same thread, the per-class flags after a barrier.
   const int c = blockIdx.x;
+  long long it = 0;
+  if (iter_state) {
+    it = *reinterpret_cast<volatile long long*>(iter_state);
+    if (it > 0) {
+      double a = 1.0 - 1.0 / (double)(it + 1);
+      if (alpha < a) a = alpha;
+      a32 = (float)a;
+      b32 = (float)(1.0 - a);
+    } else {
+      a32 = 0.f;
+      b32 = 1.f;
+    }
+  }
   const float cnt = packed[(int64_t)C * D + c];
   const bool has = cnt > 0.f;
   const bool seen = seen_prev ? seen_prev[c] != 0 : false;
@@ -309,6 +327,13 @@ __global__ void proto_finalize_kernel(float* __restrict__ packed, int C, int D,
     if (cnt_out) cnt_out[c] = (int64_t)cnt;
     if (seen_out) seen_out[c] = (has || seen) ? 1 : 0;
     if (reset) packed[(int64_t)C * D + c] = 0.f;
+    if (iter_state) {
+      __threadfence();
+      if (atomicAdd(reinterpret_cast<unsigned long long*>(iter_state + 1), 1ull) == gridDim.x - 1) {
+        iter_state[1] = 0;
+        iter_state[0] = it + 1;      // every block has read `it` before it could finish
+      }
+    }
   }
 }
 
@@ -542,8 +567,19 @@ int pfst_proto_finalize(float* packed, int32_t C, int32_t D, const float* mu_pre
                         uint8_t* seen_out, int32_t reset_packed, void* stream) {
   if (!packed || !mu_out || C < 1 || D < 1) return PFST_ERR_INVALID_ARG;
   pfst::proto_finalize_kernel<<<(unsigned)C, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      packed, C, D, mu_prev, seen_prev, a32, b32, mu_out, cnt_out, seen_out, reset_packed);
+      packed, C, D, mu_prev, seen_prev, a32, b32, 0.0, nullptr, mu_out, cnt_out, seen_out, reset_packed);
   PFST_CHECK_LAUNCH("pfst_proto_finalize");
+  return PFST_OK;
+}
+
+int pfst_proto_finalize_dev(float* packed, int32_t C, int32_t D, const float* mu_prev,
+                            const uint8_t* seen_prev, double alpha, int64_t* iter_state, float* mu_out,
+                            int64_t* cnt_out, uint8_t* seen_out, int32_t reset_packed, void* stream) {
+  if (!packed || !mu_out || !iter_state || C < 1 || D < 1) return PFST_ERR_INVALID_ARG;
+  pfst::proto_finalize_kernel<<<(unsigned)C, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      packed, C, D, mu_prev, seen_prev, 0.f, 1.f, alpha, reinterpret_cast<long long*>(iter_state), mu_out, cnt_out,
+      seen_out, reset_packed);
+  PFST_CHECK_LAUNCH("pfst_proto_finalize_dev");
   return PFST_OK;
 }
 

@@ -36,6 +36,7 @@ class PrototypeBank:
         self.seen = torch.zeros(self.C, dtype=torch.uint8, device=self.device)
         self.counts = torch.zeros(self.C, dtype=torch.int64, device=self.device)
         self.comm_stream = comm_stream
+        self.iter_state = torch.zeros(2, dtype=torch.int64, device=self.device)   # device copy of `iter` (+ counter)
 
     # P1
     def accumulate(self, feats: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None,
@@ -59,16 +60,20 @@ class PrototypeBank:
 
     # P2
     def finalize(self, work=None, stream: Optional[int] = None) -> torch.Tensor:
+        """In place (mu / seen keep their addresses); the kernel also zeroes `packed` for the next
+        step's accumulation and advances the device-resident iteration, from which it derives the
+        prototype-EMA coefficients — no per-step host argument, so the launch is graph-capturable
+        (`finalize_captured` below is the same call without the host bookkeeping)."""
         if work is not None:
             work.wait()
-        a32, b32 = ops.ema_coeffs(max(self.iter, 1), self.alpha) if self.iter > 0 else (0.0, 1.0)
-        # in place (mu / seen keep their addresses: CUDA-graph friendly); the kernel also zeroes
-        # `packed` for the next step's accumulation
-        _lib.call("pfst_proto_finalize", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
-                  self.seen.data_ptr(), a32, b32, self.mu.data_ptr(), self.counts.data_ptr(),
-                  self.seen.data_ptr(), 1, ops._stream() if stream is None else stream)
+        self.finalize_captured(ops._stream() if stream is None else stream)
         self.iter += 1
         return self.mu
+
+    def finalize_captured(self, stream: int) -> None:
+        _lib.call("pfst_proto_finalize_dev", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
+                  self.seen.data_ptr(), float(self.alpha), self.iter_state.data_ptr(), self.mu.data_ptr(),
+                  self.counts.data_ptr(), self.seen.data_ptr(), 1, stream)
 
     def update(self, feats, labels, conf=None, conf_thr: float = 0.0) -> torch.Tensor:
         self.accumulate(feats, labels, conf, conf_thr)

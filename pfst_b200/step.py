@@ -105,6 +105,7 @@ class SelfTrainingStep:
         self._aux = torch.cuda.Stream(device=self.device)
         self._ev = [torch.cuda.Event() for _ in range(8)]
         self._world = None        # world size, resolved on first use
+        self._prefetched = None   # data_ptr of the gt whose presence bits are in flight
 
     # ------------------------------------------------------------------ segments
     def _segment_a(self, b: _Buffers, ema_logits, x_ema, geo):
@@ -174,28 +175,59 @@ class SelfTrainingStep:
             self._world = dist.get_world_size(self.bank.group) if dist.is_available() and dist.is_initialized() else 1
         return self._world > 1
 
+    def _whole_step(self, b, args_a, args_b):
+        """Single rank: segment A, proto_finalize (device-resident iteration) and segment B in one
+        stream-ordered sequence — ONE CUDA graph per step."""
+        self._segment_a(b, *args_a)
+        self.bank.finalize_captured(ops._stream())
+        self._segment_b(b, *args_b, part="all")
+
     def _captured(self, key, b, args_a, args_b, parts):
-        """CUDA graphs of the segments for one set of input addresses (captured after a warm-up
-        pass on a side stream, as CUDA requires for first-use initialisation)."""
+        """CUDA graphs for one set of input addresses, captured after a warm-up pass on a side
+        stream (CUDA needs first-use initialisation outside a capture). Single rank: [whole step];
+        multi-rank: [A, B1, B2] with the all-reduce and proto_finalize between them."""
         if key in self._graphs:
             return self._graphs[key]
+        bank = self.bank
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        snap = self.bank.packed.clone()
+        snap = [t.clone() for t in (bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state)]
         with torch.cuda.stream(side):              # warm-up: module load, cudaFuncSetAttribute
-            self._segment_a(b, *args_a)
-            for part in parts:
-                self._segment_b(b, *args_b, part=part)
+            if parts == ("all",):
+                self._whole_step(b, args_a, args_b)
+            else:
+                self._segment_a(b, *args_a)
+                for part in parts:
+                    self._segment_b(b, *args_b, part=part)
         torch.cuda.current_stream().wait_stream(side)
-        self.bank.packed.copy_(snap)               # the warm-up accumulated into the all-reduce buffer
-        graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
-        with torch.cuda.graph(graphs[0]):
-            self._segment_a(b, *args_a)
-        for g, part in zip(graphs[1:], parts):
-            with torch.cuda.graph(g):
-                self._segment_b(b, *args_b, part=part)
+        for t, c in zip((bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state), snap):
+            t.copy_(c)                             # the warm-up touched the prototype bank
+        if parts == ("all",):
+            graphs = [torch.cuda.CUDAGraph()]
+            with torch.cuda.graph(graphs[0]):
+                self._whole_step(b, args_a, args_b)
+        else:
+            graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
+            with torch.cuda.graph(graphs[0]):
+                self._segment_a(b, *args_a)
+            for g, part in zip(graphs[1:], parts):
+                with torch.cuda.graph(g):
+                    self._segment_b(b, *args_b, part=part)
         self._graphs[key] = graphs
         return graphs
+
+    def prefetch(self, gt, wait_stream: Optional[torch.cuda.Stream] = None) -> None:
+        """M1 part 1 for the NEXT run(): class-presence kernel + its 36-byte D2H on the auxiliary
+        stream. `gt` is known as soon as the batch is loaded (long before the network passes that
+        precede the hot path), so a trainer calls this early — e.g. right after enqueueing the
+        previous step — and run() then never blocks the host: it only finds the bits already there.
+        `gt` must already be materialised on the device, or `wait_stream` must be the stream that
+        produces it (the auxiliary stream then waits for the work enqueued there so far)."""
+        if wait_stream is not None:
+            self._ev[7].record(wait_stream)
+            self._aux.wait_event(self._ev[7])
+        self.plan.start(gt, self._aux)
+        self._prefetched = gt.data_ptr()
 
     def _launch_ema(self, it: int, main) -> None:
         """E2 on its own stream (bounded persistent grid): independent of everything else in the
@@ -231,11 +263,10 @@ class SelfTrainingStep:
             self._bufs[skey] = ent
         b, geo = ent
         main = torch.cuda.current_stream()
-        # M1 part 1: presence bits + tiny D2H on an auxiliary stream — only the HOST waits for it
-        # (in choose()); segment A does not
-        self._ev[7].record(main)
-        self._aux.wait_event(self._ev[7])
-        self.plan.start(gt, self._aux)
+        # M1: presence bits (prefetched, or computed now on the auxiliary stream), host draw, H2D
+        if self._prefetched != gt.data_ptr():
+            self.prefetch(gt, wait_stream=main)
+        self._prefetched = None
         args_a = (ema_logits, x_ema, geo)
         chosen_buf = self.plan._chosen[:B]
         args_b = (img, trg_img, gt, chosen_buf, logits_trg, x_src, geo)
@@ -245,27 +276,40 @@ class SelfTrainingStep:
         if self.graphs:
             pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
             graphs = self._captured(pkey, b, args_a, args_b, parts)
+        self.plan.choose(rng)                          # waits for the 36-byte copy only
         if self.ema_at == "start":
             self._launch_ema(it, main)
-        # S1/S2, L2(x_ema), P1
-        if graphs:
-            graphs[0].replay()
-        else:
-            self._segment_a(b, *args_a)
-        work = self.bank.all_reduce()                 # async; None on a single rank
-        if len(parts) == 1:
-            mu = self.bank.finalize(work, main.cuda_stream)             # P2
-        # M1 part 2 (host) -> M2, L2(x_src), L1/L3-L6 (+ P3 and the fused backward on a single rank)
-        self.plan.choose(rng)
-        if self.ema_at != "start":
-            self._launch_ema(it, main)
-        for i, part in enumerate(parts):
-            if part == "b2":
-                mu = self.bank.finalize(work, main.cuda_stream)         # P2: waits for the all-reduce only here
-            if graphs:
-                graphs[1 + i].replay()
+        elif self.ema_at == "serial":          # experiment: full grid on the main stream, nothing overlaps it
+            if self.ema_events is not None:
+                self.ema_events[0].record(main)
+            if it == 0:
+                self.table.update(0.0, 1.0, mode=1, stream=main.cuda_stream)
             else:
-                self._segment_b(b, *args_b, part=part)
+                self.table.update(*ops.ema_coeffs(it, self.alpha), stream=main.cuda_stream)
+            if self.ema_events is not None:
+                self.ema_events[1].record(main)
+            self._ev[6].record(main)
+        if not split:
+            # S1/S2, L2(x_ema), P1 -> P2 -> M2, L2(x_src), P3, L1/L3-L6, backward
+            if graphs:
+                graphs[0].replay()
+            else:
+                self._whole_step(b, args_a, args_b)
+            self.bank.iter += 1
+        else:
+            if graphs:
+                graphs[0].replay()
+            else:
+                self._segment_a(b, *args_a)
+            work = self.bank.all_reduce()             # async NCCL all-reduce of [sums|counts]
+            for i, part in enumerate(parts):
+                if part == "b2":
+                    self.bank.finalize(work, main.cuda_stream)   # P2: the only wait for the all-reduce
+                if graphs:
+                    graphs[1 + i].replay()
+                else:
+                    self._segment_b(b, *args_b, part=part)
+        mu = self.bank.mu
         main.wait_event(self._ev[6])
         return dict(losses=b.losses, proto_loss=b.ploss, pseudo_label=b.label, pseudo_conf=b.conf, count=b.count,
                     mixed_img=b.mixed_img, mixed_lbl=b.mixed_lbl, pseudo_weight=b.weight, mix_masks=b.mix_mask,

@@ -65,6 +65,8 @@ class ClassMixPlan:
         self._presence_np = self._presence_host.numpy().view(np.uint32)     # views of the pinned buffers
         self._chosen_np = self._chosen_host.numpy()
         self._event = torch.cuda.Event()
+        self._h2d_event = torch.cuda.Event()
+        self._h2d_pending = False
         self._batch = 0
 
     def start(self, gt: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
@@ -83,9 +85,13 @@ class ClassMixPlan:
         self._event.synchronize()
         classes = _present_classes(self._presence_np)
         chosen = draw_class_choice(classes, self._batch, rng)
+        if self._h2d_pending:
+            self._h2d_event.synchronize()      # the previous upload has read the pinned staging buffer
         self._chosen_np[: self._batch] = chosen.view(np.int32)
         dst = self._chosen[: self._batch]
         dst.copy_(self._chosen_host[: self._batch], non_blocking=True)
+        self._h2d_event.record()
+        self._h2d_pending = True
         return dst
 
 

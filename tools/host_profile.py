@@ -30,7 +30,7 @@ student = [p.to(dev) for p in model_params(wl.C, g)]
 teacher = [p.to(dev) for p in model_params(wl.C, g)]
 step = SelfTrainingStep(teacher, student, wl.C, wl.D, dev, graphs=True)
 run = lambda it: step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], inp["ema_logits"],
-                          inp["logits_trg"], inp["x_src"], inp["x_ema"])
+                          inp["logits_trg"], inp["x_src"], inp["x_ema"]) and None or step.prefetch(inp["gt"])
 for i in range(10):
     run(i)
 torch.cuda.synchronize()

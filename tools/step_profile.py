@@ -19,7 +19,7 @@ teacher = [p.to(dev) for p in model_params(wl.C, g)]
 step = SelfTrainingStep(teacher, student, wl.C, wl.D, dev, dilation=wl.dilation,
                         downscale=wl.downscale if wl.downscale != 1.0 else None, max_batch=max(wl.B, 64), graphs="--graphs" in sys.argv)
 run = lambda it: step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], inp["ema_logits"],
-                          inp["logits_trg"], inp["x_src"], inp["x_ema"])
+                          inp["logits_trg"], inp["x_src"], inp["x_ema"]) and None or step.prefetch(inp["gt"])
 for i in range(5):
     run(i)
 torch.cuda.synchronize()
