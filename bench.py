@@ -212,7 +212,9 @@ def run_ours(args, wl, rank, world, local_rank):
 
     for i in range(max(args.warmup, 3)):
         one(i)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)       # sampled on rank 0 only (one nvidia-smi poller per job)
+    if rank != 0:
+        sampler.start = lambda: None
     ema_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                  for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,7 +231,10 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop(t_wall0, t_wall1)
     step.ema_events = None
     ms = ev0.elapsed_time(ev1)
-    ema_overlapped_ms = statistics.mean(a.elapsed_time(b) for a, b in ema_pairs)
+    try:
+        ema_overlapped_ms = statistics.mean(a.elapsed_time(b) for a, b in ema_pairs)
+    except (ValueError, RuntimeError):     # the EMA is a CUDA-graph node: no per-launch events inside the step
+        ema_overlapped_ms = None
     # The dominant kernel (multi-tensor EMA) runs on its own stream inside the step and shares
     # HBM with the other kernels there, so its roofline point is taken from launches of the
     # SAME kernel/grid timed alone, on the launching stream (523 MB per launch: nothing fits in L2).
@@ -327,7 +332,7 @@ def run_ours(args, wl, rank, world, local_rank):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": ab["ema"], "us_per_launch": ema_ms * 1e3,
                          "timed": "20 launches alone after the timed steps (same grid: %d blocks/SM)" % step.ema_blocks_per_sm,
-                         "us_per_launch_overlapped_in_step": ema_overlapped_ms * 1e3}}
+                         "us_per_launch_overlapped_in_step": None if ema_overlapped_ms is None else ema_overlapped_ms * 1e3}}
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         sample_b = max(1, min(wl.B, args.ref_sample_images))

@@ -80,6 +80,15 @@ int pfst_ema_update_multi_ex(float* const* ema_ptrs, const float* const* param_p
                              int32_t chunk_elems, float a32, float b32, int32_t mode,
                              int32_t blocks_per_sm, void* stream);
 
+/* pfst_ema_update_multi_ex (mode 0) with the two coefficients read from DEVICE memory
+ * (coefs_dev = float[2] {a32, b32}, e.g. uploaded from pinned memory before a graph launch):
+ * no per-step host argument, so the launch can sit at any point of a captured CUDA graph. */
+int pfst_ema_update_multi_dev(float* const* ema_ptrs, const float* const* param_ptrs,
+                              const int64_t* numel, const int32_t* chunk_tensor,
+                              const int64_t* chunk_begin, int64_t n_chunks,
+                              int32_t chunk_elems, const float* coefs_dev,
+                              int32_t blocks_per_sm, void* stream);
+
 int pfst_ema_update_flat(float* ema, const float* param, int64_t n, float a32,
                          float b32, int32_t mode, void* stream);
 

@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(kEmaThreads)
 ema_multi_kernel(float* const* __restrict__ ema_ptrs, const float* const* __restrict__ param_ptrs,
                  const int64_t* __restrict__ numel, const int32_t* __restrict__ chunk_tensor,
                  const int64_t* __restrict__ chunk_begin, int64_t n_chunks, int32_t chunk_elems,
-                 float a, float b) {
+                 float a, float b, const float* __restrict__ coefs_dev) {
+  if (coefs_dev) {          // coefficients resident on the device: the launch is CUDA-graph capturable
+    a = coefs_dev[0];
+    b = coefs_dev[1];
+  }
   for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int32_t t = chunk_tensor[c];
     const int64_t begin = chunk_begin[c];
@@ -132,11 +136,27 @@ int pfst_ema_update_multi_ex(float* const* ema_ptrs, const float* const* param_p
   const unsigned grid = (unsigned)(n_chunks < max_grid ? n_chunks : max_grid);
   if (mode == 0)
     pfst::ema_multi_kernel<0><<<grid, pfst::kEmaThreads, 0, s>>>(
-        ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems, a32, b32);
+        ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems, a32, b32, nullptr);
   else
     pfst::ema_multi_kernel<1><<<grid, pfst::kEmaThreads, 0, s>>>(
-        ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems, a32, b32);
+        ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems, a32, b32, nullptr);
   PFST_CHECK_LAUNCH("pfst_ema_update_multi");
+  return PFST_OK;
+}
+
+int pfst_ema_update_multi_dev(float* const* ema_ptrs, const float* const* param_ptrs,
+                              const int64_t* numel, const int32_t* chunk_tensor,
+                              const int64_t* chunk_begin, int64_t n_chunks, int32_t chunk_elems,
+                              const float* coefs_dev, int32_t blocks_per_sm, void* stream) {
+  if (n_chunks == 0) return PFST_OK;
+  if (!ema_ptrs || !param_ptrs || !numel || !chunk_tensor || !chunk_begin || !coefs_dev || n_chunks < 0)
+    return PFST_ERR_INVALID_ARG;
+  if (chunk_elems <= 0 || (chunk_elems % 1024) != 0 || blocks_per_sm < 0) return PFST_ERR_INVALID_ARG;
+  const int64_t max_grid = blocks_per_sm > 0 ? (int64_t)pfst::kNumSMs * blocks_per_sm : (int64_t)pfst::kNumSMs * 8 * 64;
+  const unsigned grid = (unsigned)(n_chunks < max_grid ? n_chunks : max_grid);
+  pfst::ema_multi_kernel<0><<<grid, pfst::kEmaThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ema_ptrs, param_ptrs, numel, chunk_tensor, chunk_begin, n_chunks, chunk_elems, 0.f, 0.f, coefs_dev);
+  PFST_CHECK_LAUNCH("pfst_ema_update_multi_dev");
   return PFST_OK;
 }
 

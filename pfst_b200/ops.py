@@ -109,6 +109,19 @@ class EmaTable:
                   int(blocks_per_sm), stream)
 
 
+def _ema_update_dev(self, coefs_dev: torch.Tensor, blocks_per_sm: int = 0, stream: Optional[int] = None) -> None:
+    """EmaTable.update with {a32, b32} read from a device float[2] (graph-capturable launch)."""
+    if not self.n_chunks:
+        return
+    if stream is None:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+    _lib.call("pfst_ema_update_multi_dev", *self._ptrs, self.n_chunks, self.CHUNK,
+              _dev(coefs_dev, "coefs_dev", torch.float32), int(blocks_per_sm), stream)
+
+
+EmaTable.update_dev = _ema_update_dev
+
+
 def ema_update_flat(ema: torch.Tensor, param: torch.Tensor, a32: float, b32: float, mode: int = 0):
     if ema.shape != param.shape:
         raise ValueError("shape mismatch")

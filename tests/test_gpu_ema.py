@@ -74,3 +74,21 @@ def test_ema_flat(cuda):
     oema.ema_update(ref, [p], 5000, 0.999)
     ops.ema_update_flat(de, dp, *ops.ema_coeffs(5000, 0.999))
     assert torch.equal(de.cpu(), ref[0])
+
+
+def test_ema_device_coefficients_and_bounded_grid(cuda):
+    """pfst_ema_update_multi_dev (coefficients read from device memory: graph-capturable) and the
+    bounded persistent grid give the same bits as the host-argument launch."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(3,), (4097,), (64, 3, 3, 3), (1,), (100003,)]
+    stu = [(0.02 * torch.randn(s, generator=g)).to(cuda) for s in shapes]
+    tea_a = [(0.02 * torch.randn(s, generator=g)).to(cuda) for s in shapes]
+    tea_b = [t.clone() for t in tea_a]
+    tea_c = [t.clone() for t in tea_a]
+    a32, b32 = ops.ema_coeffs(37, 0.999)
+    ops.EmaTable(tea_a, stu).update(a32, b32)
+    ops.EmaTable(tea_b, stu).update(a32, b32, blocks_per_sm=2)
+    coefs = torch.tensor([a32, b32], dtype=torch.float32, device=cuda)
+    ops.EmaTable(tea_c, stu).update_dev(coefs, blocks_per_sm=3)
+    for x, y, z in zip(tea_a, tea_b, tea_c):
+        assert torch.equal(x, y) and torch.equal(x, z)

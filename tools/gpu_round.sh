@@ -10,6 +10,10 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; e
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref rc=$?"; cat gpurun_out/${tag}_bench_ref.json
 python tools/step_profile.py cfg2 > gpurun_out/${tag}_step_profile.txt 2>&1; echo "step_profile rc=$?"
 python tools/kbench.py > gpurun_out/${tag}_kbench.jsonl 2>&1; echo "kbench rc=$?"
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_short.json 2> gpurun_out/${tag}_bench_short.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
+    --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
+echo "ncu bench launches rc=$?"
 python tools/one_step.py cfg2 2 > gpurun_out/${tag}_one_step.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/${tag}_launches.csv python tools/one_step.py cfg2 2 > gpurun_out/${tag}_ncu_launches.log 2>&1
