@@ -300,6 +300,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms = times.tolist()
+    step.release_graphs()          # the graphs hold NCCL work: drop them before the process group goes
     if rank != 0:
         return
     px = wl.B * wl.H * wl.W

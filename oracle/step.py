@@ -13,9 +13,10 @@ from . import ema as oema, mixing as omix, pfgst_loss as OL, prototypes as OP, p
 
 
 def hot_path_step(it, teacher, student, inp, C, alpha=0.999, thr=0.98, loss_cfg=None, proto_state=None,
-                  proto_weight=0.1, rng=np.random, timings=None):
+                  proto_weight=0.1, rng=np.random, timings=None, peer_protos=None):
     """inp: dict(img, target_img_strong_aug, gt, ema_logits, logits_trg, x_src, x_ema) CPU tensors.
-    Returns dict of outputs; `timings` (dict) receives per-phase seconds."""
+    Returns dict of outputs; `timings` (dict) receives per-phase seconds. `peer_protos`: list of
+    (sums, counts) accumulated by the other ranks (what the NCCL all-reduce contributes)."""
     loss_cfg = loss_cfg or OL.LossCfg()
     t0 = time.perf_counter()
     if it == 0:
@@ -36,6 +37,8 @@ def hot_path_step(it, teacher, student, inp, C, alpha=0.999, thr=0.98, loss_cfg=
     total = sum(res[k] for k in OL.LOSS_KEYS)
     # prototypes (float64 sums -> fp32 prototypes), distance loss on the source features
     sums, counts = OP.proto_accumulate(inp["x_ema"], label, C)
+    for ps, pc in (peer_protos or []):          # multi-rank: the all-reduce adds the other ranks' sums / counts
+        sums, counts = sums + ps, counts + pc
     mu_prev, seen_prev, pit = proto_state if proto_state is not None else (None, None, 0)
     a = oema.alpha_teacher(max(pit, 1), alpha)
     mu, seen = OP.proto_finalize(sums, counts, mu_prev, seen_prev, float(np.float32(a)), float(np.float32(1 - a)))

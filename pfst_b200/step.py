@@ -96,6 +96,7 @@ class SelfTrainingStep:
         self.graphs = bool(graphs)
         self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
         self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
+        self.nccl_in_graph = os.environ.get("PFST_NCCL_IN_GRAPH", "1") != "0"
         self.ema_at = os.environ.get("PFST_EMA_AT", "start")   # 'start': with segment A; 'b': with segment B
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
@@ -103,7 +104,8 @@ class SelfTrainingStep:
         self._side = torch.cuda.Stream(device=self.device)
         self._ema_stream = torch.cuda.Stream(device=self.device)
         self._aux = torch.cuda.Stream(device=self.device)
-        self._ev = [torch.cuda.Event() for _ in range(8)]
+        self._comm = torch.cuda.Stream(device=self.device)
+        self._ev = [torch.cuda.Event() for _ in range(10)]
         self._world = None        # world size, resolved on first use
         self._prefetched = None   # data_ptr of the gt whose presence bits are in flight
 
@@ -122,7 +124,7 @@ class SelfTrainingStep:
         main.wait_event(join)
         self.bank.accumulate(x_ema, b.label)                      # x_ema again: L2 hits
 
-    def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo, part="all"):
+    def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo, part="all", mu_ready=None):
         """part 'all': the whole segment (single rank: the prototypes are final before it starts).
         Multi-rank: 'b1' = everything that does not need the prototypes (runs while the NCCL
         all-reduce is in flight), then proto_finalize, then 'b2' = distance forward + fused backward."""
@@ -145,6 +147,8 @@ class SelfTrainingStep:
                 ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
                 dots_done.record(self._side)
                 if part == "all":
+                    if mu_ready is not None:                      # prototypes come from another branch
+                        self._side.wait_event(mu_ready)
                     dist_fwd()
                     join.record(self._side)
             _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), img.data_ptr(), trg_img.data_ptr(),
@@ -175,12 +179,26 @@ class SelfTrainingStep:
             self._world = dist.get_world_size(self.bank.group) if dist.is_available() and dist.is_initialized() else 1
         return self._world > 1
 
-    def _whole_step(self, b, args_a, args_b):
-        """Single rank: segment A, proto_finalize (device-resident iteration) and segment B in one
-        stream-ordered sequence — ONE CUDA graph per step."""
+    def _whole_step(self, b, args_a, args_b, reduce: bool = False):
+        """Segment A, proto_finalize (device-resident iteration) and segment B as one stream-ordered
+        sequence — ONE CUDA graph per step. reduce=True (multi-rank): the NCCL all-reduce of the
+        packed [sums|counts] buffer and proto_finalize run on a forked branch next to ClassMix and
+        neigh_dots(x_src); only the prototype distance waits for them."""
         self._segment_a(b, *args_a)
-        self.bank.finalize_captured(ops._stream())
-        self._segment_b(b, *args_b, part="all")
+        if not reduce:
+            self.bank.finalize_captured(ops._stream())
+            self._segment_b(b, *args_b, part="all")
+            return
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        fork, mu_ready = self._ev[8], self._ev[9]
+        fork.record(main)
+        self._comm.wait_event(fork)
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(self.bank.packed, op=dist.ReduceOp.SUM, group=self.bank.group)
+            self.bank.finalize_captured(self._comm.cuda_stream)
+            mu_ready.record(self._comm)
+        self._segment_b(b, *args_b, part="all", mu_ready=mu_ready)
 
     def _captured(self, key, b, args_a, args_b, parts):
         """CUDA graphs for one set of input addresses, captured after a warm-up pass on a side
@@ -193,8 +211,8 @@ class SelfTrainingStep:
         side.wait_stream(torch.cuda.current_stream())
         snap = [t.clone() for t in (bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state)]
         with torch.cuda.stream(side):              # warm-up: module load, cudaFuncSetAttribute
-            if parts == ("all",):
-                self._whole_step(b, args_a, args_b)
+            if parts == ("all",) or parts == ("reduce",):
+                self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
             else:
                 self._segment_a(b, *args_a)
                 for part in parts:
@@ -202,10 +220,10 @@ class SelfTrainingStep:
         torch.cuda.current_stream().wait_stream(side)
         for t, c in zip((bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state), snap):
             t.copy_(c)                             # the warm-up touched the prototype bank
-        if parts == ("all",):
+        if parts == ("all",) or parts == ("reduce",):
             graphs = [torch.cuda.CUDAGraph()]
             with torch.cuda.graph(graphs[0]):
-                self._whole_step(b, args_a, args_b)
+                self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
         else:
             graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
             with torch.cuda.graph(graphs[0]):
@@ -215,6 +233,13 @@ class SelfTrainingStep:
                     self._segment_b(b, *args_b, part=part)
         self._graphs[key] = graphs
         return graphs
+
+    def release_graphs(self) -> None:
+        """Drop the captured CUDA graphs. On multi-rank runs they contain NCCL work: release them
+        (or the whole object) BEFORE destroying the process group, or the communicator teardown
+        can wait forever for resources the graphs still hold."""
+        torch.cuda.synchronize(self.device)
+        self._graphs.clear()
 
     def prefetch(self, gt, wait_stream: Optional[torch.cuda.Stream] = None) -> None:
         """M1 part 1 for the NEXT run(): class-presence kernel + its 36-byte D2H on the auxiliary
@@ -271,7 +296,10 @@ class SelfTrainingStep:
         chosen_buf = self.plan._chosen[:B]
         args_b = (img, trg_img, gt, chosen_buf, logits_trg, x_src, geo)
         split = self._multi_rank() if self.split_for_allreduce is None else bool(self.split_for_allreduce)
-        parts = ("b1", "b2") if split else ("all",)
+        # multi-rank: one graph with the collective inside ("reduce"), or three graphs around an
+        # eagerly issued all-reduce ("b1","b2") when NCCL graph capture is switched off
+        parts = (("reduce",) if self.graphs and self.nccl_in_graph and self._multi_rank() else ("b1", "b2")) if split \
+            else ("all",)
         graphs = None
         if self.graphs:
             pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
@@ -289,12 +317,12 @@ class SelfTrainingStep:
             if self.ema_events is not None:
                 self.ema_events[1].record(main)
             self._ev[6].record(main)
-        if not split:
-            # S1/S2, L2(x_ema), P1 -> P2 -> M2, L2(x_src), P3, L1/L3-L6, backward
+        if len(parts) == 1:
+            # S1/S2, L2(x_ema), P1 -> (all-reduce) P2 -> M2, L2(x_src), P3, L1/L3-L6, backward
             if graphs:
                 graphs[0].replay()
             else:
-                self._whole_step(b, args_a, args_b)
+                self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
             self.bank.iter += 1
         else:
             if graphs:
