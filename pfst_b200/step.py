@@ -75,6 +75,9 @@ class SelfTrainingStep:
     # accum, EMA, finalize, mix, dots(x_src), dist fwd, loss prep, loss fwd, loss bwd,
     # grad+dist bwd; memsets, copies and NCCL are not counted
     KERNEL_LAUNCHES = 13
+    # executable-graph instances used alternately: launching an instance that is still running makes
+    # the host wait for it, so with one instance the host could never run ahead of the device
+    GRAPH_INSTANCES = int(os.environ.get("PFST_GRAPH_INSTANCES", "2"))
 
     def __init__(self, teacher_params, student_params, num_classes: int, feat_dim: int, device,
                  alpha: float = 0.999, pseudo_threshold: float = 0.98, dilation: int = 2, top_k: int = 3,
@@ -103,11 +106,12 @@ class SelfTrainingStep:
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
         self._side = torch.cuda.Stream(device=self.device)
         self._ema_stream = torch.cuda.Stream(device=self.device)
-        self._aux = torch.cuda.Stream(device=self.device)
+        self._aux = torch.cuda.Stream(device=self.device, priority=-1)   # tiny, latency-critical for the host
         self._comm = torch.cuda.Stream(device=self.device)
         self._ev = [torch.cuda.Event() for _ in range(10)]
         self._world = None        # world size, resolved on first use
         self._prefetched = None   # data_ptr of the gt whose presence bits are in flight
+        self._step_count = 0
 
     # ------------------------------------------------------------------ segments
     def _segment_a(self, b: _Buffers, ema_logits, x_ema, geo):
@@ -220,17 +224,21 @@ class SelfTrainingStep:
         torch.cuda.current_stream().wait_stream(side)
         for t, c in zip((bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state), snap):
             t.copy_(c)                             # the warm-up touched the prototype bank
-        if parts == ("all",) or parts == ("reduce",):
-            graphs = [torch.cuda.CUDAGraph()]
-            with torch.cuda.graph(graphs[0]):
-                self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
-        else:
-            graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
-            with torch.cuda.graph(graphs[0]):
-                self._segment_a(b, *args_a)
-            for g, part in zip(graphs[1:], parts):
-                with torch.cuda.graph(g):
-                    self._segment_b(b, *args_b, part=part)
+        sets = []
+        for _ in range(self.GRAPH_INSTANCES):      # ping-pong instances: an executable graph cannot overlap itself
+            if parts == ("all",) or parts == ("reduce",):
+                graphs = [torch.cuda.CUDAGraph()]
+                with torch.cuda.graph(graphs[0]):
+                    self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
+            else:
+                graphs = [torch.cuda.CUDAGraph() for _ in range(1 + len(parts))]
+                with torch.cuda.graph(graphs[0]):
+                    self._segment_a(b, *args_a)
+                for g, part in zip(graphs[1:], parts):
+                    with torch.cuda.graph(g):
+                        self._segment_b(b, *args_b, part=part)
+            sets.append(graphs)
+        graphs = sets
         self._graphs[key] = graphs
         return graphs
 
@@ -303,7 +311,9 @@ class SelfTrainingStep:
         graphs = None
         if self.graphs:
             pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))
-            graphs = self._captured(pkey, b, args_a, args_b, parts)
+            sets = self._captured(pkey, b, args_a, args_b, parts)
+            graphs = sets[self._step_count % len(sets)]
+        self._step_count += 1
         self.plan.choose(rng)                          # waits for the 36-byte copy only
         if self.ema_at == "start":
             self._launch_ema(it, main)

@@ -56,42 +56,57 @@ class ClassMixPlan:
     waits for that copy only, draws the classes on the host and uploads the per-image
     bitmasks. This hides the one unavoidable host round trip."""
 
+    SLOTS = 4     # pinned staging slots: the host may run this many steps ahead of the device
+
     def __init__(self, device: torch.device, max_batch: int = 256):
         self.device = device
+        K = self.SLOTS
         self._presence = torch.empty(9, dtype=torch.int32, device=device)
-        self._presence_host = torch.empty(9, dtype=torch.int32).pin_memory()
-        self._chosen_host = torch.empty((max_batch, 8), dtype=torch.int32).pin_memory()
+        self._presence_host = torch.empty((K, 9), dtype=torch.int32).pin_memory()
+        self._chosen_host = torch.empty((K, max_batch, 8), dtype=torch.int32).pin_memory()
         self._chosen = torch.empty((max_batch, 8), dtype=torch.int32, device=device)
         self._presence_np = self._presence_host.numpy().view(np.uint32)     # views of the pinned buffers
         self._chosen_np = self._chosen_host.numpy()
-        self._event = torch.cuda.Event()
-        self._h2d_event = torch.cuda.Event()
-        self._h2d_pending = False
+        self._events = [torch.cuda.Event() for _ in range(K)]               # presence D2H done, per slot
+        self._h2d_events = [torch.cuda.Event() for _ in range(K)]           # upload has read the slot
+        self._h2d_pending = [False] * K
+        self._started, self._chosen_count = 0, 0                            # start() / choose() calls so far
+        self._batches = [0] * K
         self._batch = 0
 
     def start(self, gt: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
-        self._batch = gt.shape[0]
-        if self._batch > self._chosen.shape[0]:
+        if self._started - self._chosen_count >= self.SLOTS:
+            raise PfstError("ClassMixPlan: more start() calls in flight than staging slots")
+        slot = self._started % self.SLOTS
+        self._started += 1
+        batch = gt.shape[0]
+        if batch > self._chosen.shape[0]:
             raise ValueError("batch larger than the plan's capacity")
+        self._batches[slot] = batch
         if stream is None:
             stream = torch.cuda.current_stream()
         _lib.call("pfst_class_presence", ops._dev(gt, "gt", torch.int64), gt.numel(), self._presence.data_ptr(),
                   stream.cuda_stream)
         with torch.cuda.stream(stream):
-            self._presence_host.copy_(self._presence, non_blocking=True)
-        self._event.record(stream)
+            self._presence_host[slot].copy_(self._presence, non_blocking=True)
+        self._events[slot].record(stream)
 
     def choose(self, rng=np.random) -> torch.Tensor:
-        self._event.synchronize()
-        classes = _present_classes(self._presence_np)
-        chosen = draw_class_choice(classes, self._batch, rng)
-        if self._h2d_pending:
-            self._h2d_event.synchronize()      # the previous upload has read the pinned staging buffer
-        self._chosen_np[: self._batch] = chosen.view(np.int32)
-        dst = self._chosen[: self._batch]
-        dst.copy_(self._chosen_host[: self._batch], non_blocking=True)
-        self._h2d_event.record()
-        self._h2d_pending = True
+        if self._chosen_count >= self._started:
+            raise PfstError("ClassMixPlan.choose() without a matching start()")
+        slot = self._chosen_count % self.SLOTS
+        self._chosen_count += 1
+        self._batch = batch = self._batches[slot]
+        self._events[slot].synchronize()
+        classes = _present_classes(self._presence_np[slot])
+        chosen = draw_class_choice(classes, batch, rng)
+        if self._h2d_pending[slot]:
+            self._h2d_events[slot].synchronize()   # the upload issued SLOTS steps ago has read this slot
+        self._chosen_np[slot, :batch] = chosen.view(np.int32)
+        dst = self._chosen[:batch]
+        dst.copy_(self._chosen_host[slot, :batch], non_blocking=True)
+        self._h2d_events[slot].record()
+        self._h2d_pending[slot] = True
         return dst
 
 
