@@ -293,7 +293,7 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
 // feature pixel (up = 1 unless the features are coarser than the loss grid).
 constexpr int kLpMaxOwn = (kMaxC + 8) / 9;     // classes a tap-thread owns in the logits gradient
 
-__global__ void __launch_bounds__(kLpThreads)
+__global__ void __launch_bounds__(kLpThreads, 3)
 pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, const float* __restrict__ gout,
                       float* __restrict__ coef, float* __restrict__ grad_logits) {
   __shared__ float s_se[9][kLpPix];
