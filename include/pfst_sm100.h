@@ -255,6 +255,23 @@ int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_
                      const float* conf, float conf_thr, int32_t C, float* packed,
                      void* stream);
 
+/* pfst_proto_accum split in two, so that the label sort is done ONCE per (image, tile) and
+ * not by every streaming block:
+ *   pfst_proto_order          builds, per 4096-pixel tile of every image, the list of pixel
+ *                             offsets sorted by class (labels nearest-resampled to (h,w), confidence
+ *                             mask applied) into `workspace` (pfst_proto_order_ws_bytes() bytes,
+ *                             16-byte aligned) and adds the per-class pixel counts to counts[C]
+ *                             (nullable; pass packed + C*D);
+ *   pfst_proto_accum_ordered  streams the feature planes against those lists:
+ *                             packed[c*D+d] += sum of feats over the pixels of class c.
+ * Together they equal pfst_proto_accum.                                                 */
+int64_t pfst_proto_order_ws_bytes(int64_t B, int32_t h, int32_t w, int32_t C);
+int pfst_proto_order(const int64_t* labels, int64_t B, int32_t h, int32_t w, int32_t lab_h,
+                     int32_t lab_w, const float* conf, float conf_thr, int32_t C, float* counts,
+                     void* workspace, void* stream);
+int pfst_proto_accum_ordered(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+                             int32_t C, const void* workspace, float* packed, void* stream);
+
 /* mu_out[c] = packed sums / max(count,1) for classes with pixels; classes already
  * seen (seen_prev[c] != 0) are EMA-updated fl(fl(a32*mu_prev)+fl(b32*mean)) (the E2
  * rule); classes without pixels keep mu_prev. mu_prev / seen_prev may be NULL

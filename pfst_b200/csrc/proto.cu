@@ -56,7 +56,7 @@ __host__ __device__ inline PaLayout pa_layout(int tile, int stages, int C) {
   L.off_order = o; o += ((size_t)(tile + 32 * C + 256) * 2 + 15) / 16 * 16;  // u16 offsets (+ a padding block of rows)
   L.off_grp = o;   o += ((size_t)((tile + 31) / 32) * C * 2 + 15) / 16 * 16;  // u16 [groups][C]
   L.off_rows = o;  o += ((size_t)((tile + 31) / 32 + C + 8) + 15) / 16 * 16;   // u8 class of every 32-entry row
-  L.off_seg = o;   o += (size_t)(2 * C + 2) * sizeof(int);                    // seg[C+1], tot[C]
+  L.off_seg = o;   o += ((size_t)(2 * C + 2) * sizeof(int) + 15) / 16 * 16;   // seg[C+1], tot[C]
   L.total = o;
   return L;
 }
@@ -65,11 +65,16 @@ __device__ __forceinline__ void pa_sync_consumers() {
   asm volatile("bar.sync 1, %0;" ::"n"(kPaConsumers * 32) : "memory");
 }
 
+// MODE 0: self-contained (sort + stream). MODE 1: sort only — one block per (image, tile) writes
+// the class-sorted lists to `ws` (and the pixel counts to `counts`). MODE 2: stream only — the
+// lists are copied from `ws`, so the ~18 us sort prologue is paid by 8 blocks once instead of by
+// every one of the 144 streaming blocks.
+template <int MODE>
 __global__ void __launch_bounds__(kPaThreads)
 proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
                    const int64_t* __restrict__ labels, const float* __restrict__ conf, float conf_thr,
                    int lab_h, int lab_w, int C, int groups, int tile, int stages, int use_bulk,
-                   float* __restrict__ packed) {
+                   float* __restrict__ packed, float* __restrict__ counts, unsigned char* __restrict__ ws) {
   extern __shared__ __align__(128) unsigned char pa_smem[];
   __shared__ uint64_t full_bar[kPaMaxStages], empty_bar[kPaMaxStages];
   __shared__ int issued;          // number of planes the producer has issued so far
@@ -93,6 +98,8 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* base = feats + ((int64_t)b * D + ch0) * hw + p0;
 
+  const size_t list_bytes = L.total - L.off_order;           // order | grp | rowcls | seg, tot
+  unsigned char* ws_tile = ws ? ws + ((size_t)b * n_tiles + tile_id) * list_bytes : nullptr;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -105,7 +112,7 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   __syncthreads();
 
   if (warp == kPaConsumers) {          // ---- producer: stream the channel planes
-    if (lane == 0 && use_bulk) {
+    if (MODE != 1 && lane == 0 && use_bulk) {
       const uint32_t bytes = (uint32_t)np * sizeof(float);
       for (int i = 0; i < n_items; ++i) {
         const int s = i % stages;
@@ -118,108 +125,121 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
     return;
   }
 
-  // ---- consumers: class-sorted offset list of this tile (stable counting sort) ----------
-  const int ng = (np + 31) / 32;                    // 32-pixel groups, <= kPaTile / 32
-  constexpr int kGroupsPerWarp = kPaTile / 32 / kPaConsumers;
-  const float sh = (float)lab_h / (float)h, sw = (float)lab_w / (float)w;
-  for (int i = threadIdx.x; i < ng * C; i += kPaConsumers * 32) grp[i] = 0;
-  // all label gathers of this warp's groups in flight at once (one memory latency, not 16)
-  unsigned lv[kGroupsPerWarp];
-  {
-    int64_t off[kGroupsPerWarp], raw[kGroupsPerWarp];
-#pragma unroll
-    for (int u = 0; u < kGroupsPerWarp; ++u) {           // addresses first ...
-      const int p = p0 + (warp + u * kPaConsumers) * 32 + lane;
-      const int y = p / w, x = p - y * w;
-      off[u] = ((int64_t)b * lab_h + pr_nearest(y, sh, lab_h)) * lab_w + pr_nearest(x, sw, lab_w);
+  if (MODE == 2) {      // ---- the lists were built by the MODE 1 launch: copy them in
+    const uint4* src = reinterpret_cast<const uint4*>(ws_tile);
+    uint4* dst = reinterpret_cast<uint4*>(pa_smem + L.off_order);
+    for (int i = threadIdx.x; i < (int)(list_bytes / 16); i += kPaConsumers * 32) dst[i] = src[i];
+    pa_sync_consumers();
+  } else {
+    // ---- consumers: class-sorted offset list of this tile (stable counting sort) ----------
+    const int ng = (np + 31) / 32;                    // 32-pixel groups, <= kPaTile / 32
+    constexpr int kGroupsPerWarp = kPaTile / 32 / kPaConsumers;
+    const float sh = (float)lab_h / (float)h, sw = (float)lab_w / (float)w;
+    for (int i = threadIdx.x; i < ng * C; i += kPaConsumers * 32) grp[i] = 0;
+    // all label gathers of this warp's groups in flight at once (one memory latency, not 16)
+    unsigned lv[kGroupsPerWarp];
+    {
+      int64_t off[kGroupsPerWarp], raw[kGroupsPerWarp];
+  #pragma unroll
+      for (int u = 0; u < kGroupsPerWarp; ++u) {           // addresses first ...
+        const int p = p0 + (warp + u * kPaConsumers) * 32 + lane;
+        const int y = p / w, x = p - y * w;
+        off[u] = ((int64_t)b * lab_h + pr_nearest(y, sh, lab_h)) * lab_w + pr_nearest(x, sw, lab_w);
+      }
+  #pragma unroll
+      for (int u = 0; u < kGroupsPerWarp; ++u)             // ... then every load back to back
+        raw[u] = (warp + u * kPaConsumers) * 32 + lane < np ? __ldg(labels + off[u]) : (int64_t)-1;
+  #pragma unroll
+      for (int u = 0; u < kGroupsPerWarp; ++u) {
+        bool ok = raw[u] >= 0 && raw[u] < C;
+        if (conf && ok) ok = __ldg(conf + off[u]) >= conf_thr;
+        lv[u] = ok ? (unsigned)raw[u] : 255u;
+      }
     }
-#pragma unroll
-    for (int u = 0; u < kGroupsPerWarp; ++u)             // ... then every load back to back
-      raw[u] = (warp + u * kPaConsumers) * 32 + lane < np ? __ldg(labels + off[u]) : (int64_t)-1;
-#pragma unroll
+    pa_sync_consumers();
+  #pragma unroll
     for (int u = 0; u < kGroupsPerWarp; ++u) {
-      bool ok = raw[u] >= 0 && raw[u] < C;
-      if (conf && ok) ok = __ldg(conf + off[u]) >= conf_thr;
-      lv[u] = ok ? (unsigned)raw[u] : 255u;
+      const int g = warp + u * kPaConsumers;
+      if (g < ng) {                                    // warp-uniform
+        const unsigned m = __match_any_sync(0xffffffffu, lv[u]);
+        if (lv[u] != 255u && lane == __ffs(m) - 1) grp[g * C + lv[u]] = (uint16_t)__popc(m);
+      }
     }
-  }
-  pa_sync_consumers();
-#pragma unroll
-  for (int u = 0; u < kGroupsPerWarp; ++u) {
-    const int g = warp + u * kPaConsumers;
-    if (g < ng) {                                    // warp-uniform
-      const unsigned m = __match_any_sync(0xffffffffu, lv[u]);
-      if (lv[u] != 255u && lane == __ffs(m) - 1) grp[g * C + lv[u]] = (uint16_t)__popc(m);
-    }
-  }
-  pa_sync_consumers();
-  // exclusive scan over the groups, one warp per class: lane owns 4 consecutive groups
-  for (int c = warp; c < C; c += kPaConsumers) {
-    int v[4], run = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = lane * 4 + k;
-      v[k] = g < ng ? grp[g * C + c] : 0;
-      run += v[k];
-    }
-    int incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    int excl = incl - run;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = lane * 4 + k;
-      if (g < ng) grp[g * C + c] = (uint16_t)excl;
-      excl += v[k];
-    }
-    if (lane == 31) tot[c] = incl;
-  }
-  pa_sync_consumers();
-  if (warp == 0) {                                   // padded segment offsets: scan over the classes
-    int carry = 0;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int c = c0 + lane;
-      const int len = c < C ? (tot[c] + 31) & ~31 : 0;
-      int incl = len;
-#pragma unroll
+    pa_sync_consumers();
+    // exclusive scan over the groups, one warp per class: lane owns 4 consecutive groups
+    for (int c = warp; c < C; c += kPaConsumers) {
+      int v[4], run = 0;
+  #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = lane * 4 + k;
+        v[k] = g < ng ? grp[g * C + c] : 0;
+        run += v[k];
+      }
+      int incl = run;
+  #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (c < C) seg[c] = carry + incl - len;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+      int excl = incl - run;
+  #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = lane * 4 + k;
+        if (g < ng) grp[g * C + c] = (uint16_t)excl;
+        excl += v[k];
+      }
+      if (lane == 31) tot[c] = incl;
     }
-    if (lane == 0) seg[C] = carry;
-  }
-  pa_sync_consumers();
-#pragma unroll
-  for (int u = 0; u < kGroupsPerWarp; ++u) {
-    const int g = warp + u * kPaConsumers;
-    if (g < ng) {
-      const unsigned l = lv[u];
-      const unsigned m = __match_any_sync(0xffffffffu, l);
-      if (l != 255u) order[seg[l] + grp[g * C + l] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g * 32 + lane);
+    pa_sync_consumers();
+    if (warp == 0) {                                   // padded segment offsets: scan over the classes
+      int carry = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int len = c < C ? (tot[c] + 31) & ~31 : 0;
+        int incl = len;
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (c < C) seg[c] = carry + incl - len;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) seg[C] = carry;
     }
-  }
-  for (int c = warp; c < C; c += kPaConsumers) {              // pad every segment with the zero slot
-    const int j = seg[c] + tot[c] + lane;
-    if (j < seg[c + 1]) order[j] = (uint16_t)np;
-    for (int r = seg[c] / 32 + lane; r < seg[c + 1] / 32; r += 32) rowcls[r] = (uint8_t)c;
-  }
-  {   // rows are consumed eight at a time: pad the list to a multiple of 8 rows (class 255, zero slot)
-    const int n_rows = seg[C] / 32, n_pad = ((n_rows + 7) & ~7) - n_rows;
-    for (int i = threadIdx.x; i < n_pad * 32; i += kPaConsumers * 32) order[n_rows * 32 + i] = (uint16_t)np;
-    if (threadIdx.x < n_pad) rowcls[n_rows + threadIdx.x] = 255;
-  }
-  // pixel counts: once per (image, tile), by channel group 0
-  if (grp_id == 0)
-    for (int c = threadIdx.x; c < C; c += kPaConsumers * 32)
-      if (tot[c]) atomicAdd(&packed[(int64_t)C * D + c], (float)tot[c]);
-  pa_sync_consumers();
+    pa_sync_consumers();
+  #pragma unroll
+    for (int u = 0; u < kGroupsPerWarp; ++u) {
+      const int g = warp + u * kPaConsumers;
+      if (g < ng) {
+        const unsigned l = lv[u];
+        const unsigned m = __match_any_sync(0xffffffffu, l);
+        if (l != 255u) order[seg[l] + grp[g * C + l] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(g * 32 + lane);
+      }
+    }
+    for (int c = warp; c < C; c += kPaConsumers) {              // pad every segment with the zero slot
+      const int j = seg[c] + tot[c] + lane;
+      if (j < seg[c + 1]) order[j] = (uint16_t)np;
+      for (int r = seg[c] / 32 + lane; r < seg[c + 1] / 32; r += 32) rowcls[r] = (uint8_t)c;
+    }
+    {   // rows are consumed eight at a time: pad the list to a multiple of 8 rows (class 255, zero slot)
+      const int n_rows = seg[C] / 32, n_pad = ((n_rows + 7) & ~7) - n_rows;
+      for (int i = threadIdx.x; i < n_pad * 32; i += kPaConsumers * 32) order[n_rows * 32 + i] = (uint16_t)np;
+      if (threadIdx.x < n_pad) rowcls[n_rows + threadIdx.x] = 255;
+    }
+    // pixel counts: once per (image, tile), by channel group 0
+    if (grp_id == 0 && counts)
+      for (int c = threadIdx.x; c < C; c += kPaConsumers * 32)
+        if (tot[c]) atomicAdd(&counts[c], (float)tot[c]);
+    pa_sync_consumers();
 
+    if (MODE == 1) {    // ---- sort-only launch: publish the lists
+      const uint4* src = reinterpret_cast<const uint4*>(pa_smem + L.off_order);
+      uint4* dst = reinterpret_cast<uint4*>(ws_tile);
+      for (int i = threadIdx.x; i < (int)(list_bytes / 16); i += kPaConsumers * 32) dst[i] = src[i];
+      return;
+    }
+  }
   // ---- consumers: one channel plane per warp per turn ------------------------------------
   for (int i = warp; i < n_items; i += kPaConsumers) {
     const int s = use_bulk ? i % stages : warp;
@@ -523,6 +543,59 @@ proto_dist_all_kernel(const float* __restrict__ feats, int B, int D, int h, int 
 
 }  // namespace pfst
 
+namespace {
+
+struct PaPlan {
+  int tile, n_tiles, stages, use_bulk;
+  int64_t groups;
+  pfst::PaLayout L;
+  size_t list_bytes;
+};
+
+// Launch geometry shared by the three accumulate entry points (stream = with plane stages).
+int pa_plan(PaPlan& P, const float* feats, int64_t B, int32_t D, int32_t h, int32_t w, int32_t C, bool stream) {
+  const int64_t hw = (int64_t)h * w;
+  P.tile = (int)(hw < pfst::kPaTile ? hw : pfst::kPaTile);
+  P.n_tiles = (int)((hw + P.tile - 1) / P.tile);
+  // bulk async copies need 16-byte aligned planes whose tiles are multiples of 16 bytes
+  P.use_bulk = (hw % 4 == 0) && (!feats || pfst::aligned16(feats)) ? 1 : 0;
+  if (getenv("PFST_ACCUM_NO_BULK")) P.use_bulk = 0;   // debugging aid
+  P.stages = 0;
+  if (stream) {   // stages: as many as fit next to the sort buffers, at least one per consumer warp + 1
+    P.stages = pfst::kPaMaxStages;
+    while (P.stages > pfst::kPaConsumers + 1 && pfst::pa_layout(P.tile, P.stages, C).total > 200 * 1024) --P.stages;
+  }
+  P.L = pfst::pa_layout(P.tile, P.stages, C);
+  if (P.L.total > 200 * 1024) return PFST_ERR_UNSUPPORTED;
+  P.list_bytes = P.L.total - P.L.off_order;
+  // channel groups: fill every SM's shared memory with blocks, keep >= 2 planes per consumer warp
+  int per_sm = (int)((220 * 1024) / (P.L.total + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
+  P.groups = ((int64_t)pfst::kNumSMs * per_sm) / (B * P.n_tiles);
+  const int64_t max_groups = (D + 2 * pfst::kPaConsumers - 1) / (2 * pfst::kPaConsumers);
+  if (P.groups > max_groups) P.groups = max_groups;
+  if (P.groups < 1) P.groups = 1;
+  if (B * P.n_tiles * P.groups > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+  return PFST_OK;
+}
+
+template <int MODE>
+int pa_launch(const PaPlan& P, const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
+              const int64_t* labels, int32_t lab_h, int32_t lab_w, const float* conf, float conf_thr, int32_t C,
+              float* packed, float* counts, unsigned char* ws, cudaStream_t s, const char* what) {
+  auto k = pfst::proto_accum_kernel<MODE>;
+  PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.L.total), what);
+  const int64_t groups = MODE == 1 ? 1 : P.groups;
+  k<<<(unsigned)(B * P.n_tiles * groups), pfst::kPaThreads, P.L.total, s>>>(
+      feats, (int)B, D, h, w, labels, conf, conf_thr, lab_h, lab_w, C, (int)groups, P.tile, P.stages, P.use_bulk,
+      packed, counts, ws);
+  PFST_CHECK_LAUNCH(what);
+  return PFST_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
@@ -532,34 +605,45 @@ int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_
     return PFST_ERR_INVALID_ARG;
   if (C > pfst::kPrMaxC) return PFST_ERR_UNSUPPORTED;
   if (B == 0) return PFST_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t hw = (int64_t)h * w;
-  const int tile = (int)(hw < pfst::kPaTile ? hw : pfst::kPaTile);
-  const int n_tiles = (int)((hw + tile - 1) / tile);
-  // bulk async copies need 16-byte aligned planes whose tiles are multiples of 16 bytes
-  int use_bulk = (hw % 4 == 0) && pfst::aligned16(feats) ? 1 : 0;
-  if (getenv("PFST_ACCUM_NO_BULK")) use_bulk = 0;   // debugging aid
-  // stages: as many as fit next to the sort buffers, at least one per consumer warp + 1
-  int stages = pfst::kPaMaxStages;
-  while (stages > pfst::kPaConsumers + 1 && pfst::pa_layout(tile, stages, C).total > 200 * 1024) --stages;
-  const pfst::PaLayout L = pfst::pa_layout(tile, stages, C);
-  if (L.total > 200 * 1024) return PFST_ERR_UNSUPPORTED;
-  PFST_CUDA_TRY(cudaFuncSetAttribute(pfst::proto_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)L.total), "pfst_proto_accum/attr");
-  // channel groups: fill every SM's shared memory with blocks, keep >= 2 planes per consumer warp
-  int per_sm = (int)((220 * 1024) / (L.total + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 6) per_sm = 6;
-  int64_t groups = ((int64_t)pfst::kNumSMs * per_sm) / (B * n_tiles);
-  const int64_t max_groups = (D + 2 * pfst::kPaConsumers - 1) / (2 * pfst::kPaConsumers);
-  if (groups > max_groups) groups = max_groups;
-  if (groups < 1) groups = 1;
-  const int64_t grid = B * n_tiles * groups;
-  if (grid > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
-  pfst::proto_accum_kernel<<<(unsigned)grid, pfst::kPaThreads, L.total, s>>>(
-      feats, (int)B, D, h, w, labels, conf, conf_thr, lab_h, lab_w, C, (int)groups, tile, stages, use_bulk, packed);
-  PFST_CHECK_LAUNCH("pfst_proto_accum");
-  return PFST_OK;
+  PaPlan P;
+  const int rc = pa_plan(P, feats, B, D, h, w, C, true);
+  if (rc != PFST_OK) return rc;
+  return pa_launch<0>(P, feats, B, D, h, w, labels, lab_h, lab_w, conf, conf_thr, C, packed,
+                      packed + (int64_t)C * D, nullptr, static_cast<cudaStream_t>(stream), "pfst_proto_accum");
+}
+
+int64_t pfst_proto_order_ws_bytes(int64_t B, int32_t h, int32_t w, int32_t C) {
+  if (B < 1 || h < 1 || w < 1 || C < 1 || C > pfst::kPrMaxC) return 0;
+  PaPlan P;
+  if (pa_plan(P, nullptr, B, 1, h, w, C, false) != PFST_OK) return 0;
+  return (int64_t)(B * P.n_tiles * P.list_bytes);
+}
+
+int pfst_proto_order(const int64_t* labels, int64_t B, int32_t h, int32_t w, int32_t lab_h, int32_t lab_w,
+                     const float* conf, float conf_thr, int32_t C, float* counts, void* workspace,
+                     void* stream) {
+  if (!labels || !workspace || B < 0 || h < 1 || w < 1 || lab_h < 1 || lab_w < 1 || C < 1)
+    return PFST_ERR_INVALID_ARG;
+  if (C > pfst::kPrMaxC || !pfst::aligned16(workspace)) return PFST_ERR_UNSUPPORTED;
+  if (B == 0) return PFST_OK;
+  PaPlan P;
+  const int rc = pa_plan(P, nullptr, B, 1, h, w, C, false);
+  if (rc != PFST_OK) return rc;
+  return pa_launch<1>(P, nullptr, B, 1, h, w, labels, lab_h, lab_w, conf, conf_thr, C, nullptr, counts,
+                      static_cast<unsigned char*>(workspace), static_cast<cudaStream_t>(stream), "pfst_proto_order");
+}
+
+int pfst_proto_accum_ordered(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w, int32_t C,
+                             const void* workspace, float* packed, void* stream) {
+  if (!feats || !workspace || !packed || B < 0 || D < 1 || h < 1 || w < 1 || C < 1) return PFST_ERR_INVALID_ARG;
+  if (C > pfst::kPrMaxC || !pfst::aligned16(workspace)) return PFST_ERR_UNSUPPORTED;
+  if (B == 0) return PFST_OK;
+  PaPlan P;
+  const int rc = pa_plan(P, feats, B, D, h, w, C, true);
+  if (rc != PFST_OK) return rc;
+  return pa_launch<2>(P, feats, B, D, h, w, nullptr, 1, 1, nullptr, 0.f, C, packed, nullptr,
+                      static_cast<unsigned char*>(const_cast<void*>(workspace)), static_cast<cudaStream_t>(stream),
+                      "pfst_proto_accum_ordered");
 }
 
 int pfst_proto_finalize(float* packed, int32_t C, int32_t D, const float* mu_prev,

@@ -36,11 +36,47 @@ class PrototypeBank:
         self.seen = torch.zeros(self.C, dtype=torch.uint8, device=self.device)
         self.counts = torch.zeros(self.C, dtype=torch.int64, device=self.device)
         self.comm_stream = comm_stream
+        self._order_key, self._order_ws = None, None
         self.iter_state = torch.zeros(2, dtype=torch.int64, device=self.device)   # device copy of `iter` (+ counter)
 
     # P1
     def accumulate(self, feats: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None,
                    conf_thr: float = 0.0) -> None:
+        """packed += [class sums | class counts] of `feats` over `labels` — two launches: the label
+        sort (once per image tile) and the streaming segment-reduce (`order` / `accumulate_ordered`
+        can also be issued separately, e.g. the sort next to another kernel)."""
+        B, D, h, w = feats.shape
+        self.order(labels, B, h, w, conf, conf_thr)
+        self.accumulate_ordered(feats)
+
+    def order(self, labels: torch.Tensor, B: int, h: int, w: int, conf: Optional[torch.Tensor] = None,
+              conf_thr: float = 0.0) -> None:
+        """Class-sorted pixel lists of every (image, tile) into the cached workspace; adds the pixel
+        counts to `packed`."""
+        labels = _lab3(labels)
+        key = (B, h, w)
+        if self._order_key != key:
+            nbytes = int(_lib.load().pfst_proto_order_ws_bytes(B, h, w, self.C))
+            if nbytes <= 0:
+                raise PfstError(f"prototype accumulation does not support B={B}, h={h}, w={w}, C={self.C}")
+            self._order_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._order_key = key
+        _lib.call("pfst_proto_order", ops._dev(labels, "labels", torch.int64), B, h, w, labels.shape[-2],
+                  labels.shape[-1], ops._opt(conf, "conf", torch.float32), float(conf_thr), self.C,
+                  self.packed.data_ptr() + 4 * self.C * self.D, self._order_ws.data_ptr(), ops._stream())
+
+    def accumulate_ordered(self, feats: torch.Tensor) -> None:
+        B, D, h, w = feats.shape
+        if D != self.D:
+            raise ValueError("feature dim mismatch")
+        if self._order_key != (B, h, w):
+            raise PfstError("accumulate_ordered: call order() for this batch geometry first")
+        _lib.call("pfst_proto_accum_ordered", ops._dev(feats, "feats", torch.float32), B, D, h, w, self.C,
+                  self._order_ws.data_ptr(), self.packed.data_ptr(), ops._stream())
+
+    def accumulate_single_launch(self, feats: torch.Tensor, labels: torch.Tensor,
+                                 conf: Optional[torch.Tensor] = None, conf_thr: float = 0.0) -> None:
+        """The self-contained kernel (every streaming block sorts its own tile): no workspace."""
         labels = _lab3(labels)
         B, D, h, w = feats.shape
         if D != self.D:

@@ -72,9 +72,9 @@ class _Buffers:
 
 class SelfTrainingStep:
     # launches of THIS library's kernels per run(): presence, pseudo-label, dots(x_ema), proto
-    # accum, EMA, finalize, mix, dots(x_src), dist fwd, loss prep, loss fwd, loss bwd,
+    # order + accum, EMA, finalize, mix, dots(x_src), dist fwd, loss prep, loss fwd, loss bwd,
     # grad+dist bwd; memsets, copies and NCCL are not counted
-    KERNEL_LAUNCHES = 13
+    KERNEL_LAUNCHES = 14
     # executable-graph instances used alternately: launching an instance that is still running makes
     # the host wait for it, so with one instance the host could never run ahead of the device
     GRAPH_INSTANCES = int(os.environ.get("PFST_GRAPH_INSTANCES", "2"))
@@ -125,8 +125,9 @@ class SelfTrainingStep:
             join.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), ops._stream())
+        self.bank.order(b.label, x_ema.shape[0], x_ema.shape[2], x_ema.shape[3])   # label sort: 1 block / tile
         main.wait_event(join)
-        self.bank.accumulate(x_ema, b.label)                      # x_ema again: L2 hits
+        self.bank.accumulate_ordered(x_ema)                       # x_ema again: L2 hits
 
     def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo, part="all", mu_ready=None):
         """part 'all': the whole segment (single rank: the prototypes are final before it starts).

@@ -99,3 +99,19 @@ def test_proto_dist_all(cuda):
         want = OP.proto_dist_all(feats.double(), mu.double())
         got = P.proto_dist_all(feats.to(cuda), mu.to(cuda)).cpu().double()
         assert (got - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+@pytest.mark.parametrize("B,D,h,w,C,H,W", [(8, 96, 64, 64, 6, 512, 512), (2, 40, 128, 128, 2, 1024, 1024),
+                                            (5, 24, 15, 15, 33, 120, 120), (1, 8, 5, 7, 4, 40, 56)])
+def test_single_launch_accumulate_equals_the_split_form(cuda, B, D, h, w, C, H, W):
+    """pfst_proto_accum (self-contained) vs pfst_proto_order + pfst_proto_accum_ordered: identical
+    counts, sums equal up to the summation order."""
+    feats, labels = _case(B, D, h, w, C, H, W, seed=5)
+    g = torch.Generator().manual_seed(2)
+    conf = torch.rand((B, H, W), generator=g).to(cuda)
+    a, b = P.PrototypeBank(C, D, cuda), P.PrototypeBank(C, D, cuda)
+    a.accumulate(feats.to(cuda), labels.to(cuda), conf, 0.3)
+    b.accumulate_single_launch(feats.to(cuda), labels.to(cuda), conf, 0.3)
+    pa, pb = a.packed.cpu(), b.packed.cpu()
+    assert torch.equal(pa[C * D:], pb[C * D:])
+    assert (pa[:C * D] - pb[:C * D]).abs().max() <= 1e-5 * pb[:C * D].abs().max()

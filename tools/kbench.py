@@ -140,7 +140,10 @@ def main():
         gt = inp["gt"].to(dev)
         lab3 = gt[:, 0].contiguous()
         bank = PrototypeBank(C, D, dev)
-        report("proto_accum", 4 * D * p, lambda i: bank.accumulate(xs[i], lab3))
+        report("proto_accum(order+stream)", 4 * D * p, lambda i: bank.accumulate(xs[i], lab3))
+        report("proto_order", 8 * p, lambda i: bank.order(lab3, B, h, w))
+        report("proto_accum_ordered", 4 * D * p, lambda i: bank.accumulate_ordered(xs[i]))
+        report("proto_accum_single_launch", 4 * D * p, lambda i: bank.accumulate_single_launch(xs[i], lab3))
         mu = bank.finalize()
         geo = ops.LossGeometry(inp["logits_trg"].shape, inp["x_src"].shape, gt.shape,
                                wl.downscale if wl.downscale != 1.0 else None, dil)
