@@ -31,20 +31,20 @@ for lc, suffix, title in ((src / f"{tag}_bench_launches.csv", "bench_launches",
                           (src / f"{tag}_launches.csv", "launches", "tools/one_step.py cfg2 2 (eager launches of two steps)")):
     if not lc.exists():
         continue
-        lines = [l for l in lc.read_text().splitlines() if l.startswith('"')]
-        rows = list(csv.DictReader(io.StringIO("\n".join(lines))))
-        per = defaultdict(list)
-        for r in rows:
-            per[r["Kernel Name"].split("(")[0]].append(float(r["Metric Value"]) / 1e3)
-        tot = sum(sum(v) for v in per.values())
-        md = [f"# ncu launch list `{tag}`: {title} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)",
-              "", "| kernel | launches | avg us | share of step |", "|---|---|---|---|"]
-        for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
-            md.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.2f} | {sum(v) / tot:.3f} |")
-        md.append(f"\nTotal kernel time: {tot:.1f} us over {len(rows)} launches.")
-        (dst / f"{out}_{suffix}.md").write_text("\n".join(md) + "\n")
-        (dst / f"{out}_{suffix}.csv").write_text("\n".join(lines) + "\n")
-        print("\n".join(md))
+    lines = [l for l in lc.read_text().splitlines() if l.startswith('"')]
+    rows = list(csv.DictReader(io.StringIO("\n".join(lines))))
+    per = defaultdict(list)
+    for r in rows:
+        per[r["Kernel Name"].split("(")[0]].append(float(r["Metric Value"]) / 1e3)
+    tot = sum(sum(v) for v in per.values())
+    md = [f"# ncu launch list `{tag}`: {title} (gpu__time_duration.sum, --clock-control none; cold-cache, serialised)",
+          "", "| kernel | launches | avg us | share of step |", "|---|---|---|---|"]
+    for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        md.append(f"| `{k}` | {len(v)} | {sum(v) / len(v):.2f} | {sum(v) / tot:.3f} |")
+    md.append(f"\nTotal kernel time: {tot:.1f} us over {len(rows)} launches.")
+    (dst / f"{out}_{suffix}.md").write_text("\n".join(md) + "\n")
+    (dst / f"{out}_{suffix}.csv").write_text("\n".join(lines) + "\n")
+    print("\n".join(md))
 
 rep = src / f"{tag}_step_full.ncu-rep"
 if rep.exists():
