@@ -314,6 +314,21 @@ int pfst_proto_dist_bwd(const float* feats, int64_t B, int32_t D, int32_t h, int
 int pfst_proto_dist_all(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
                         const float* mu, int32_t C, float* out, void* stream);
 
+/* ---- next row: decode-head loss ------------------------------
+ * Replaces BaseDecodeHead.losses (rsiseg/models/decode_heads/decode_head.py:249-283) with
+ * CrossEntropyLoss (cross_entropy_loss.py:12-65, utils.py:48-79) and accuracy (accuracy.py:6-59):
+ *   up   = bilinear(logits -> (H,W), align_corners=False)
+ *   out2[0] = loss_weight * mean over ALL B*H*W pixels of CE(up, label; ignore_index)
+ *             * weight[pixel] (nullable) * class_weight[label] (nullable)
+ *   out2[1] = top-1 accuracy in percent over the non-ignored pixels
+ *   grad_logits (nullable, (B,C,lh,lw), zeroed here) = d out2[0] / d logits
+ * in ONE pass: the up-sampled logits are never materialised. Integer up-sampling factors
+ * only (H = s*lh, W = s*lw). stats: device double[4] workspace (zeroed here).             */
+int pfst_weighted_ce(const float* logits, const int64_t* labels, const float* weight,
+                     const float* class_weight, int64_t B, int32_t C, int32_t lh, int32_t lw,
+                     int32_t H, int32_t W, int64_t ignore_index, float loss_weight,
+                     float* grad_logits, double* stats, float* out2, void* stream);
+
 /* ---- V1/V4: confusion matrix / area histograms -------------------------------
  * Replaces intersect_and_union (rsiseg/core/evaluation/metrics.py:26-86, three
  * float32 torch.histc per image on the CPU) and the integer confusion matrix of

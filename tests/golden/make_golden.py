@@ -11,6 +11,8 @@ reference on machines where the reference checkout does not exist (the GPU box).
                    (pfgst.py:259-300, dacs_transforms.py:110-144)
   pfgst_loss.npz   PFGSTLoss.forward + autograd backward      (pfgst_loss.py:44-234)
   pfgst_step.npz   three PFGST.train_step iterations on a tiny segmentor
+  weighted_ce.npz  BaseDecodeHead.losses: resize + cross_entropy + accuracy (+ autograd backward)
+                   (decode_head.py:249-283, cross_entropy_loss.py:12-65, accuracy.py:6-59)
 """
 from __future__ import annotations
 
@@ -202,11 +204,50 @@ def gen_pfgst_step():
     np.savez_compressed(OUT / "pfgst_step.npz", **out)
 
 
+def ce_cases():
+    """(name, B, C, lh, lw, scale, use_weight, use_class_weight, loss_weight)"""
+    return [("plain", 2, 6, 32, 32, 4, False, False, 1.0), ("weighted", 2, 6, 32, 32, 4, True, False, 1.0),
+            ("aux", 1, 6, 16, 24, 4, True, True, 0.4), ("many", 2, 33, 15, 15, 2, True, False, 1.0),
+            ("same_res", 1, 3, 20, 12, 1, False, True, 1.0), ("x8", 1, 2, 13, 9, 8, True, False, 1.0)]
+
+
+def ce_inputs(name, B, C, lh, lw, scale, use_w, use_cw, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(map(ord, name)))
+    H, W = lh * scale, lw * scale
+    logits = 2.0 * torch.randn((B, C, lh, lw), generator=g)
+    label = blocky_labels(B, H, W, C, g, min_rect=2, max_rect=max(4, min(H, W) // 2))
+    weight = torch.rand((B, H, W), generator=g) if use_w else None
+    cw = (0.5 + torch.rand(C, generator=g)) if use_cw else None
+    return logits, label, weight, cw
+
+
+def gen_weighted_ce():
+    resize, cross_entropy, accuracy = R.decode_head_loss_fns()
+    out = {}
+    for name, B, C, lh, lw, scale, use_w, use_cw, lwt in ce_cases():
+        logits, label, weight, cw = ce_inputs(name, B, C, lh, lw, scale, use_w, use_cw)
+        z = logits.clone().requires_grad_(True)
+        up = resize(input=z, size=label.shape[2:], mode='bilinear', align_corners=False)       # decode_head.py:253-257
+        lab = label.squeeze(1)
+        loss = lwt * cross_entropy(up, lab, weight=weight, class_weight=cw, reduction='mean', avg_factor=None,
+                                   ignore_index=255)                                          # CrossEntropyLoss.forward
+        acc = accuracy(up, lab, ignore_index=255)
+        loss.backward()
+        out[f"{name}_loss"] = loss.detach().numpy()
+        out[f"{name}_acc"] = acc.detach().numpy()
+        out[f"{name}_grad"] = z.grad.numpy()
+    np.savez_compressed(OUT / "weighted_ce.npz", **out)
+    print("weighted_ce.npz", {k: float(v) for k, v in out.items() if k.endswith("_loss")})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "weighted_ce":
+        gen_weighted_ce()
+        sys.exit(0)
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step):
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce):
         fn()
         print("wrote", fn.__name__)
     for p in sorted(OUT.glob("*.npz")):

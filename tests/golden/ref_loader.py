@@ -91,6 +91,26 @@ def pfgst_loss():
     return _cache["loss"]
 
 
+def decode_head_loss_fns():
+    """-> (resize, cross_entropy, accuracy): rsiseg/ops/wrappers.py, rsiseg/models/losses/
+    cross_entropy_loss.py (with its real losses/utils.py) and accuracy.py, loaded by path."""
+    if "ce" not in _cache:
+        had = "mmcv" in sys.modules
+        _stub("mmcv")
+        pkg = "_pfst_ref_ce"
+        _stub(pkg)
+        _stub(pkg + ".builder", LOSSES=_Registry())
+        _stub(pkg + ".losses")
+        _load(pkg + ".losses.utils", "rsiseg/models/losses/utils.py")
+        ce = _load(pkg + ".losses.cross_entropy_loss", "rsiseg/models/losses/cross_entropy_loss.py")
+        acc = _load(pkg + ".losses.accuracy", "rsiseg/models/losses/accuracy.py")
+        wr = _load("_pfst_ref_wrappers", "rsiseg/ops/wrappers.py")
+        if not had:
+            sys.modules.pop("mmcv", None)
+        _cache["ce"] = (wr.resize, ce.cross_entropy, acc.accuracy)
+    return _cache["ce"]
+
+
 class cpu_cuda_identity:
     """Context manager: make Tensor.cuda() the identity on a CUDA-less host."""
 

@@ -146,3 +146,25 @@ def test_oracle_bitwise_equals_reference_live():
         assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
     assert torch.equal(t1['x_src'].grad, t2['x_src'].grad)
     assert torch.equal(t1['logits_trg'].grad, t2['logits_trg'].grad)
+
+
+def test_weighted_ce_oracle_vs_reference_live_and_golden():
+    """Decode-head loss oracle == the reference's resize + cross_entropy + accuracy (loaded by
+    path) bit for bit, and == the committed golden vectors."""
+    from oracle import weighted_ce as OC
+    from tests.golden.make_golden import ce_cases, ce_inputs
+    z = np.load(G / "weighted_ce.npz")
+    live = R.decode_head_loss_fns() if R.available() else None
+    for name, B, C, lh, lw, scale, use_w, use_cw, lwt in ce_cases():
+        logits, label, weight, cw = ce_inputs(name, B, C, lh, lw, scale, use_w, use_cw)
+        zo = logits.clone().requires_grad_(True)
+        lo, ao, _ = OC.decode_head_losses(zo, label, weight, cw, 255, lwt)
+        lo.backward()
+        assert np.array_equal(lo.detach().numpy(), z[f"{name}_loss"]), name
+        assert np.array_equal(ao.numpy(), z[f"{name}_acc"]), name
+        assert np.array_equal(zo.grad.numpy(), z[f"{name}_grad"]), name
+        if live is not None:
+            resize, cross_entropy, accuracy = live
+            up = resize(input=logits, size=label.shape[2:], mode='bilinear', align_corners=False)
+            lr = lwt * cross_entropy(up, label.squeeze(1), weight=weight, class_weight=cw, ignore_index=255)
+            assert torch.equal(lr, lo.detach()) and torch.equal(accuracy(up, label.squeeze(1), ignore_index=255), ao)
