@@ -10,10 +10,11 @@
 // The reference materialises the (B,C,H,W) up-sampled logits (50 MB at cfg2), their
 // log-softmax and, in backward, both gradients. Here one kernel reads the low-resolution
 // logits (3 MB), the labels and the pixel weights once and produces the loss, the accuracy
-// and d loss / d low-res logits: a block owns an 8x8 tile of low-res pixels (+1 halo) in
-// shared memory, evaluates the (8s)^2 high-res pixels it covers (bilinear taps from shared
-// memory, torch's align_corners=False arithmetic), and scatters the per-class gradients back
-// into the shared tile; only the tile (100*C values) goes to global memory with atomics.
+// and d loss / d low-res logits: a block owns a 16x16 tile of low-res cells in shared memory,
+// one thread per cell evaluates the s x s high-res pixels whose bilinear taps start there
+// (torch's align_corners=False arithmetic, taps read from shared memory) and sums their
+// per-class gradients privately; only the low-res tile (17*17*C values) goes to global
+// memory with atomics.
 // HBM-bound in principle: (8 + 4 [+4]) B per high-res pixel.
 #include <float.h>
 #include <math.h>
@@ -22,10 +23,11 @@
 
 namespace pfst {
 
-constexpr int kCeTile = 8;                       // low-res pixels per tile side
-constexpr int kCeHalo = kCeTile + 2;             // + one neighbour on each side
-constexpr int kCeThreads = 256;
+constexpr int kCeTile = 16;                      // low-res CELLS per tile side (one thread per cell)
+constexpr int kCeHalo = kCeTile + 1;             // low-res pixels touched by a tile of cells
+constexpr int kCeThreads = kCeTile * kCeTile;
 constexpr int kCeMaxC = 64;
+constexpr int kCeRegC = 8;                       // up to this many classes the up-sampled logits stay in registers
 
 struct CeParams {
   const float* logits;       // (B, C, lh, lw)
@@ -50,80 +52,146 @@ __device__ __forceinline__ void ce_src(int dst, float scale, int in, int& i0, in
   l0 = 1.f - l1;
 }
 
+// One thread per low-resolution CELL (y0, x0): the high-res pixels whose bilinear taps start at
+// that low-res pixel (s x s of them in the interior) all read and update the same four low-res
+// corners, so their per-class gradients are summed in a private shared-memory accumulator
+// ([class][corner][thread]: conflict-free, no atomics) and only four shared atomics per class and
+// thread fold them into the block's low-res tile; the tile goes to global memory once.
+template <bool REGC, bool PRIV>
 __global__ void __launch_bounds__(kCeThreads)
 weighted_ce_kernel(const CeParams P) {
   extern __shared__ __align__(16) float ce_smem[];
-  float* z_s = ce_smem;                                   // [C][kCeHalo*kCeHalo] low-res logits
-  float* g_s = ce_smem + (size_t)P.C * kCeHalo * kCeHalo;   // same shape: gradient accumulator
+  float* z_s = ce_smem;                                       // [C][kCeHalo*kCeHalo] low-res logits
+  float* g_s = z_s + (size_t)P.C * kCeHalo * kCeHalo;           // same shape: gradient tile
+  float* a_s = g_s + (size_t)P.C * kCeHalo * kCeHalo;           // [C][4][kCeThreads] private accumulators
   __shared__ double red[3][kCeThreads / 32];
   const int b = blockIdx.z;
-  const int ly0 = blockIdx.y * kCeTile - 1, lx0 = blockIdx.x * kCeTile - 1;   // halo origin (may be -1)
+  const int ly0 = blockIdx.y * kCeTile, lx0 = blockIdx.x * kCeTile;   // first cell of the tile
   const int64_t lplane = (int64_t)P.lh * P.lw;
   const float* zb = P.logits + (int64_t)b * P.C * lplane;
   for (int i = threadIdx.x; i < P.C * kCeHalo * kCeHalo; i += kCeThreads) {
     const int c = i / (kCeHalo * kCeHalo), r = i - c * (kCeHalo * kCeHalo);
     const int ly = ly0 + r / kCeHalo, lx = lx0 + r % kCeHalo;
-    z_s[i] = (ly >= 0 && ly < P.lh && lx >= 0 && lx < P.lw) ? zb[c * lplane + (int64_t)ly * P.lw + lx] : 0.f;
+    z_s[i] = (ly < P.lh && lx < P.lw) ? zb[c * lplane + (int64_t)ly * P.lw + lx] : 0.f;
     g_s[i] = 0.f;
   }
+  if (P.grad && PRIV)
+    for (int i = threadIdx.x; i < P.C * 4 * kCeThreads; i += kCeThreads) a_s[i] = 0.f;
   __syncthreads();
 
+  const int cy = threadIdx.x / kCeTile, cx = threadIdx.x % kCeTile;
+  const int y0c = ly0 + cy, x0c = lx0 + cx;                         // this thread's cell
   const float sch = (float)P.lh / (float)P.H, scw = (float)P.lw / (float)P.W;
-  const int hy0 = blockIdx.y * kCeTile * P.s, hx0 = blockIdx.x * kCeTile * P.s;
-  const int side = kCeTile * P.s;
   const float gscale = P.loss_weight / (float)((double)P.B * P.H * P.W);
   double loss = 0.0, correct = 0.0, valid = 0.0;
-  for (int p = threadIdx.x; p < side * side; p += kCeThreads) {
-    const int y = hy0 + p / side, x = hx0 + p % side;
-    if (y >= P.H || x >= P.W) continue;
-    const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
-    const int64_t lab = P.labels[pix];
-    int y0, y1, x0, x1;
-    float hy0l, hy1l, wx0l, wx1l;
-    ce_src(y, sch, P.lh, y0, y1, hy0l, hy1l);
-    ce_src(x, scw, P.lw, x0, x1, wx0l, wx1l);
-    const int i00 = (y0 - ly0) * kCeHalo + (x0 - lx0), i01 = (y0 - ly0) * kCeHalo + (x1 - lx0);
-    const int i10 = (y1 - ly0) * kCeHalo + (x0 - lx0), i11 = (y1 - ly0) * kCeHalo + (x1 - lx0);
-    auto up = [&](int c) {
-      const float* z = z_s + c * (kCeHalo * kCeHalo);
-      return hy0l * (wx0l * z[i00] + wx1l * z[i01]) + hy1l * (wx0l * z[i10] + wx1l * z[i11]);
-    };
-    float m = -INFINITY;
-    int arg = 0;
-    for (int c = 0; c < P.C; ++c) {
-      const float v = up(c);
-      if (v > m) { m = v; arg = c; }        // first maximum wins
+  if (y0c < P.lh && x0c < P.lw) {
+    // candidate high-res range of the cell (one extra pixel each side: the exact membership test
+    // is torch's own fp32 source-index arithmetic, re-evaluated per pixel)
+    const int ya = max(0, y0c * P.s + P.s / 2 - 1), yb = min(P.H - 1, (y0c + 1) * P.s + P.s / 2);
+    const int xa = max(0, x0c * P.s + P.s / 2 - 1), xb = min(P.W - 1, (x0c + 1) * P.s + P.s / 2);
+    const int i00 = cy * kCeHalo + cx;                               // the cell's corners inside the tile
+    for (int y = (y0c == 0 ? 0 : ya); y <= yb; ++y) {
+      int y0, y1;
+      float hy0l, hy1l;
+      ce_src(y, sch, P.lh, y0, y1, hy0l, hy1l);
+      if (y0 != y0c) continue;
+      const int dy = (y1 - y0) * kCeHalo;
+      for (int x = (x0c == 0 ? 0 : xa); x <= xb; ++x) {
+        int x0, x1;
+        float wx0l, wx1l;
+        ce_src(x, scw, P.lw, x0, x1, wx0l, wx1l);
+        if (x0 != x0c) continue;
+        const int dx = x1 - x0;
+        const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
+        const int64_t lab = P.labels[pix];
+        const float t00 = hy0l * wx0l, t01 = hy0l * wx1l, t10 = hy1l * wx0l, t11 = hy1l * wx1l;
+        auto up = [&](int c) {
+          const float* z = z_s + c * (kCeHalo * kCeHalo) + i00;
+          return hy0l * (wx0l * z[0] + wx1l * z[dx]) + hy1l * (wx0l * z[dy] + wx1l * z[dy + dx]);
+        };
+        float vreg[REGC ? kCeRegC : 1];
+        float m = -INFINITY;
+        int arg = 0;
+        if (REGC) {
+#pragma unroll
+          for (int c = 0; c < kCeRegC; ++c) {
+            vreg[c] = c < P.C ? up(c) : -INFINITY;
+            if (vreg[c] > m) { m = vreg[c]; arg = c; }        // first maximum wins
+          }
+        } else {
+          for (int c = 0; c < P.C; ++c) {
+            const float v = up(c);
+            if (v > m) { m = v; arg = c; }
+          }
+        }
+        const bool ign = lab == P.ignore_index || lab < 0 || lab >= P.C;
+        if (ign) continue;
+        valid += 1.0;
+        if (arg == (int)lab) correct += 1.0;
+        float sum = 0.f, vlab = 0.f;
+        if (REGC) {
+#pragma unroll
+          for (int c = 0; c < kCeRegC; ++c) {
+            if (c < P.C) {
+              vreg[c] = expf(vreg[c] - m);
+              sum += vreg[c];
+              if (c == (int)lab) vlab = up(c);
+            }
+          }
+        } else {
+          for (int c = 0; c < P.C; ++c) {
+            const float v = up(c);
+            sum += expf(v - m);
+            if (c == (int)lab) vlab = v;
+          }
+        }
+        float wpx = P.weight ? P.weight[pix] : 1.f;
+        if (P.class_weight) wpx *= P.class_weight[lab];
+        loss += (double)(((m + logf(sum)) - vlab) * wpx);
+        if (P.grad) {
+          const float inv = 1.f / sum, k = gscale * wpx;
+          float* acc = a_s + threadIdx.x;
+          if (REGC) {
+#pragma unroll
+            for (int c = 0; c < kCeRegC; ++c) {
+              if (c < P.C) {
+                const float g = k * (vreg[c] * inv - (c == (int)lab ? 1.f : 0.f));
+                float* q = acc + c * 4 * kCeThreads;
+                q[0] += t00 * g; q[kCeThreads] += t01 * g; q[2 * kCeThreads] += t10 * g; q[3 * kCeThreads] += t11 * g;
+              }
+            }
+          } else {
+            for (int c = 0; c < P.C; ++c) {
+              const float g = k * (expf(up(c) - m) * inv - (c == (int)lab ? 1.f : 0.f));
+              if (PRIV) {
+                float* q = acc + c * 4 * kCeThreads;
+                q[0] += t00 * g; q[kCeThreads] += t01 * g; q[2 * kCeThreads] += t10 * g; q[3 * kCeThreads] += t11 * g;
+              } else {      // many classes: the private accumulators do not fit, scatter into the tile directly
+                float* gs = g_s + c * (kCeHalo * kCeHalo) + i00;
+                atomicAdd(gs, t00 * g); atomicAdd(gs + dx, t01 * g);
+                atomicAdd(gs + dy, t10 * g); atomicAdd(gs + dy + dx, t11 * g);
+              }
+            }
+          }
+        }
+      }
     }
-    const bool ign = lab == P.ignore_index || lab < 0 || lab >= P.C;
-    if (!ign) {
-      valid += 1.0;
-      if (arg == (int)lab) correct += 1.0;
-    }
-    float sum = 0.f, vlab = 0.f;
-    for (int c = 0; c < P.C; ++c) {
-      const float v = up(c);
-      sum += expf(v - m);
-      if (c == (int)lab) vlab = v;
-    }
-    if (ign) continue;
-    float wpx = P.weight ? P.weight[pix] : 1.f;
-    if (P.class_weight) wpx *= P.class_weight[lab];
-    loss += (double)(((m + logf(sum)) - vlab) * wpx);
-    if (P.grad) {
-      const float inv = 1.f / sum, k = gscale * wpx;
-      const float t00 = hy0l * wx0l, t01 = hy0l * wx1l, t10 = hy1l * wx0l, t11 = hy1l * wx1l;
+    // fold the cell's four corners into the block's low-res tile. The second tap of a clamped border
+    // cell coincides with the first (x1 == x0 at the last column / y1 == y0 at the last row).
+    if (P.grad && PRIV) {
+      const int ddx = x0c < P.lw - 1 ? 1 : 0, ddy = (y0c < P.lh - 1 ? 1 : 0) * kCeHalo;
       for (int c = 0; c < P.C; ++c) {
-        const float g = k * (expf(up(c) - m) * inv - (c == (int)lab ? 1.f : 0.f));
-        float* gs = g_s + c * (kCeHalo * kCeHalo);
-        atomicAdd(gs + i00, t00 * g);
-        atomicAdd(gs + i01, t01 * g);
-        atomicAdd(gs + i10, t10 * g);
-        atomicAdd(gs + i11, t11 * g);
+        const float* q = a_s + c * 4 * kCeThreads + threadIdx.x;
+        float* gs = g_s + c * (kCeHalo * kCeHalo) + i00;
+        atomicAdd(gs, q[0]);
+        atomicAdd(gs + ddx, q[kCeThreads]);
+        atomicAdd(gs + ddy, q[2 * kCeThreads]);
+        atomicAdd(gs + ddy + ddx, q[3 * kCeThreads]);
       }
     }
   }
 
-  // gradient tile -> global (halo pixels belong to neighbouring tiles too: atomics)
+  // gradient tile -> global (the last row / column of the tile belongs to the next tile too: atomics)
   __syncthreads();
   if (P.grad) {
     float* gb = P.grad + (int64_t)b * P.C * lplane;
@@ -132,7 +200,7 @@ weighted_ce_kernel(const CeParams P) {
       if (v == 0.f) continue;
       const int c = i / (kCeHalo * kCeHalo), r = i - c * (kCeHalo * kCeHalo);
       const int ly = ly0 + r / kCeHalo, lx = lx0 + r % kCeHalo;
-      if (ly >= 0 && ly < P.lh && lx >= 0 && lx < P.lw) atomicAdd(gb + c * lplane + (int64_t)ly * P.lw + lx, v);
+      if (ly < P.lh && lx < P.lw) atomicAdd(gb + c * lplane + (int64_t)ly * P.lw + lx, v);
     }
   }
   // statistics: block partials in fp64, last block finalises on the device
@@ -185,10 +253,15 @@ int pfst_weighted_ce(const float* logits, const int64_t* labels, const float* we
   const dim3 grid((unsigned)((lw + pfst::kCeTile - 1) / pfst::kCeTile),
                   (unsigned)((lh + pfst::kCeTile - 1) / pfst::kCeTile), (unsigned)B);
   if (grid.y > 65535) return PFST_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)2 * C * pfst::kCeHalo * pfst::kCeHalo * sizeof(float);
-  PFST_CUDA_TRY(cudaFuncSetAttribute(pfst::weighted_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                "pfst_weighted_ce/attr");
-  pfst::weighted_ce_kernel<<<grid, pfst::kCeThreads, smem, s>>>(P);
+  const size_t tile = (size_t)2 * C * pfst::kCeHalo * pfst::kCeHalo * sizeof(float);
+  const size_t priv = grad_logits ? (size_t)C * 4 * pfst::kCeThreads * sizeof(float) : 0;
+  const bool use_priv = tile + priv <= 100 * 1024;          // keeps two blocks per SM
+  const size_t smem = tile + (use_priv ? priv : 0);
+  if (smem > 200 * 1024) return PFST_ERR_UNSUPPORTED;
+  auto k = C <= pfst::kCeRegC ? pfst::weighted_ce_kernel<true, true>
+                              : (use_priv ? pfst::weighted_ce_kernel<false, true> : pfst::weighted_ce_kernel<false, false>);
+  PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_weighted_ce/attr");
+  k<<<grid, pfst::kCeThreads, smem, s>>>(P);
   PFST_CHECK_LAUNCH("pfst_weighted_ce");
   return PFST_OK;
 }

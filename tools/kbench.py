@@ -187,6 +187,32 @@ def main():
         del xs, grads
     keep.clear()
 
+    if want("ce"):
+        # decode-head loss: fused kernel vs the PyTorch op sequence of the reference (both on this GPU)
+        import torch.nn.functional as F
+        from pfst_b200.losses import upsample_cross_entropy
+        lh, lw = H // 4, W // 4
+        zs = [(2.0 * torch.randn((B, C, lh, lw), generator=g)).to(dev).requires_grad_(True) for _ in range(R)]
+        lab = inp["gt"].to(dev)
+        wgt = torch.rand((B, H, W), generator=g).to(dev)
+        nbytes = 2 * 4 * C * B * lh * lw + (8 + 4) * P
+
+        def fused(i):
+            loss, acc = upsample_cross_entropy(zs[i], lab, wgt)
+            loss.backward()
+            zs[i].grad = None
+        report("weighted_ce fused fwd+bwd", nbytes, fused)
+
+        def torch_ref(i):
+            up = F.interpolate(zs[i], (H, W), mode="bilinear", align_corners=False)
+            loss = (F.cross_entropy(up, lab[:, 0], reduction="none", ignore_index=255) * wgt).mean()
+            (up.argmax(1) == lab[:, 0]).float().sum()
+            loss.backward()
+            zs[i].grad = None
+        report("weighted_ce torch ops fwd+bwd (reference sequence, same GPU)", nbytes, torch_ref)
+        del zs
+    keep.clear()
+
     if want("conf"):
         n = 16
         pred, gt = eval_maps(n, 1024, 1024, 6, seed=1)
