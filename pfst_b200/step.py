@@ -100,7 +100,6 @@ class SelfTrainingStep:
         self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
         self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
         self.nccl_in_graph = os.environ.get("PFST_NCCL_IN_GRAPH", "1") != "0"
-        self.ema_at = os.environ.get("PFST_EMA_AT", "start")   # 'start': with segment A; 'b': with segment B
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
@@ -316,18 +315,7 @@ class SelfTrainingStep:
             graphs = sets[self._step_count % len(sets)]
         self._step_count += 1
         self.plan.choose(rng)                          # waits for the 36-byte copy only
-        if self.ema_at == "start":
-            self._launch_ema(it, main)
-        elif self.ema_at == "serial":          # experiment: full grid on the main stream, nothing overlaps it
-            if self.ema_events is not None:
-                self.ema_events[0].record(main)
-            if it == 0:
-                self.table.update(0.0, 1.0, mode=1, stream=main.cuda_stream)
-            else:
-                self.table.update(*ops.ema_coeffs(it, self.alpha), stream=main.cuda_stream)
-            if self.ema_events is not None:
-                self.ema_events[1].record(main)
-            self._ev[6].record(main)
+        self._launch_ema(it, main)                     # E2 on its own stream, joined below
         if len(parts) == 1:
             # S1/S2, L2(x_ema), P1 -> (all-reduce) P2 -> M2, L2(x_src), P3, L1/L3-L6, backward
             if graphs:
