@@ -78,6 +78,9 @@ class SelfTrainingStep:
     # executable-graph instances used alternately: launching an instance that is still running makes
     # the host wait for it, so with one instance the host could never run ahead of the device
     GRAPH_INSTANCES = int(os.environ.get("PFST_GRAPH_INSTANCES", "2"))
+    # graphs are keyed by the input addresses (a trainer whose allocator hands the network outputs
+    # back at the same addresses replays; new addresses trigger a new capture): bounded cache
+    MAX_GRAPH_SETS = 8
 
     def __init__(self, teacher_params, student_params, num_classes: int, feat_dim: int, device,
                  alpha: float = 0.999, pseudo_threshold: float = 0.98, dilation: int = 2, top_k: int = 3,
@@ -210,6 +213,8 @@ class SelfTrainingStep:
         multi-rank: [A, B1, B2] with the all-reduce and proto_finalize between them."""
         if key in self._graphs:
             return self._graphs[key]
+        while len(self._graphs) >= self.MAX_GRAPH_SETS:        # inputs keep moving: forget the oldest capture
+            self._graphs.pop(next(iter(self._graphs)))
         bank = self.bank
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
