@@ -411,6 +411,187 @@ neigh_grad_generic_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+// ------------------------------------------- small planes (any width): bulk-copy kernels
+// Feature maps whose width is not a multiple of four (SeasonNet: 15x15) cannot be described by
+// the TMA tensor map above, but a chunk of channels of one image, x[b, c:c+16], is ONE contiguous
+// block of 16*h*w floats: it streams into shared memory with 1-D bulk async copies (mbarrier ring,
+// one producer lane) and every thread owns one or two pixels, reading its taps from shared memory
+// (consecutive threads -> consecutive addresses: conflict-free). HBM traffic = the tensor, once.
+constexpr int kSpCH = 16;            // channels per stage
+constexpr int kSpStages = 4;
+constexpr int kSpConsumers = 256;
+constexpr int kSpThreads = kSpConsumers + 32;
+constexpr int kSpMaxHW = 400;        // 4 stages x 16 channels x 400 px x 4 B = 102 KB (two blocks per SM)
+constexpr int kSpPix = (kSpMaxHW + kSpConsumers - 1) / kSpConsumers;   // pixels per thread (2)
+
+__device__ __forceinline__ void sp_init(uint64_t* full_bar, uint64_t* empty_bar) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kSpStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kSpConsumers / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void sp_produce(const float* src, int hw, int c_begin, int c_end, float* stage_buf,
+                                           uint64_t* full_bar, uint64_t* empty_bar) {
+  int it = 0;
+  for (int c = c_begin; c < c_end; c += kSpCH, ++it) {
+    const int s = it % kSpStages, n = min(kSpCH, c_end - c);
+    if (it >= kSpStages) mbar_wait(&empty_bar[s], ((uint32_t)(it / kSpStages) & 1u) ^ 1u);
+    const uint32_t bytes = (uint32_t)n * hw * sizeof(float);
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_load_1d(stage_buf + (size_t)s * kSpCH * hw, src + (int64_t)c * hw, bytes, &full_bar[s]);
+  }
+}
+
+__global__ void __launch_bounds__(kSpThreads)
+neigh_dots_plane_kernel(const float* __restrict__ xa, const float* __restrict__ xb, int B, int D, int h, int w,
+                        int dil, int ksplit, int slot0, int n_slots, float* __restrict__ dots) {
+  extern __shared__ __align__(128) unsigned char sp_smem[];
+  float* stage_buf = reinterpret_cast<float*>(sp_smem);
+  __shared__ uint64_t full_bar[kSpStages], empty_bar[kSpStages];
+  const int hw = h * w;
+  int z = blockIdx.x;
+  const int split = z % ksplit; z /= ksplit;
+  const int b = z % B, t = z / B;
+  const int c_begin = (int)((int64_t)split * D / ksplit), c_end = (int)((int64_t)(split + 1) * D / ksplit);
+  const float* src = (t == 0 ? xa : xb) + (int64_t)b * D * hw;
+  sp_init(full_bar, empty_bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == kSpConsumers / 32) {
+    if (lane == 0) sp_produce(src, hw, c_begin, c_end, stage_buf, full_bar, empty_bar);
+    return;
+  }
+  int off[kSpPix][4];
+  bool ok[kSpPix][4], live[kSpPix];
+  float acc[kSpPix][5];
+#pragma unroll
+  for (int q = 0; q < kSpPix; ++q) {
+    const int p = threadIdx.x + q * kSpConsumers;
+    live[q] = p < hw;
+    const int y = p / w, x = p - y * w;
+    ok[q][0] = live[q] && x + dil < w;                       // ( 0, +d)
+    ok[q][1] = live[q] && y + dil < h && x - dil >= 0;       // (+d, -d)
+    ok[q][2] = live[q] && y + dil < h;                       // (+d,  0)
+    ok[q][3] = live[q] && y + dil < h && x + dil < w;        // (+d, +d)
+    off[q][0] = dil; off[q][1] = dil * w - dil; off[q][2] = dil * w; off[q][3] = dil * w + dil;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[q][k] = 0.f;
+  }
+  int it = 0;
+  for (int c = c_begin; c < c_end; c += kSpCH, ++it) {
+    const int s = it % kSpStages, n = min(kSpCH, c_end - c);
+    mbar_wait(&full_bar[s], (uint32_t)(it / kSpStages) & 1u);
+    const float* buf = stage_buf + (size_t)s * kSpCH * hw;
+#pragma unroll
+    for (int q = 0; q < kSpPix; ++q) {
+      if (!live[q]) continue;
+      const float* pq = buf + threadIdx.x + q * kSpConsumers;
+      for (int ch = 0; ch < n; ++ch) {
+        const float* r = pq + ch * hw;
+        const float v = r[0];
+        acc[q][0] = fmaf(v, v, acc[q][0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ok[q][k]) acc[q][k + 1] = fmaf(v, r[off[q][k]], acc[q][k + 1]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  float* out = dots + ((((int64_t)split * n_slots + slot0 + t) * B + b) * 5) * hw;
+#pragma unroll
+  for (int q = 0; q < kSpPix; ++q)
+    if (live[q])
+#pragma unroll
+      for (int k = 0; k < 5; ++k) out[(int64_t)k * hw + threadIdx.x + q * kSpConsumers] = acc[q][k];
+}
+
+// grad[b,c,p] = sum_k coef[b,k,p] * x[b,c,p+delta_k]  (+ the prototype-distance term, as ProtoBwd above)
+template <bool PROTO>
+__global__ void __launch_bounds__(kSpThreads)
+neigh_grad_plane_kernel(const float* __restrict__ x, const float* __restrict__ coef, int B, int D, int h, int w,
+                        int dil, int ksplit, float* __restrict__ grad, const ProtoBwd pb) {
+  extern __shared__ __align__(128) unsigned char sp_smem[];
+  float* stage_buf = reinterpret_cast<float*>(sp_smem);
+  __shared__ uint64_t full_bar[kSpStages], empty_bar[kSpStages];
+  const int hw = h * w;
+  float* mu_s = stage_buf + (size_t)kSpStages * kSpCH * hw;     // [C][mu_stride]  (PROTO only)
+  const int split = blockIdx.x % ksplit, b = blockIdx.x / ksplit;
+  const int c_begin = (int)((int64_t)split * D / ksplit), c_end = (int)((int64_t)(split + 1) * D / ksplit);
+  if (PROTO) {
+    const int nch = c_end - c_begin;
+    for (int i = threadIdx.x; i < pb.C * nch; i += kSpThreads) {
+      const int c = i / nch, j = i - c * nch;
+      mu_s[c * pb.mu_stride + j] = pb.mu[(int64_t)c * D + c_begin + j];
+    }
+  }
+  sp_init(full_bar, empty_bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == kSpConsumers / 32) {
+    if (lane == 0) sp_produce(x + (int64_t)b * D * hw, hw, c_begin, c_end, stage_buf, full_bar, empty_bar);
+    return;
+  }
+  float K[kSpPix][9], pcoef[kSpPix];
+  int off[kSpPix][9], prow[kSpPix];
+  bool live[kSpPix];
+#pragma unroll
+  for (int q = 0; q < kSpPix; ++q) {
+    const int p = threadIdx.x + q * kSpConsumers;
+    live[q] = p < hw;
+    const int y = p / w, xx = p - y * w;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int yy = y + (k / 3 - 1) * dil, xk = xx + (k % 3 - 1) * dil;
+      const bool in = live[q] && yy >= 0 && yy < h && xk >= 0 && xk < w;
+      K[q][k] = in ? coef[((int64_t)b * 9 + k) * hw + p] : 0.f;
+      off[q][k] = in ? (yy - y) * w + (xk - xx) : 0;
+    }
+    pcoef[q] = 0.f;
+    prow[q] = 0;
+    if (PROTO && live[q]) {
+      const float sh = (float)pb.lab_h / (float)h, sw = (float)pb.lab_w / (float)w;
+      uint8_t l = pr_label(pb.labels, nullptr, 0.f, b, p, w, pb.lab_h, pb.lab_w, sh, sw, pb.C);
+      if (l != 255 && pb.seen && !pb.seen[l]) l = 255;
+      const float dn = pb.dist[(int64_t)b * hw + p];
+      pcoef[q] = (l != 255 && dn > 0.f) ? pb.grad_loss[0] / (dn * (float)pb.acc[1]) : 0.f;
+      prow[q] = (l != 255 ? (int)l : 0) * pb.mu_stride;
+    }
+  }
+  float* gout = grad + (int64_t)b * D * hw;
+  int it = 0;
+  for (int c = c_begin; c < c_end; c += kSpCH, ++it) {
+    const int s = it % kSpStages, n = min(kSpCH, c_end - c);
+    mbar_wait(&full_bar[s], (uint32_t)(it / kSpStages) & 1u);
+    const float* buf = stage_buf + (size_t)s * kSpCH * hw;
+#pragma unroll
+    for (int q = 0; q < kSpPix; ++q) {
+      if (!live[q]) continue;
+      const int p = threadIdx.x + q * kSpConsumers;
+      for (int ch = 0; ch < n; ++ch) {
+        const float* r = buf + ch * hw + p;
+        float o = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o = fmaf(K[q][k], r[off[q][k]], o);
+        if (PROTO) o = fmaf(pcoef[q], r[0] - mu_s[prow[q] + (c - c_begin) + ch], o);
+        gout[(int64_t)(c + ch) * hw + p] = o;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+}
+
+// planes the bulk-copy kernels cover: small, 16-byte aligned channel chunks for every split
+static bool sp_ok(const void* p0, const void* p1, int D, int h, int w, int ks) {
+  const int hw = h * w;
+  return hw <= kSpMaxHW && aligned16(p0) && (!p1 || aligned16(p1)) && D % (4 * ks) == 0;
+}
+
 static bool nb_tma_ok(const void* p0, const void* p1, int w, int dil) {
   return (w % 4 == 0) && aligned16(p0) && (!p1 || aligned16(p1)) && (dil == 1 || dil == 2 || dil == 4) &&
          get_encode_tiled() != nullptr;
@@ -491,6 +672,30 @@ static int launch_grad_generic(const float* x, const float* coef, int64_t B, int
   return PFST_OK;
 }
 
+// small-plane backward: channel splits so that about two blocks per SM are in flight
+static int sp_grad_splits(int64_t B, int D) {
+  int ks = (int)((2 * (int64_t)kNumSMs + B - 1) / B);
+  if (ks > D / kSpCH) ks = D / kSpCH;
+  if (ks < 1) ks = 1;
+  while (ks > 1 && D % (4 * ks) != 0) --ks;
+  return ks;
+}
+
+template <bool PROTO>
+static int launch_grad_plane(const float* x, const float* coef, int64_t B, int D, int h, int w, int dilation,
+                             float* grad, ProtoBwd pb, int ks, cudaStream_t s) {
+  size_t smem = (size_t)kSpStages * kSpCH * h * w * sizeof(float);
+  if (PROTO) {
+    pb.mu_stride = D / ks + 1;
+    smem += (size_t)pb.C * pb.mu_stride * sizeof(float);
+  }
+  auto k = neigh_grad_plane_kernel<PROTO>;
+  PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_neigh_grad/attr");
+  k<<<(unsigned)(B * ks), kSpThreads, smem, s>>>(x, coef, (int)B, D, h, w, dilation, ks, grad, pb);
+  PFST_CHECK_LAUNCH("pfst_neigh_grad");
+  return PFST_OK;
+}
+
 }  // namespace pfst
 
 extern "C" {
@@ -510,6 +715,15 @@ static int neigh_dots_impl(const float* x_a, const float* x_b, int64_t B, int32_
       case 2: return pfst::launch_dots_tma<2>(x_a, x_b, T, (int)B, D, h, w, ks, slot0, n_slots, dots, s);
       default: return pfst::launch_dots_tma<4>(x_a, x_b, T, (int)B, D, h, w, ks, slot0, n_slots, dots, s);
     }
+  }
+  if (pfst::sp_ok(x_a, x_b, D, h, w, ks) && (int64_t)T * B * ks <= 0x7fffffffll) {
+    const size_t smem = (size_t)pfst::kSpStages * pfst::kSpCH * h * w * sizeof(float);
+    PFST_CUDA_TRY(cudaFuncSetAttribute(pfst::neigh_dots_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem), "pfst_neigh_dots/attr");
+    pfst::neigh_dots_plane_kernel<<<(unsigned)(T * B * ks), pfst::kSpThreads, smem, s>>>(
+        x_a, x_b, (int)B, D, h, w, dilation, ks, slot0, n_slots, dots);
+    PFST_CHECK_LAUNCH("pfst_neigh_dots");
+    return PFST_OK;
   }
   const int64_t plane = (int64_t)h * w;
   const dim3 grid((unsigned)((plane + 127) / 128), (unsigned)(T * B * ks), 1);
@@ -547,6 +761,9 @@ int pfst_neigh_grad(const float* x, const float* coef, int64_t B, int32_t D, int
     const int ks = pfst::nb_splits(B, h, w, D);
     return pfst::dispatch_grad_tma<false>(dilation, x, coef, (int)B, D, h, w, ks, grad_x, pfst::ProtoBwd{}, s);
   }
+  const int ksp = pfst::sp_grad_splits(B, D);
+  if (pfst::sp_ok(x, grad_x, D, h, w, ksp))
+    return pfst::launch_grad_plane<false>(x, coef, B, D, h, w, dilation, grad_x, pfst::ProtoBwd{}, ksp, s);
   return pfst::launch_grad_generic(x, coef, B, D, h, w, dilation, grad_x, s);
 }
 
@@ -568,7 +785,13 @@ int pfst_neigh_grad_proto(const float* x, const float* coef, int64_t B, int32_t 
       return pfst::dispatch_grad_tma<true>(dilation, x, coef, (int)B, D, h, w, ks, grad_x, pb, s);
     }
   }
-  // shapes the fused kernel does not cover: two passes over grad_x
+  const int ksp = pfst::sp_grad_splits(B, D);
+  if (pfst::sp_ok(x, grad_x, D, h, w, ksp) &&
+      (size_t)pfst::kSpStages * pfst::kSpCH * h * w * 4 + (size_t)C * (D / ksp + 1) * 4 <= 200 * 1024) {
+    pfst::ProtoBwd pb{labels, lab_h, lab_w, mu, seen, C, dist, acc, grad_loss, 0};
+    return pfst::launch_grad_plane<true>(x, coef, B, D, h, w, dilation, grad_x, pb, ksp, s);
+  }
+  // shapes the fused kernels do not cover: two passes over grad_x
   const int rc = pfst_neigh_grad(x, coef, B, D, h, w, dilation, grad_x, stream);
   if (rc != PFST_OK) return rc;
   return pfst_proto_dist_bwd(x, B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist, acc, grad_loss, grad_x, 1,
