@@ -329,6 +329,19 @@ int pfst_weighted_ce(const float* logits, const int64_t* labels, const float* we
                      int32_t H, int32_t W, int64_t ignore_index, float loss_weight,
                      float* grad_logits, double* stats, float* out2, void* stream);
 
+/* ---- next row: offline class-wise thresholds -------------------
+ * Replaces PseudoLabelingHookV4._cal_threshold
+ * (rsiseg/core/hook/pseudo_labeling_hookv4.py:173-205): for the n sampled pixels idx[] (row
+ * indices of the (B*HW, C) pixel-major view; NULL = all pixels in order) compute pred = argmax
+ * softmax, ent = sum -p*log(p), and for every class c and ratio r
+ *   thr_out[c*R + r] = (n_c == 0) ? 0 : sorted(ent[pred == c])[int(n_c * ratios[r])]
+ * — an exact order statistic by radix select, no sort. ratios_dev: device double[R].
+ * workspace: pfst_class_quantile_ws_bytes(n, C, R) bytes, 16-byte aligned.                */
+int64_t pfst_class_quantile_ws_bytes(int64_t n, int32_t C, int32_t R);
+int pfst_class_quantile(const float* logits, int64_t B, int32_t C, int64_t HW, const int64_t* idx,
+                        int64_t n, const double* ratios_dev, int32_t R, void* workspace,
+                        float* thr_out, void* stream);
+
 /* ---- V1/V4: confusion matrix / area histograms -------------------------------
  * Replaces intersect_and_union (rsiseg/core/evaluation/metrics.py:26-86, three
  * float32 torch.histc per image on the CPU) and the integer confusion matrix of

@@ -512,8 +512,8 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
 __global__ void __launch_bounds__(kPrThreads)
 proto_dist_all_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
                       const float* __restrict__ mu, int C, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char pa_smem[];
-  float* mu_s = reinterpret_cast<float*>(pa_smem);     // [C][D]
+  extern __shared__ __align__(16) unsigned char pall_smem[];
+  float* mu_s = reinterpret_cast<float*>(pall_smem);     // [C][D]
   const int hw = h * w;
   for (int i = threadIdx.x; i < C * D; i += kPrThreads) mu_s[i] = mu[i];
   __syncthreads();

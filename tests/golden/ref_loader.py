@@ -111,6 +111,22 @@ def decode_head_loss_fns():
     return _cache["ce"]
 
 
+def cal_threshold_fn():
+    """PseudoLabelingHookV4._cal_threshold compiled straight from the reference source file
+    (rsiseg/core/hook/pseudo_labeling_hookv4.py:173-205; its module needs mmcv / h5py)."""
+    if "calthr" not in _cache:
+        import ast
+        import numpy as np
+        import torch
+        import torch.nn.functional as F
+        tree = ast.parse((REF_ROOT / "rsiseg/core/hook/pseudo_labeling_hookv4.py").read_text())
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "_cal_threshold")
+        ns = {"np": np, "torch": torch, "F": F}
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref:pseudo_labeling_hookv4.py:_cal_threshold", "exec"), ns)
+        _cache["calthr"] = ns["_cal_threshold"]
+    return _cache["calthr"]
+
+
 class cpu_cuda_identity:
     """Context manager: make Tensor.cuda() the identity on a CUDA-less host."""
 

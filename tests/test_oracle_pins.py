@@ -168,3 +168,22 @@ def test_weighted_ce_oracle_vs_reference_live_and_golden():
             up = resize(input=logits, size=label.shape[2:], mode='bilinear', align_corners=False)
             lr = lwt * cross_entropy(up, label.squeeze(1), weight=weight, class_weight=cw, ignore_index=255)
             assert torch.equal(lr, lo.detach()) and torch.equal(accuracy(up, label.squeeze(1), ignore_index=255), ao)
+
+
+@pytest.mark.skipif(not R.available(), reason="reference checkout not present")
+def test_class_threshold_oracle_equals_reference_live():
+    """oracle.class_thresholds.cal_threshold == PseudoLabelingHookV4._cal_threshold (compiled from the
+    reference source), same numpy stream, bit for bit."""
+    import types
+    from oracle import class_thresholds as OT
+    from pfst_b200.synthetic import teacher_logits
+    ref = R.cal_threshold_fn()
+    for seed, (B, C, H, W, ratio) in enumerate([(2, 6, 32, 32, 0.5), (1, 33, 24, 24, 1.0), (2, 3, 17, 9, 0.3)]):
+        logits = teacher_logits(B, C, H, W, torch.Generator().manual_seed(seed))
+        ratios = [0.1, 0.5, 0.9]
+        np.random.seed(seed)
+        a = ref(types.SimpleNamespace(cls_thre_ratios=ratios), logits, ratio)
+        b = OT.cal_threshold(logits, ratio, ratios, np.random.RandomState(seed))
+        assert list(a) == list(b)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)), k
