@@ -184,6 +184,10 @@ class SelfTrainingStep:
         if self._world is None:
             import torch.distributed as dist
             self._world = dist.get_world_size(self.bank.group) if dist.is_available() and dist.is_initialized() else 1
+            if self._world > 1:
+                # first use on every rank (they construct and step symmetrically): one eager collective
+                # so that NCCL's lazy communicator set-up never happens inside a graph capture
+                dist.all_reduce(torch.zeros(1, device=self.device), group=self.bank.group)
         return self._world > 1
 
     def _whole_step(self, b, args_a, args_b, reduce: bool = False):
@@ -220,8 +224,10 @@ class SelfTrainingStep:
         side.wait_stream(torch.cuda.current_stream())
         snap = [t.clone() for t in (bank.packed, bank.mu, bank.seen, bank.counts, bank.iter_state)]
         with torch.cuda.stream(side):              # warm-up: module load, cudaFuncSetAttribute
+            # (no collective in the warm-up: a rank that re-captures alone must not issue an
+            # all-reduce its peers do not match; the communicator is initialised in _multi_rank())
             if parts == ("all",) or parts == ("reduce",):
-                self._whole_step(b, args_a, args_b, reduce=parts == ("reduce",))
+                self._whole_step(b, args_a, args_b, reduce=False)
             else:
                 self._segment_a(b, *args_a)
                 for part in parts:
