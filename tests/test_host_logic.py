@@ -1,0 +1,97 @@
+"""Host-side logic that needs no GPU: the ClassMix class draw (must consume the global numpy
+stream exactly like the reference), the EMA coefficient rule (host-only C entry point), the loss
+geometry validation, the registry plug-in mechanics and the byte accounting bench.py reports."""
+import numpy as np
+import pytest
+import torch
+
+from pfst_b200 import ops, registry
+from pfst_b200._lib import PfstError
+from pfst_b200.step import algorithmic_bytes
+from pfst_b200.utils.dacs_transforms import _present_classes, draw_class_choice
+from tests.golden import ref_loader as R
+
+
+def _presence_words(values):
+    w = np.zeros(9, dtype=np.uint32)
+    for v in values:
+        w[v >> 5] |= np.uint32(1) << np.uint32(v & 31)
+    return w
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_class_draw_equals_numpy_choice_on_the_same_stream(seed):
+    rs = np.random.RandomState(seed)
+    classes = np.array(sorted(rs.choice(256, size=rs.randint(1, 40), replace=False)), dtype=np.int64)
+    assert np.array_equal(_present_classes(_presence_words(classes.tolist())), classes)
+    a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+    got = draw_class_choice(classes, 7, a)
+    n = len(classes)
+    for i in range(7):
+        pick = b.choice(n, int((n + n % 2) / 2), replace=False)          # dacs_transforms.py:115-117
+        want = _presence_words(classes[pick].tolist())[:8]
+        assert np.array_equal(got[i], want)
+    assert a.randint(1 << 30) == b.randint(1 << 30)                      # stream left in the same state
+
+
+@pytest.mark.skipif(not R.available(), reason="reference checkout not present")
+def test_class_draw_reproduces_reference_get_class_masks():
+    ref = R.dacs_transforms()
+    g = torch.Generator().manual_seed(0)
+    labels = torch.randint(0, 6, (3, 1, 16, 16), generator=g)
+    labels[0, 0, :2] = 255
+    np.random.seed(42)
+    want = ref.get_class_masks(labels)                                   # list of (1,1,H,W) int64 masks
+    np.random.seed(42)
+    classes = torch.unique(labels).numpy()
+    chosen = draw_class_choice(classes, 3, np.random)
+    for i in range(3):
+        members = [v for v in range(256) if (chosen[i, v >> 5] >> np.uint32(v & 31)) & np.uint32(1)]
+        mask = torch.isin(labels[i], torch.tensor(members)).long().unsqueeze(0)
+        assert torch.equal(mask, want[i])
+
+
+def test_ema_coefficients_follow_the_reference_rule():
+    for it, alpha in [(1, 0.999), (2, 0.999), (10, 0.999), (999, 0.999), (1000, 0.999), (5000, 0.999), (3, 0.5)]:
+        a, b = ops.ema_coeffs(it, alpha)                                  # host-only entry point: no GPU needed
+        at = min(1 - 1 / (it + 1), alpha)                                 # pfgst.py:117
+        assert a == float(np.float32(at)) and b == float(np.float32(1 - at))
+
+
+def test_loss_geometry_rejects_unsupported_resampling():
+    geo = ops.LossGeometry((8, 6, 128, 128), (8, 512, 64, 64), (8, 1, 512, 512), 0.5, 2)
+    assert (geo.gh, geo.gw, geo.up, geo.lscale) == (64, 64, 1, 2.0)
+    geo = ops.LossGeometry((64, 33, 30, 30), (64, 512, 15, 15), (64, 1, 120, 120), None, 2)
+    assert (geo.gh, geo.up) == (30, 2)
+    with pytest.raises(PfstError):
+        ops.LossGeometry((1, 6, 100, 100), (1, 512, 64, 64), (1, 1, 512, 512), None, 2)     # 100 is not k*64
+    with pytest.raises(PfstError):
+        ops.LossGeometry((1, 6, 128, 128), (1, 512, 64, 64), (1, 1, 512, 512), None, 3)     # dilation % up
+
+
+def test_registry_plugs_into_a_foreign_registry():
+    import pfst_b200.losses  # noqa: F401  (registers PFGSTLoss)
+    import pfst_b200.uda     # noqa: F401  (registers PFGST)
+
+    class Foreign:                       # the slice of mmcv.utils.Registry that register_into uses
+        def __init__(self):
+            self.modules = {}
+
+        def register_module(self, name=None, force=False, module=None):
+            assert force and module is not None
+            self.modules[name] = module
+
+    f = Foreign()
+    registry.MODELS.register_into(f)
+    assert {"PFGST", "PFGSTLoss"} <= set(f.modules)
+    assert registry.UDA.get("PFGST") is f.modules["PFGST"]
+    with pytest.raises(KeyError):
+        registry.LOSSES.build(dict(type="NoSuchLoss"))
+
+
+def test_algorithmic_bytes_match_the_survey_table():
+    ab = algorithmic_bytes(8, 6, 512, 512, 512, 64, 64, 43579868)
+    assert ab["ema"] == 522958416                                         # 12 B x 43 579 868 params
+    assert ab["pseudo_label"] == (4 * 6 + 12) * 8 * 512 * 512              # 75.5 MB
+    assert ab["neigh_dots"] == 2 * 4 * 512 * 8 * 64 * 64                   # 134.2 MB
+    assert 1.30e9 < sum(ab.values()) < 1.45e9                              # ~1.31 GB + loss maps
