@@ -216,7 +216,7 @@ int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, i
  * to the loss grid (:62-67). weights6 (host): src_pos, src_neg, src_pos_std,
  * src_neg_std, sim_pos, sim_neg (:110-135).
  * workspace: device buffer of pfst_pfgst_loss_ws_bytes() bytes, 16-byte aligned, kept
- * (with stats) for the backward. stats: device double[16] (zeroed here).
+ * (with stats) for the backward. stats: device double[16] (first nine written here).
  * losses: device float[6] = loss_src_pos_mean, loss_src_neg_mean, loss_src_pos_std,
  * loss_src_neg_std, loss_sim_pos, loss_sim_neg. density (nullable): (B,fh*up,fw*up)
  * = 1 - mean_k cos_ema ('vis|density_sim_feat', :136); eroded (nullable): uint8 of
