@@ -1,0 +1,44 @@
+"""bench.py contract checks that need no GPU: the `--impl reference` arm prints one JSON line with
+the contract's keys (it times the CPU oracle, so it runs anywhere), and the product arm fails
+loudly on a machine without CUDA instead of falling back to anything."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "tiny"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "self_training_hot_path_throughput"
+    assert d["unit"] == "pixels/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
+    assert d["config"]["workload"].startswith("tiny")
+
+
+def test_reference_arm_under_torchrun_env_only_rank0_prints():
+    env = dict(**__import__("os").environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--workload", "tiny"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a host without CUDA")
+def test_product_arm_fails_loudly_without_a_gpu():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0", "--workload", "tiny"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
