@@ -362,6 +362,23 @@ int pfst_confusion_accum(const void* pred, int32_t pred_dtype, const void* label
                          const uint8_t* lut, int64_t* conf, int32_t per_image,
                          void* stream);
 
+/* ---- V0+V1: on-device evaluation input path ------------------
+ * Replaces, for a batch of n_images logit maps that are already on the GPU,
+ *   output   = F.softmax(seg_logit, dim=1)            encoder_decoder.py:311
+ *   seg_pred = output.argmax(dim=1).cpu().numpy()     encoder_decoder.py:329-338
+ *   intersect_and_union(seg_pred[i], gt[i], ...)      custom.py:644-682, metrics.py:26-86
+ * by one pass over logits (n_images, C, pixels) fp32 NCHW and label (n_images, pixels):
+ * pred = first index of the maximum of the softmax as torch CUDA computes it (ties in
+ * softmax space go to the lowest class; a NaN anywhere in the pixel's softmax gives 0),
+ * then conf[slot(i)][row][col] += 1 exactly as pfst_confusion_accum (same label_map LUT,
+ * reduce_zero_label, ignore_index, out-of-range row C; accumulated INTO conf).
+ * pred_out (nullable): the arg-max map itself, uint8 or int64 (pred_dtype), for callers
+ * that keep simple_test's return value. conf and label may both be NULL (arg-max only).  */
+int pfst_argmax_confusion(const float* logits, int64_t n_images, int32_t C, int64_t pixels,
+                          const void* label, int32_t label_dtype, int64_t ignore_index,
+                          int32_t reduce_zero_label, const uint8_t* lut, int64_t* conf,
+                          int32_t per_image, void* pred_out, int32_t pred_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,3 +86,19 @@ def eval_metrics(preds, labels, num_classes, ignore_index, metrics=("mIoU",), na
     """metrics.py:257-293."""
     return metrics_from_areas(*total_areas(preds, labels, num_classes, ignore_index, label_map,
                                            reduce_zero_label), metrics, nan_to_num, beta)
+
+
+def seg_argmax(seg_logits: torch.Tensor) -> torch.Tensor:
+    """EncoderDecoder.inference + simple_test, rsiseg/models/segmentors/encoder_decoder.py:311
+    (`output = F.softmax(seg_logit, dim=1)`) and :332 (`seg_pred = seg_logit.argmax(dim=1)`;
+    `seg_logit` there IS the softmax output). (N,C,H,W) -> int64 (N,H,W)."""
+    return torch.nn.functional.softmax(seg_logits, dim=1).argmax(dim=1)
+
+
+def pre_eval(seg_logits: torch.Tensor, gt_seg_maps, num_classes: int, ignore_index: int,
+             label_map=None, reduce_zero_label: bool = False):
+    """simple_test (encoder_decoder.py:329-338: arg-max, `.cpu().numpy()`, `list(seg_pred)`) followed
+    by dataset.pre_eval (rsiseg/datasets/custom.py:644-682: one intersect_and_union per image)."""
+    preds = list(seg_argmax(seg_logits).cpu().numpy())
+    return [areas(p, np.asarray(g), num_classes, ignore_index, label_map, reduce_zero_label)
+            for p, g in zip(preds, gt_seg_maps)]

@@ -67,6 +67,8 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_proto_dist_all": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "pfst_confusion_accum": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _vp,
                                        _i32, _vp]),
+    "pfst_argmax_confusion": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _i32,
+                                        _vp]),
 }
 
 _lock = threading.Lock()

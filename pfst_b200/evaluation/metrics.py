@@ -97,6 +97,28 @@ def intersect_and_union_batch(preds, labels, num_classes, ignore_index, label_ma
     return torch.stack(_areas_from_conf(conf, num_classes), dim=1)
 
 
+def seg_argmax(seg_logits: torch.Tensor, dtype: torch.dtype = torch.int64) -> torch.Tensor:
+    """`F.softmax(seg_logit, dim=1).argmax(dim=1)` of EncoderDecoder.inference/simple_test
+    (encoder_decoder.py:311,332) in one pass, kept on the device. (N,C,H,W) fp32 -> (N,H,W)."""
+    return ops.argmax_confusion(seg_logits, None, return_pred=dtype)[1]
+
+
+def pre_eval_logits(seg_logits: torch.Tensor, gt_seg_maps, num_classes: int, ignore_index: int,
+                    label_map=dict(), reduce_zero_label: bool = False):
+    """simple_test + dataset.pre_eval for logits that are still on the GPU
+    (encoder_decoder.py:329-338 + custom.py:644-682): the arg-max map never exists in memory and
+    never crosses PCIe; one launch and one (N,(C+1)^2) int64 read for the whole batch.
+    gt_seg_maps: (N,H,W) tensor/array or a list of N (H,W) maps. -> list of N tuples of four
+    float32 (C,) CPU tensors, exactly what `pre_eval` returns per image."""
+    if isinstance(gt_seg_maps, (list, tuple)):
+        gt_seg_maps = torch.stack([_to_device_map(g, "label") for g in gt_seg_maps])
+    l = _to_device_map(gt_seg_maps, "label")
+    conf, _ = ops.argmax_confusion(seg_logits, l, num_classes, ignore_index, reduce_zero_label,
+                                   _label_lut(label_map, seg_logits.device), per_image=True)
+    areas = [a.cpu().to(torch.float32) for a in _areas_from_conf(conf, num_classes)]
+    return [tuple(a[i] for a in areas) for i in range(conf.shape[0])]
+
+
 def total_intersect_and_union(results, gt_seg_maps, num_classes, ignore_index, label_map=dict(),
                               reduce_zero_label=False):
     """metrics.py:89-129 — float64 totals over a list of maps."""
@@ -207,6 +229,12 @@ class ConfusionMeter:
     def update(self, preds: torch.Tensor, labels: torch.Tensor) -> None:
         ops.confusion_accum(preds, labels, self.C, self.ignore_index, self.reduce_zero_label, self._lut,
                             out=self.conf)
+
+    def update_logits(self, seg_logits: torch.Tensor, labels: torch.Tensor) -> None:
+        """Same as `update(softmax(seg_logits,1).argmax(1), labels)` without materialising the
+        prediction map (fused arg-max + confusion kernel)."""
+        ops.argmax_confusion(seg_logits, labels, self.C, self.ignore_index, self.reduce_zero_label,
+                             self._lut, out=self.conf)
 
     def all_reduce(self, group=None) -> None:
         import torch.distributed as dist

@@ -243,6 +243,50 @@ def confusion_accum(pred: torch.Tensor, label: torch.Tensor, num_classes: int, i
     return out
 
 
+def argmax_confusion(seg_logits: torch.Tensor, label: Optional[torch.Tensor], num_classes: Optional[int] = None,
+                     ignore_index: int = 255, reduce_zero_label: bool = False,
+                     lut: Optional[torch.Tensor] = None, per_image: bool = False,
+                     out: Optional[torch.Tensor] = None, return_pred: Optional[torch.dtype] = None):
+    """Fused `softmax(seg_logits,1).argmax(1)` + confusion matrix (encoder_decoder.py:311,329-332 +
+    metrics.py:26-86). seg_logits (N,C,H,W) fp32; label (N,H,W) uint8/int32/int64 or None (arg-max
+    only, then ``return_pred`` is required). -> (conf int64 (slots,C+1,C+1) or None, pred or None)."""
+    _dev(seg_logits, "seg_logits", torch.float32)
+    if seg_logits.dim() != 4:
+        raise ValueError("seg_logits must be (N,C,H,W)")
+    N, Cn, H, W = seg_logits.shape
+    if num_classes is not None and int(num_classes) != Cn:
+        raise ValueError(f"seg_logits has {Cn} channels, num_classes={num_classes}")
+    if return_pred not in (None, torch.uint8, torch.int64):
+        raise TypeError("return_pred must be None, torch.uint8 or torch.int64")
+    if label is None and return_pred is None:
+        raise ValueError("nothing to compute: give a label map and/or return_pred")
+    pred = None
+    if return_pred is not None:
+        pred = torch.empty((N, H, W), dtype=return_pred, device=seg_logits.device)
+    conf = None
+    ldt = _lib.DT_U8
+    if label is not None:
+        if label.dtype not in _TORCH2DT:
+            raise TypeError("label must be uint8, int32 or int64")
+        _dev(label, "label")
+        if label.numel() != N * H * W:
+            raise ValueError("seg_logits/label shape mismatch")
+        ldt = _TORCH2DT[label.dtype]
+        slots = N if per_image else 1
+        if out is None:
+            out = torch.zeros((slots, Cn + 1, Cn + 1), dtype=torch.int64, device=seg_logits.device)
+        elif out.numel() != slots * (Cn + 1) * (Cn + 1):
+            raise ValueError("out has the wrong size")
+        conf = out
+    _lib.call("pfst_argmax_confusion", seg_logits.data_ptr(), N, Cn, H * W,
+              None if label is None else label.data_ptr(), ldt, int(ignore_index),
+              int(bool(reduce_zero_label)), _opt(lut, "lut", torch.uint8),
+              None if conf is None else _dev(conf, "out", torch.int64), int(per_image),
+              None if pred is None else pred.data_ptr(),
+              _lib.DT_I64 if return_pred == torch.int64 else _lib.DT_U8, _stream())
+    return conf, pred
+
+
 # ------------------------------------------------------------ L1-L6: PFGST loss
 def neigh_dots(x_a: torch.Tensor, x_b: Optional[torch.Tensor], dilation: int):
     """-> (dots float32 (splits, T, B, 5, h, w), splits)."""

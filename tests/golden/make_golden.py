@@ -240,14 +240,46 @@ def gen_weighted_ce():
     print("weighted_ce.npz", {k: float(v) for k, v in out.items() if k.endswith("_loss")})
 
 
+def eval_logits_cases():
+    """(name, N, C, H, W, label_map, reduce_zero_label)"""
+    return [("isprs", 3, 6, 64, 64, {}, False), ("inria", 2, 2, 48, 80, {}, False),
+            ("seasonnet", 2, 33, 30, 30, {}, False), ("remap", 2, 6, 40, 40, {7: 0, 6: 255}, True)]
+
+
+def eval_logits_inputs(name, N, C, H, W):
+    from pfst_b200.synthetic import blocky_labels, teacher_logits
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    logits = teacher_logits(N, C, H, W, g)
+    gt = blocky_labels(N, H, W, C + (2 if name == "remap" else 0), g)[:, 0].to(torch.uint8)
+    return logits, gt
+
+
+def gen_eval_logits():
+    """The reference's own EncoderDecoder.inference + simple_test (compiled from its source) on
+    synthetic logits, then its intersect_and_union per image (dataset.pre_eval, custom.py:644-682)."""
+    M = R.metrics()
+    out = {}
+    for name, N, C, H, W, lm, rz in eval_logits_cases():
+        logits, gt = eval_logits_inputs(name, N, C, H, W)
+        preds = R.simple_test_on_logits(logits)
+        per = [M.intersect_and_union(p, g, C, 255, label_map=dict(lm), reduce_zero_label=rz)
+               for p, g in zip(preds, gt.numpy())]
+        out[name + "_pred"] = np.stack(preds).astype(np.uint8)
+        out[name + "_areas"] = np.stack([np.stack([a.numpy() for a in t]) for t in per])
+    np.savez_compressed(OUT / "eval_logits.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "weighted_ce":
         gen_weighted_ce()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "eval_logits":
+        gen_eval_logits()
+        sys.exit(0)
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce):
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits):
         fn()
         print("wrote", fn.__name__)
     for p in sorted(OUT.glob("*.npz")):

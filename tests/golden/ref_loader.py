@@ -127,6 +127,41 @@ def cal_threshold_fn():
     return _cache["calthr"]
 
 
+def simple_test_fns():
+    """-> (inference, simple_test): EncoderDecoder.inference / simple_test compiled straight from
+    the reference source file (rsiseg/models/segmentors/encoder_decoder.py:283-353; its module
+    needs mmcv). Usable unbound on a duck-typed object that supplies `test_cfg.mode`,
+    `whole_inference` (the network pass, replaced by synthetic logits) and `inference`."""
+    if "simple_test" not in _cache:
+        import ast
+        import torch
+        import torch.nn.functional as F
+
+        class DataContainer:  # mmcv.parallel.DataContainer: only used in an isinstance test
+            pass
+
+        tree = ast.parse((REF_ROOT / "rsiseg/models/segmentors/encoder_decoder.py").read_text())
+        fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in ("inference", "simple_test")]
+        assert len(fns) == 2
+        ns = {"torch": torch, "F": F, "DataContainer": DataContainer}
+        exec(compile(ast.Module(body=fns, type_ignores=[]), "ref:encoder_decoder.py", "exec"), ns)
+        _cache["simple_test"] = (ns["inference"], ns["simple_test"])
+    return _cache["simple_test"]
+
+
+def simple_test_on_logits(seg_logits):
+    """Run the reference's inference + simple_test on synthetic logits (whole mode, no flip)
+    -> list of per-image int64 numpy arg-max maps, as simple_test returns them."""
+    import types
+    inference, simple_test = simple_test_fns()
+    obj = types.SimpleNamespace(test_cfg=types.SimpleNamespace(mode="whole"))
+    obj.whole_inference = lambda img, img_meta, rescale: (seg_logits, {})
+    obj.inference = lambda img, img_meta, rescale: inference(obj, img, img_meta, rescale)
+    meta = [dict(ori_shape=tuple(seg_logits.shape[2:]) + (3,), flip=False)]
+    seg_pred, _ = simple_test(obj, None, meta, True)
+    return seg_pred
+
+
 class cpu_cuda_identity:
     """Context manager: make Tensor.cuda() the identity on a CUDA-less host."""
 

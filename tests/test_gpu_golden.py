@@ -92,3 +92,18 @@ def test_pfgst_loss_golden(cuda, name):
         assert np.abs(g.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max(), key
     assert np.array_equal(res['vis|density_sim_feat'][2].cpu().numpy(), z[f"{name}_eroded"])
     assert np.allclose(res['vis|density_sim_feat'][1].cpu().numpy(), z[f"{name}_density"], rtol=0, atol=2e-6)
+
+
+def test_eval_logits_golden(cuda):
+    """fused arg-max + confusion kernel vs the fixture written by the reference's own
+    inference / simple_test / intersect_and_union on the same synthetic logits."""
+    from tests.golden.make_golden import eval_logits_cases, eval_logits_inputs
+    z = np.load(G / "eval_logits.npz")
+    for name, N, C, H, W, lm, rz in eval_logits_cases():
+        logits, gt = eval_logits_inputs(name, N, C, H, W)
+        top2 = torch.softmax(logits, 1).topk(2, dim=1).values
+        assert not bool(((top2[:, 0] - top2[:, 1]) < 1e-6).any()), "fixture holds a near tie"
+        pred = M.seg_argmax(logits.to(cuda), torch.uint8).cpu().numpy()
+        assert np.array_equal(pred, z[name + "_pred"]), name
+        per = M.pre_eval_logits(logits.to(cuda), gt.to(cuda), C, 255, lm, rz)
+        assert np.array_equal(np.stack([np.stack([a.numpy() for a in t]) for t in per]), z[name + "_areas"]), name

@@ -187,3 +187,36 @@ def test_class_threshold_oracle_equals_reference_live():
         assert list(a) == list(b)
         for k in a:
             assert np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)), k
+
+
+# ------------------------------------------------------------------ on-device evaluation path
+def test_eval_logits_oracle_vs_golden():
+    """oracle simple_test + pre_eval restatement vs the fixture written by the reference's own
+    inference/simple_test/intersect_and_union (tests/golden/make_golden.py::gen_eval_logits)."""
+    from tests.golden.make_golden import eval_logits_cases, eval_logits_inputs
+    z = load("eval_logits.npz")
+    for name, N, C, H, W, lm, rz in eval_logits_cases():
+        logits, gt = eval_logits_inputs(name, N, C, H, W)
+        assert np.array_equal(om.seg_argmax(logits).numpy(), z[name + "_pred"].astype(np.int64)), name
+        per = om.pre_eval(logits, list(gt.numpy()), C, 255, lm, rz)
+        assert np.array_equal(np.stack([np.stack([a.numpy() for a in t]) for t in per]), z[name + "_areas"]), name
+
+
+@needs_ref
+def test_eval_logits_oracle_equals_reference_live():
+    from pfst_b200.synthetic import teacher_logits
+    M = R.metrics()
+    for seed, (N, C, H, W) in enumerate([(2, 6, 32, 32), (1, 19, 17, 23), (2, 2, 8, 12)]):
+        g = torch.Generator().manual_seed(seed)
+        logits = teacher_logits(N, C, H, W, g)
+        logits[0, :, 0, 0] = 1.5            # exact tie -> first index
+        logits[0, 0, 0, 1] = float("nan")   # NaN -> softmax all NaN -> index 0
+        gt = torch.randint(0, C + 1, (N, H, W), generator=g).to(torch.uint8)
+        gt[:, :2] = 255
+        preds = R.simple_test_on_logits(logits)
+        assert np.array_equal(np.stack(preds), om.seg_argmax(logits).numpy())
+        want = [M.intersect_and_union(p, l, C, 255, label_map=dict(), reduce_zero_label=False)
+                for p, l in zip(preds, gt.numpy())]
+        got = om.pre_eval(logits, list(gt.numpy()), C, 255)
+        for a, b in zip(got, want):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))

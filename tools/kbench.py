@@ -254,6 +254,30 @@ def main():
         d33, l33 = torch.from_numpy(p33).to(dev), torch.from_numpy(g33).to(dev)
         out33 = torch.zeros((1, 34, 34), dtype=torch.int64, device=dev)
         report("conf_c33_random", 9 * n * 1024 * 1024, lambda i: ops.confusion_accum(d33, l33, 33, out=out33))
+    keep.clear()
+
+    if want("evallogits"):
+        # on-device evaluation input path: fused arg-max + confusion vs arg-max kernel -> confusion kernel
+        from pfst_b200.synthetic import blocky_labels, teacher_logits
+        n = 8
+        lgs = [teacher_logits(n, 6, 1024, 1024, g).to(dev) for _ in range(min(R, 4))]
+        gts8 = [blocky_labels(n, 1024, 1024, 6, g)[:, 0].to(torch.uint8).to(dev) for _ in range(min(R, 4))]
+        outp = torch.zeros((n, 7, 7), dtype=torch.int64, device=dev)
+        px = n * 1024 * 1024
+        report("argmax_confusion fused (blocky gt)", (4 * 6 + 1) * px,
+               lambda i: ops.argmax_confusion(lgs[i % len(lgs)], gts8[i % len(lgs)], 6, per_image=True, out=outp))
+
+        def two_kernels(i):
+            lab = ops.pseudo_label(lgs[i % len(lgs)], 0.0)[0]
+            ops.confusion_accum(lab, gts8[i % len(lgs)], 6, per_image=True, out=outp)
+        report("argmax kernel -> confusion kernel (same bytes counted)", (4 * 6 + 1) * px, two_kernels)
+        rnd = [torch.randn((n, 6, 1024, 1024), generator=g).to(dev) for _ in range(2)]
+        rgt = torch.randint(0, 6, (n, 1024, 1024), generator=g).to(torch.uint8).to(dev)
+        report("argmax_confusion fused (noise logits, random gt)", (4 * 6 + 1) * px,
+               lambda i: ops.argmax_confusion(rnd[i % 2], rgt, 6, per_image=True, out=outp))
+        report("argmax only (u8 map out)", (4 * 6 + 1) * px,
+               lambda i: keep.append(ops.argmax_confusion(rnd[i % 2], None, return_pred=torch.uint8)))
+        del lgs, gts8, rnd
     print(json.dumps({"peak_gbs": peak, "workload": wl.name, "graph": not args.no_graph}))
 
 
