@@ -379,6 +379,19 @@ int pfst_argmax_confusion(const float* logits, int64_t n_images, int32_t C, int6
                           int32_t reduce_zero_label, const uint8_t* lut, int64_t* conf,
                           int32_t per_image, void* pred_out, int32_t pred_dtype, void* stream);
 
+/* ---- strong augmentation: Gaussian blur of the mixed image -----
+ * Replaces gaussian_blur, rsiseg/models/utils/dacs_transforms.py:88-107:
+ *   kornia.filters.GaussianBlur2d(kernel_size=(ksize_y,ksize_x), sigma=(s,s))(data)
+ * (kornia: third-party, unpinned; published algorithm = normalised 1-D Gaussians
+ * exp(-x^2/(2 s^2)), x = t - k/2, 'reflect' border, per-channel correlation).
+ * in/out: (n_images, C, H, W) fp32, out != in. ksize_*: odd, ksize/2 < size (reflect).
+ * sigma_host: HOST array of n_images floats (one sigma per image, both axes, as the call
+ * site draws them); it is copied into the launch parameters, so the call is asynchronous
+ * and needs no staging buffer. Taps below 2^-40 of the centre weight are not evaluated.   */
+int pfst_gaussian_blur(const float* in, float* out, int64_t n_images, int32_t C, int32_t H,
+                       int32_t W, int32_t ksize_y, int32_t ksize_x, const float* sigma_host,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,6 +287,36 @@ def argmax_confusion(seg_logits: torch.Tensor, label: Optional[torch.Tensor], nu
     return conf, pred
 
 
+# --------------------------------------------- strong augmentation: Gaussian blur
+def blur_kernel_size(n: int) -> int:
+    """dacs_transforms.py:94-101: int(floor(ceil(0.1 n) - 0.5 + ceil(0.1 n) % 2)) (always odd)."""
+    import math
+    c = math.ceil(0.1 * n)
+    return int(math.floor(c - 0.5 + c % 2))
+
+
+def gaussian_blur(data: torch.Tensor, sigmas: Sequence[float], kernel_size: Optional[tuple] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kornia.filters.GaussianBlur2d(kernel_size, (sigma, sigma)) per image of data (N,C,H,W) fp32 with
+    one sigma per image (host floats). kernel_size defaults to the reference's rule (~10 % of the size)."""
+    _dev(data, "data", torch.float32)
+    if data.dim() != 4:
+        raise ValueError("data must be (N,C,H,W)")
+    N, Cn, H, W = data.shape
+    sig = [float(x) for x in sigmas]
+    if len(sig) != N:
+        raise ValueError(f"need one sigma per image ({N}), got {len(sig)}")
+    ky, kx = kernel_size if kernel_size is not None else (blur_kernel_size(H), blur_kernel_size(W))
+    if out is None:
+        out = torch.empty_like(data)
+    elif out.shape != data.shape or out.data_ptr() == data.data_ptr():
+        raise ValueError("out must be a distinct tensor of the same shape")
+    arr = (C.c_float * max(N, 1))(*sig)
+    _lib.call("pfst_gaussian_blur", data.data_ptr(), _dev(out, "out", torch.float32), N, Cn, H, W,
+              int(ky), int(kx), arr, _stream())
+    return out
+
+
 # ------------------------------------------------------------ L1-L6: PFGST loss
 def neigh_dots(x_a: torch.Tensor, x_b: Optional[torch.Tensor], dilation: int):
     """-> (dots float32 (splits, T, B, 5, h, w), splits)."""

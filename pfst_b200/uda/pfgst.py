@@ -16,6 +16,7 @@ sm_100a kernels of this package:
   :282      torch.unique + np.random.choice + eq/sum     ClassMixPlan (presence kernel,
                                                          36-byte D2H, host draw)
   :287-300  2B strong_transform calls in a Python loop   ops.class_mix, 1 launch
+            + kornia GaussianBlur2d per image (51x51)    ops.gaussian_blur, 1 launch
   :333-342  PFGSTLoss (~60 ATen kernels, 3+ syncs)       losses.PFGSTLoss, 2+2 launches
   optional  --                                           PrototypeBank / proto_dist_loss
                                                          (north_star P1-P3, cfg 'prototypes')
@@ -37,7 +38,7 @@ from .. import ops
 from .._lib import PfstError
 from ..prototypes import PrototypeBank, proto_dist_loss
 from ..registry import UDA, build_loss
-from ..utils.dacs_transforms import ClassMixPlan, get_mean_std
+from ..utils.dacs_transforms import ClassMixPlan, gaussian_blur_batch, get_mean_std
 from .uda_decorator import UDADecorator, build_model, get_module
 
 
@@ -159,16 +160,11 @@ class PFGST(UDADecorator):
             self._thr_vec = torch.tensor(list(self.pseudo_threshold_per_class), dtype=torch.float32, device=dev)
         return 0.0, self._thr_vec
 
-    def _check_kornia(self, color_jitter, blur):
-        wants = []
-        if color_jitter > self.color_jitter_p:
-            wants.append("ColorJitter (set color_jitter_probability=1.0)")
-        if blur > 0.5:
-            wants.append("GaussianBlur2d (set blur=False)")
-        if not wants:
+    def _check_kornia(self, color_jitter):
+        if not (color_jitter > self.color_jitter_p):
             return
-        msg = ("the kornia " + " and ".join(wants) + " branch of strong_transform is third-party arithmetic "
-               "outside the B200 hot path (SURVEY.md §8c)")
+        msg = ("the kornia ColorJitter (set color_jitter_probability=1.0) branch of strong_transform is "
+               "third-party arithmetic with its own random sampler, outside the B200 hot path (SURVEY.md §8c)")
         if self.kornia_aug == 'skip':
             warnings.warn(msg + "; skipped (kornia_aug='skip')", stacklevel=3)
         else:
@@ -193,7 +189,7 @@ class PFGST(UDADecorator):
         means, stds = get_mean_std(img_metas, dev)
         color_jitter = random.uniform(0, 1)
         blur = random.uniform(0, 1) if self.blur else 0
-        self._check_kornia(color_jitter, blur)
+        self._check_kornia(color_jitter)
 
         # ClassMix needs the batch's class set: start the presence kernel + 36-byte D2H now,
         # read it after the two network passes have been enqueued
@@ -240,6 +236,9 @@ class PFGST(UDADecorator):
             gt_semantic_seg, chosen, img.contiguous(), trg_img.contiguous(), pseudo_label,
             weight_in=weight_part, count=count, ps_size=ps_size,
             ignore_top=self.psweight_ignore_top, ignore_bottom=self.psweight_ignore_bottom)
+        # gaussian_blur of strong_transform (dacs_transforms.py:88-107): B sigma draws in image
+        # order on the global numpy stream (after the ClassMix draws, as in the reference loop)
+        mixed_img = gaussian_blur_batch(blur, mixed_img)
 
         # ⑧ student on the mixed batch (pfgst.py:303-310)
         mix_losses = self.get_model().forward_train(

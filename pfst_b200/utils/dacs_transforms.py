@@ -172,10 +172,32 @@ def one_mix(mask, data=None, target=None):
     return data, target
 
 
+def gaussian_blur(blur, data=None, target=None, rng=np.random):
+    """dacs_transforms.py:88-107. Same host behaviour as the reference: when `blur > 0.5` and data
+    has three channels, ONE `np.random.uniform(0.15, 1.15)` is drawn (global numpy stream) and the
+    whole `data` batch is blurred with it; the kernel edge is ~10 % of the image (odd). The
+    arithmetic is kornia's GaussianBlur2d restated in csrc/blur.cu (third-party, unpinned: see
+    oracle/strong_aug.py)."""
+    if data is not None and data.shape[1] == 3 and blur > 0.5:
+        sigma = rng.uniform(0.15, 1.15)
+        data = ops.gaussian_blur(data.contiguous(), [sigma] * data.shape[0])
+    return data, target
+
+
+def gaussian_blur_batch(blur, mixed_img: torch.Tensor, rng=np.random) -> torch.Tensor:
+    """The B per-image `gaussian_blur` calls of the mixing loop (pfgst.py:287-300) as ONE launch:
+    B sigma draws in image order (exactly the reference's numpy stream), one sigma per image."""
+    if mixed_img.shape[1] != 3 or not (blur > 0.5):
+        return mixed_img
+    sigmas = [rng.uniform(0.15, 1.15) for _ in range(mixed_img.shape[0])]
+    return ops.gaussian_blur(mixed_img.contiguous(), sigmas)
+
+
 def strong_transform(param, data=None, target=None):
-    """dacs_transforms.py:12-27. Colour jitter and Gaussian blur are kornia arithmetic
-    (third-party, unpinned — SURVEY.md §8c) and are NOT part of this path: requesting
-    them raises instead of silently skipping."""
+    """dacs_transforms.py:12-27: one_mix -> color_jitter -> gaussian_blur. The colour jitter is
+    kornia.augmentation.ColorJitter (third-party, version unpinned, random parameters drawn from
+    kornia's own torch-RNG sampler — SURVEY.md §8c) and is NOT part of this path: requesting it
+    raises instead of silently skipping."""
     assert (data is not None) or (target is not None)
     if "mix" in param:
         data, target = one_mix(mask=param["mix"], data=data, target=target)
@@ -183,8 +205,7 @@ def strong_transform(param, data=None, target=None):
         if param.get("color_jitter", 0) > param.get("color_jitter_p", 1.0):
             raise PfstError("kornia ColorJitter branch is outside the B200 hot path "
                             "(set color_jitter_probability=1.0)")
-        if param.get("blur", 0) > 0.5:
-            raise PfstError("kornia GaussianBlur2d branch is outside the B200 hot path (set blur=False)")
+    data, target = gaussian_blur(blur=param.get("blur", 0), data=data, target=target)
     return data, target
 
 

@@ -95,7 +95,19 @@ def test_one_mix_and_strong_transform_api(cuda):
     wpair = torch.stack((torch.ones(H, W), torch.full((H, W), 0.37)))
     _, w = T.strong_transform(param, target=wpair.to(cuda))
     assert torch.equal(w.cpu(), omix.mix_pair(mask, wpair[0], wpair[1]))
+    # blur branch (dacs_transforms.py:88-107): one sigma from the global numpy stream, then kornia's
+    # GaussianBlur2d (restated in oracle/strong_aug.py) on the mixed image
+    from oracle import strong_aug as osa
     param["blur"] = 0.9
+    np.random.seed(21)
+    d3, _ = T.strong_transform(param, data=data.to(cuda))
+    after = np.random.random()
+    np.random.seed(21)
+    want, sigma = osa.gaussian_blur(0.9, d_o)
+    assert 0.15 <= sigma <= 1.15 and after == np.random.random()      # same stream consumption
+    assert torch.allclose(d3.cpu(), want, rtol=1e-5, atol=1e-5 * float(d_o.abs().max()))
+    # the colour-jitter branch is kornia's random sampler + arithmetic: loud failure, never a silent skip
+    param["color_jitter"] = 0.5
     with pytest.raises(ops.PfstError):
         T.strong_transform(param, data=data.to(cuda))
 

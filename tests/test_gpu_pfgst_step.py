@@ -80,6 +80,30 @@ def test_kornia_branches_fail_loudly_or_skip(cuda):
         m.forward_train(**batch)
 
 
+def test_blur_branch_consumes_the_numpy_stream_like_the_reference(cuda, monkeypatch):
+    """blur=True, jitter disabled: per iteration the reference draws B class choices (get_class_masks)
+    and then, inside the mixing loop, one sigma per image (dacs_transforms.py:93). The drop-in must
+    leave the global numpy stream in exactly that state, and the mixed image must be blurred."""
+    batch = _to(next(iter(step_batches(1))), cuda)
+    m = _build(cuda, blur=True, color_jitter_probability=1.0)
+    monkeypatch.setattr(random, "uniform", lambda a, b: 0.9)      # color_jitter=0.9 <= p, blur=0.9 > 0.5
+    seen = {}
+    orig = ops.gaussian_blur
+    monkeypatch.setattr(ops, "gaussian_blur", lambda data, sigmas, *a, **k: seen.setdefault(
+        "out", (list(sigmas), orig(data, sigmas, *a, **k)))[1])
+    np.random.seed(17)
+    m.forward_train(**batch)
+    after = np.random.random()
+    rs = np.random.RandomState(17)
+    B = batch['img'].shape[0]
+    n = int(torch.unique(batch['gt_semantic_seg']).numel())
+    for _ in range(B):
+        rs.choice(n, int((n + n % 2) / 2), replace=False)
+    sig = [rs.uniform(0.15, 1.15) for _ in range(B)]
+    assert after == rs.random_sample()
+    assert seen["out"][0] == sig and tuple(seen["out"][1].shape) == tuple(batch['img'].shape)
+
+
 def test_part_threshold_and_prototype_extension(cuda):
     batch = _to(next(iter(step_batches(1))), cuda)
     m = _build(cuda, thre_type='part', prototypes=dict(weight=0.1, conf_threshold=0.5),

@@ -278,6 +278,16 @@ def main():
         report("argmax only (u8 map out)", (4 * 6 + 1) * px,
                lambda i: keep.append(ops.argmax_confusion(rnd[i % 2], None, return_pred=torch.uint8)))
         del lgs, gts8, rnd
+    keep.clear()
+
+    if want("blur"):
+        # strong_transform's Gaussian blur of the mixed image (kornia GaussianBlur2d, 51x51 at 512^2)
+        imgs = [inp["img"].to(dev) + 0.0 for _ in range(R)]
+        outs = [torch.empty_like(imgs[0]) for _ in range(R)]
+        for name, sig in (("sigma 1.15 (17 taps)", [1.15] * B), ("sigma 0.65 (9 taps)", [0.65] * B),
+                          ("sigma 0.15 (3 taps)", [0.15] * B)):
+            report("gaussian_blur " + name, 8 * 3 * P, lambda i: ops.gaussian_blur(imgs[i], sig, out=outs[i]))
+        del imgs, outs
     print(json.dumps({"peak_gbs": peak, "workload": wl.name, "graph": not args.no_graph}))
 
 
