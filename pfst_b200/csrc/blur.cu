@@ -32,6 +32,8 @@ constexpr int kBlTile = 64;        // output tile edge
 constexpr int kBlOut = 8;          // outputs per thread and task
 constexpr int kBlMaxImages = 64;   // sigmas carried in the launch parameters
 constexpr int kBlMaxTaps = 2 * 80 + 1;
+// taps with |x| > kBlCutoff * sigma weigh less than 2^-40 of the centre tap: sqrt(2 * 40 * ln 2)
+constexpr float kBlCutoff = 7.4465948f;
 
 struct BlurParams {
   const float* in;
@@ -111,9 +113,13 @@ gaussian_blur_kernel(const BlurParams q) {
   const float* __restrict__ src = q.in + ((int64_t)b * q.C + c) * q.H * (int64_t)q.W;
   float* __restrict__ dst = q.out + ((int64_t)b * q.C + c) * q.H * (int64_t)q.W;
 
+  // this image's own effective radii (<= the launch's, which size the halo): the result of an
+  // image does not depend on which other images share its launch
   const float sigma = q.sigma[b];
-  if (tid < 32) blur_weights(wx, q.kx, rx, sigma);
-  else if (tid < 64) blur_weights(wy, q.ky, ry, sigma);
+  const int r_img = (int)floorf(kBlCutoff * sigma);
+  const int rxi = min(rx, r_img), ryi = min(ry, r_img);
+  if (tid < 32) blur_weights(wx, q.kx, rxi, sigma);
+  else if (tid < 64) blur_weights(wy, q.ky, ryi, sigma);
 
   // stage the tile and its halo (reflect border)
   for (int i = tid; i < rows * cols; i += kBlThreads) {
@@ -133,7 +139,7 @@ gaussian_blur_kernel(const BlurParams q) {
     for (int t = tid; t < tasks; t += kBlThreads) {
       const int chunk = t / rows, r = t - chunk * rows;
       float acc[kBlOut];
-      blur_slide<1>(A + r * PA + chunk * kBlOut, 1, wx, 2 * rx + 1, acc);
+      blur_slide<1>(A + r * PA + chunk * kBlOut + (rx - rxi), 1, wx, 2 * rxi + 1, acc);
 #pragma unroll
       for (int j = 0; j < kBlOut; ++j) Bm[r * PB + chunk * kBlOut + j] = acc[j];
     }
@@ -146,7 +152,7 @@ gaussian_blur_kernel(const BlurParams q) {
     for (int t = tid; t < tasks; t += kBlThreads) {
       const int chunk = t / kBlTile, cc = t - chunk * kBlTile;
       float acc[kBlOut];
-      blur_slide<0>(Bm + (chunk * kBlOut) * PB + cc, PB, wy, 2 * ry + 1, acc);
+      blur_slide<0>(Bm + (chunk * kBlOut + (ry - ryi)) * PB + cc, PB, wy, 2 * ryi + 1, acc);
       const int gx = x_org + cc;
       if (gx < q.W) {
 #pragma unroll
@@ -168,7 +174,7 @@ static size_t blur_smem_bytes(int ry, int rx) {
 // taps with |x| <= r are evaluated: weights below 2^-40 of the centre are dropped
 static int blur_radius(int k, float sigma_max) {
   const int half = k / 2;
-  const double r = floor(sqrt(2.0 * 40.0 * 0.6931471805599453) * (double)sigma_max);
+  const double r = floor((double)kBlCutoff * (double)sigma_max) + 1.0;   // >= the kernel's per-image floorf
   return r < (double)half ? (int)r : half;
 }
 

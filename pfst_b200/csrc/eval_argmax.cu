@@ -368,11 +368,11 @@ extern "C" int pfst_argmax_confusion(const float* logits, int64_t n_images, int3
                                      int32_t per_image, void* pred_out, int32_t pred_dtype,
                                      void* stream) {
   if (n_images < 0 || pixels < 0 || C < 1 || C > 255) return PFST_ERR_INVALID_ARG;
+  if (pred_out && pred_dtype != PFST_DT_U8 && pred_dtype != PFST_DT_I64) return PFST_ERR_INVALID_ARG;
+  if (n_images == 0 || pixels == 0) return PFST_OK;               // empty tensors may carry NULL pointers
+  if (!logits) return PFST_ERR_INVALID_ARG;
   if (!conf && !pred_out) return PFST_ERR_INVALID_ARG;            // nothing to produce
   if ((conf != nullptr) != (label != nullptr)) return PFST_ERR_INVALID_ARG;
-  if (pred_out && pred_dtype != PFST_DT_U8 && pred_dtype != PFST_DT_I64) return PFST_ERR_INVALID_ARG;
-  if (n_images == 0 || pixels == 0) return PFST_OK;
-  if (!logits) return PFST_ERR_INVALID_ARG;
   if (pixels > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;         // 32-bit per-image counters
   pfst::EvParams q;
   q.logits = logits;
