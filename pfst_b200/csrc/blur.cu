@@ -213,7 +213,7 @@ extern "C" int pfst_gaussian_blur(const float* in, float* out, int64_t n_images,
     q.tiles_x = (W + kBlTile - 1) / kBlTile;
     const size_t smem = blur_smem_bytes(q.ry, q.rx);
     if (smem > 200 * 1024) return PFST_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024)
+    if (smem + 4096 > 48 * 1024)   // the static weight arrays count against the 48 KB default too
       PFST_CUDA_TRY(cudaFuncSetAttribute(gaussian_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem), "pfst_gaussian_blur/attr");
     const int64_t grid = (int64_t)q.n_img * C * q.tiles_y * q.tiles_x;

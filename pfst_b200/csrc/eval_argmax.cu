@@ -92,20 +92,23 @@ __device__ __forceinline__ int ev_pixel(const float (&x)[CMAX], const float* __r
   return am;
 }
 
-template <typename LT>
-__device__ __forceinline__ void ev_load_labels4(const LT* __restrict__ p, int64_t (&l)[4]) {
-  if constexpr (sizeof(LT) == 1) {
-    const unsigned w = __ldcs(reinterpret_cast<const unsigned*>(p));
-    l[0] = w & 0xffu; l[1] = (w >> 8) & 0xffu; l[2] = (w >> 16) & 0xffu; l[3] = w >> 24;
-  } else if constexpr (sizeof(LT) == 4) {
-    const int4 w = ldg_stream_i4(p);
-    l[0] = w.x; l[1] = w.y; l[2] = w.z; l[3] = w.w;
-  } else {
-    const longlong2 a = ldg_stream_l2(reinterpret_cast<const int64_t*>(p));
-    const longlong2 b = ldg_stream_l2(reinterpret_cast<const int64_t*>(p) + 2);
-    l[0] = a.x; l[1] = a.y; l[2] = b.x; l[3] = b.y;
-  }
-}
+// Four consecutive labels kept as loaded (one register for uint8 maps) and unpacked on use.
+template <typename LT> struct EvLab4;
+template <> struct EvLab4<uint8_t> {
+  unsigned w = 0;
+  __device__ __forceinline__ void load(const uint8_t* __restrict__ p) { w = __ldcs(reinterpret_cast<const unsigned*>(p)); }
+  __device__ __forceinline__ int64_t get(int k) const { return (int64_t)((w >> (8 * k)) & 0xffu); }
+};
+template <> struct EvLab4<int32_t> {
+  int4 v = {0, 0, 0, 0};
+  __device__ __forceinline__ void load(const int32_t* __restrict__ p) { v = ldg_stream_i4(p); }
+  __device__ __forceinline__ int64_t get(int k) const { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+};
+template <> struct EvLab4<int64_t> {
+  longlong2 a = {0, 0}, b = {0, 0};
+  __device__ __forceinline__ void load(const int64_t* __restrict__ p) { a = ldg_stream_l2(p); b = ldg_stream_l2(p + 2); }
+  __device__ __forceinline__ int64_t get(int k) const { return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? b.x : b.y)); }
+};
 
 // bin (row*(C+1)+col) of a raw label and an in-range prediction; >= bins when ignored
 __device__ __forceinline__ unsigned ev_bin(int64_t lab, unsigned pred, const unsigned* row_off,
@@ -165,14 +168,45 @@ struct EvBlock {
 // C <= 8, 128-bit loads: four consecutive pixels per thread, next item's loads in flight
 // while the current one is ranked and counted. Blocks own contiguous spans of the pixel
 // stream and flush their histogram once per image they touch.
+// Counting (as csrc/confusion.cu, strategy 0): every thread owns a private column of 16-bit
+// counters, priv[bin][tid] — plain LDS/ADD/STS, no atomics, no warp votes, independent of the
+// label distribution; columns are summed and flushed per image (and before they can wrap).
 template <int C, typename LT>
 __global__ void __launch_bounds__(kEvThreads)
 argmax_confusion_vec4_kernel(const EvParams q) {
   extern __shared__ __align__(16) unsigned ev_smem[];
-  __shared__ unsigned row_off[256];
-  EvBlock blk;
-  blk.init(q, ev_smem, row_off);
-  const int tid = threadIdx.x;
+  __shared__ unsigned row_off[256];   // raw label byte -> element offset of its matrix row in priv
+  constexpr unsigned C1 = C + 1;
+  constexpr int kBins = (int)(C1 * C1);            // flushed bins; the scratch row follows them
+  constexpr int kRowsTotal = (int)(C1 * (C1 + 1));
+  constexpr int kWordsPerBin = kEvThreads / 2;     // two 16-bit counters per 32-bit word
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool on = q.conf != nullptr;
+  unsigned short* priv = reinterpret_cast<unsigned short*>(ev_smem);
+  row_off[tid] = (unsigned)ev_row(tid, q, q.lut) * C1 * kEvThreads;   // kEvThreads == 256
+  if (on)
+    for (int i = tid; i < kRowsTotal * kWordsPerBin; i += kEvThreads) ev_smem[i] = 0u;
+  __syncthreads();
+
+  // add the block's counts into the image's matrix and clear them (all threads)
+  auto flush = [&](int64_t* out) {
+    if (!on) return;
+    __syncthreads();
+    for (int b = warp; b < kBins; b += kEvWarps) {
+      unsigned sum = 0;
+#pragma unroll
+      for (int k = 0; k < kWordsPerBin / 32; ++k) {
+        const unsigned w = ev_smem[b * kWordsPerBin + k * 32 + lane];
+        sum += (w & 0xffffu) + (w >> 16);
+        ev_smem[b * kWordsPerBin + k * 32 + lane] = 0u;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0 && sum) atomicAdd(reinterpret_cast<unsigned long long*>(out) + b, (unsigned long long)sum);
+    }
+    __syncthreads();
+  };
+  constexpr int kItersPerFlush = 65535 / 4;   // a private counter gains at most 4 per iteration
+
   const LT* __restrict__ label = static_cast<const LT*>(q.label);
   const int64_t HW = q.pixels;
   const int64_t upi = HW / 4;   // units per image
@@ -182,7 +216,7 @@ argmax_confusion_vec4_kernel(const EvParams q) {
   if (span_end > total_units) span_end = total_units;
 
   float cur[4][C], nxt[4][C];
-  int64_t lcur[4] = {0, 0, 0, 0}, lnxt[4] = {0, 0, 0, 0};
+  EvLab4<LT> lcur, lnxt;
 
   while (u < span_end) {
     const int64_t img = u / upi;
@@ -190,21 +224,26 @@ argmax_confusion_vec4_kernel(const EvParams q) {
     int64_t seg_end = u0 + upi;
     if (seg_end > span_end) seg_end = span_end;
     const float* __restrict__ lg = q.logits + img * (int64_t)C * HW;
-    const LT* __restrict__ lb = blk.on ? label + img * HW : nullptr;
-    int64_t* out = blk.on ? q.conf + (q.per_image ? img : 0) * (int64_t)blk.bins : nullptr;
+    const LT* __restrict__ lb = on ? label + img * HW : nullptr;
+    int64_t* out = on ? q.conf + (q.per_image ? img : 0) * (int64_t)kBins : nullptr;
 
-    auto load = [&](int64_t unit, float (&X)[4][C], int64_t (&L)[4]) {
+    auto load = [&](int64_t unit, float (&X)[4][C], EvLab4<LT>& L) {
       const int64_t off = (unit - u0) * 4;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float4 v = ldg_stream_f4(lg + (int64_t)c * HW + off);
         X[0][c] = v.x; X[1][c] = v.y; X[2][c] = v.z; X[3][c] = v.w;
       }
-      if (lb) ev_load_labels4<LT>(lb + off, L);
+      if (lb) L.load(lb + off);
     };
 
     if (u + tid < seg_end) load(u + tid, cur, lcur);
+    int iters = 0;
     for (int64_t base = u; base < seg_end; base += kEvThreads) {
+      if (++iters > kItersPerFlush) {   // block-uniform
+        flush(out);
+        iters = 1;
+      }
       const int64_t unit = base + tid;
       const bool live = unit < seg_end;
       if (unit + kEvThreads < seg_end) load(unit + kEvThreads, nxt, lnxt);
@@ -225,27 +264,28 @@ argmax_confusion_vec4_kernel(const EvParams q) {
                 pred[0] | (pred[1] << 8) | (pred[2] << 16) | (pred[3] << 24);
           }
         }
-      }
-      if (blk.on) {
-        unsigned bin[4];
+        if (on) {
+          // all four counter addresses first (independent LDS lookups), then the updates
+          unsigned idx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) bin[k] = live ? ev_bin(lcur[k], pred[k], row_off, q) : blk.bins;
-        const bool same = (bin[0] == bin[1]) && (bin[1] == bin[2]) && (bin[2] == bin[3]);
-        if (__all_sync(0xffffffffu, same)) {
-          ev_count(bin[0], 4u, blk.bins, blk.hist, out, blk.n_hist);
-        } else {
+          for (int k = 0; k < 4; ++k) {
+            const int64_t lab = lcur.get(k);
+            const unsigned roff = ((unsigned long long)lab < 256ull)
+                                      ? row_off[lab]
+                                      : (unsigned)ev_row(lab, q, nullptr) * C1 * kEvThreads;
+            idx[k] = roff + pred[k] * kEvThreads + tid;
+          }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ev_count(bin[k], 1u, blk.bins, blk.hist, out, blk.n_hist);
+          for (int k = 0; k < 4; ++k) priv[idx[k]] += 1;
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int c = 0; c < C; ++c) cur[k][c] = nxt[k][c];
-        lcur[k] = lnxt[k];
-      }
+      lcur = lnxt;
     }
-    blk.flush(out);
+    flush(out);
     u = seg_end;
   }
 }
@@ -314,11 +354,9 @@ argmax_confusion_generic_kernel(const EvParams q) {
 }
 
 template <typename K>
-static int launch_ev(K kernel, EvParams q, int vec, cudaStream_t s) {
-  const int64_t bins = (int64_t)(q.C + 1) * (q.C + 1);
-  q.n_hist = !q.conf ? 0 : (bins <= kEvWarpHistMaxBins ? kEvWarps : (bins <= kEvBlockHistMaxBins ? 1 : 0));
-  const size_t smem = (size_t)q.n_hist * bins * sizeof(unsigned);
-  if (smem > 48 * 1024)
+static int launch_ev(K kernel, EvParams q, int vec, size_t smem, cudaStream_t s) {
+  // static shared memory (row_off) counts against the 48 KB default limit too
+  if (smem + 2048 > 48 * 1024)
     PFST_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "pfst_argmax_confusion/attr");
   int occ = 0;
@@ -341,23 +379,36 @@ static int launch_ev(K kernel, EvParams q, int vec, cudaStream_t s) {
   return PFST_OK;
 }
 
+// private 16-bit counter columns of the vec4 kernel: (C+1)(C+2) bins x 256 threads
+static size_t ev_private_smem(const EvParams& q) {
+  return q.conf ? (size_t)(q.C + 1) * (q.C + 2) * kEvThreads * sizeof(unsigned short) : 0;
+}
+
+template <typename LT>
+static int launch_ev_generic(EvParams q, cudaStream_t s) {
+  const int64_t bins = (int64_t)(q.C + 1) * (q.C + 1);
+  q.n_hist = !q.conf ? 0 : (bins <= kEvWarpHistMaxBins ? kEvWarps : (bins <= kEvBlockHistMaxBins ? 1 : 0));
+  return launch_ev(argmax_confusion_generic_kernel<LT>, q, 1, (size_t)q.n_hist * bins * sizeof(unsigned), s);
+}
+
 template <typename LT>
 static int dispatch_ev(const EvParams& q, cudaStream_t s) {
   const bool vec4 = q.C <= 8 && (q.pixels % 4 == 0) && aligned16(q.logits) &&
                     (!q.label || aligned16(q.label)) && (!q.pred_out || aligned16(q.pred_out));
   if (vec4) {
+    const size_t smem = ev_private_smem(q);
     switch (q.C) {
-      case 1: return launch_ev(argmax_confusion_vec4_kernel<1, LT>, q, 4, s);
-      case 2: return launch_ev(argmax_confusion_vec4_kernel<2, LT>, q, 4, s);
-      case 3: return launch_ev(argmax_confusion_vec4_kernel<3, LT>, q, 4, s);
-      case 4: return launch_ev(argmax_confusion_vec4_kernel<4, LT>, q, 4, s);
-      case 5: return launch_ev(argmax_confusion_vec4_kernel<5, LT>, q, 4, s);
-      case 6: return launch_ev(argmax_confusion_vec4_kernel<6, LT>, q, 4, s);
-      case 7: return launch_ev(argmax_confusion_vec4_kernel<7, LT>, q, 4, s);
-      default: return launch_ev(argmax_confusion_vec4_kernel<8, LT>, q, 4, s);
+      case 1: return launch_ev(argmax_confusion_vec4_kernel<1, LT>, q, 4, smem, s);
+      case 2: return launch_ev(argmax_confusion_vec4_kernel<2, LT>, q, 4, smem, s);
+      case 3: return launch_ev(argmax_confusion_vec4_kernel<3, LT>, q, 4, smem, s);
+      case 4: return launch_ev(argmax_confusion_vec4_kernel<4, LT>, q, 4, smem, s);
+      case 5: return launch_ev(argmax_confusion_vec4_kernel<5, LT>, q, 4, smem, s);
+      case 6: return launch_ev(argmax_confusion_vec4_kernel<6, LT>, q, 4, smem, s);
+      case 7: return launch_ev(argmax_confusion_vec4_kernel<7, LT>, q, 4, smem, s);
+      default: return launch_ev(argmax_confusion_vec4_kernel<8, LT>, q, 4, smem, s);
     }
   }
-  return launch_ev(argmax_confusion_generic_kernel<LT>, q, 1, s);
+  return launch_ev_generic<LT>(q, s);
 }
 
 }  // namespace pfst

@@ -51,6 +51,19 @@ def test_blur_reference_sigma_range_and_image_statistics(cuda):
     _check(cuda, x, [osa.draw_sigma(rs) for _ in range(4)])
 
 
+def test_blur_cfg2_batch_at_the_largest_reference_sigma(cuda):
+    # B=8 x 512^2, sigma at the top of the reference's range: 19 of 51 taps, ~49 KB of shared memory
+    # (the size at which the launch needs the opt-in above the 48 KB default)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((8, 3, 512, 512), generator=g)
+    sig = [1.15, 0.9, 0.15, 0.5, 1.0, 0.3, 0.75, 1.149]
+    got = ops.gaussian_blur(x.to(cuda), sig).cpu()
+    tol = 1e-5 * float(x.abs().max())
+    for i in (0, 2, 7):
+        want = osa.gaussian_blur2d(x[i:i + 1], (51, 51), (sig[i], sig[i]))
+        assert float((got[i:i + 1] - want).abs().max()) <= tol, i
+
+
 def test_blur_wide_sigma_uses_every_tap(cuda):
     # sigma large against the kernel: no tap is below the 2^-40 cut-off, reflect border fully used
     g = torch.Generator().manual_seed(4)

@@ -95,3 +95,33 @@ def test_algorithmic_bytes_match_the_survey_table():
     assert ab["pseudo_label"] == (4 * 6 + 12) * 8 * 512 * 512              # 75.5 MB
     assert ab["neigh_dots"] == 2 * 4 * 512 * 8 * 64 * 64                   # 134.2 MB
     assert 1.30e9 < sum(ab.values()) < 1.45e9                              # ~1.31 GB + loss maps
+
+
+def test_blur_kernel_size_rule_and_sigma_stream():
+    """dacs_transforms.py:93-101: kernel edge ~10 % of the image, odd; one uniform(0.15, 1.15) per call.
+    The inactive branches must not touch the numpy stream (and need no GPU)."""
+    from oracle import strong_aug as osa
+    from pfst_b200.utils import dacs_transforms as T
+    for n in list(range(1, 300)) + [512, 1000, 1024, 2048]:
+        k = ops.blur_kernel_size(n)
+        want = int(np.floor(np.ceil(0.1 * n) - 0.5 + np.ceil(0.1 * n) % 2))
+        assert k == want == osa.kernel_size(n) and k % 2 == 1 and k // 2 < max(n, 2)
+    x = torch.zeros((2, 3, 8, 8))
+    np.random.seed(4)
+    before = np.random.get_state()[1].copy()
+    assert T.gaussian_blur_batch(0.5, x) is x                 # blur <= 0.5: inactive
+    assert T.gaussian_blur(0.2, data=x)[0] is x
+    assert T.gaussian_blur(0.9, data=torch.zeros((2, 1, 8, 8)))[0].shape[1] == 1    # not an RGB batch
+    assert T.gaussian_blur(0.9, data=None, target=x) == (None, x)
+    assert np.array_equal(before, np.random.get_state()[1])
+    with pytest.raises(PfstError):                            # active branch on a CPU tensor: loud, no fallback
+        T.gaussian_blur(0.9, data=x)
+
+
+def test_eval_logits_argument_validation_needs_no_gpu():
+    z = torch.zeros((1, 6, 4, 4))
+    with pytest.raises(PfstError):
+        ops.argmax_confusion(z, torch.zeros((1, 4, 4), dtype=torch.uint8), 6)      # CPU tensors
+    from pfst_b200.evaluation import metrics as M
+    with pytest.raises(PfstError):
+        M.seg_argmax(z)
