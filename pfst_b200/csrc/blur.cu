@@ -121,12 +121,36 @@ gaussian_blur_kernel(const BlurParams q) {
   if (tid < 32) blur_weights(wx, q.kx, rxi, sigma);
   else if (tid < 64) blur_weights(wy, q.ky, ryi, sigma);
 
-  // stage the tile and its halo (reflect border)
-  for (int i = tid; i < rows * cols; i += kBlThreads) {
-    const int r = i / cols, cc = i - r * cols;
-    const int gy = reflect_index(y_org - ry + r, q.H);
-    const int gx = reflect_index(x_org - rx + cc, q.W);
-    A[r * PA + cc] = __ldg(src + (int64_t)gy * q.W + gx);
+  // stage the tile and its halo (reflect border). A warp takes one 32-column segment of one row
+  // per item (coalesced, no per-element division) and every thread issues a batch of loads before
+  // its first store: with one load in flight per thread the staging is latency-bound at ~1 TB/s.
+  {
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int nseg = (cols + 31) >> 5;
+    const int items = rows * nseg;
+    constexpr int kBatch = 8, kWarps = kBlThreads / 32;
+    for (int it0 = wrp; it0 < items; it0 += kWarps * kBatch) {
+      float v[kBatch];
+      int at[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int item = it0 + j * kWarps;
+        at[j] = -1;
+        v[j] = 0.f;
+        if (item < items) {
+          const int r = item / nseg, cc = (item - r * nseg) * 32 + lane;
+          if (cc < cols) {
+            const int gy = reflect_index(y_org - ry + r, q.H);
+            const int gx = reflect_index(x_org - rx + cc, q.W);
+            v[j] = __ldg(src + (int64_t)gy * q.W + gx);
+            at[j] = r * PA + cc;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j)
+        if (at[j] >= 0) A[at[j]] = v[j];
+    }
   }
   // slack elements read (and discarded) by the last slide of every task
   for (int r = tid; r < rows; r += kBlThreads) A[r * PA + cols] = 0.f;
