@@ -121,35 +121,59 @@ gaussian_blur_kernel(const BlurParams q) {
   if (tid < 32) blur_weights(wx, q.kx, rxi, sigma);
   else if (tid < 64) blur_weights(wy, q.ky, ryi, sigma);
 
-  // stage the tile and its halo (reflect border). A warp takes one 32-column segment of one row
-  // per item (coalesced, no per-element division) and every thread issues a batch of loads before
-  // its first store: with one load in flight per thread the staging is latency-bound at ~1 TB/s.
+  // stage the tile and its halo (reflect border). One warp per row: the row index is reflected
+  // once, the 64 interior columns are one aligned 64-bit load per lane and the 2*rx halo columns one
+  // scalar load per lane — ~10 instructions per row and thread (a flat element loop spends ~45
+  // integer instructions per element on division, two reflections and 64-bit addressing, which
+  // made the staging, not the convolution, the bulk of the kernel).
   {
     const int lane = tid & 31, wrp = tid >> 5;
-    const int nseg = (cols + 31) >> 5;
-    const int items = rows * nseg;
-    constexpr int kBatch = 8, kWarps = kBlThreads / 32;
-    for (int it0 = wrp; it0 < items; it0 += kWarps * kBatch) {
-      float v[kBatch];
-      int at[kBatch];
+    constexpr int kWarps = kBlThreads / 32, kRows = 4;   // rows in flight per warp
+    const bool fast = (q.W % 2 == 0) && (x_org + kBlTile <= q.W) &&
+                      ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+    if (fast) {
+      // halo column of this lane (first 32 halo columns; wider halos loop below)
+      const int hc0 = lane < rx ? lane : lane + kBlTile;        // left halo [0,rx), right [rx+64, cols)
+      const bool has_h = lane < 2 * rx;
+      const int gxh = reflect_index(x_org - rx + hc0, q.W);
+      for (int r0 = wrp; r0 < rows; r0 += kWarps * kRows) {
+        float2 v[kRows];
+        float hv[kRows];
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int item = it0 + j * kWarps;
-        at[j] = -1;
-        v[j] = 0.f;
-        if (item < items) {
-          const int r = item / nseg, cc = (item - r * nseg) * 32 + lane;
-          if (cc < cols) {
-            const int gy = reflect_index(y_org - ry + r, q.H);
-            const int gx = reflect_index(x_org - rx + cc, q.W);
-            v[j] = __ldg(src + (int64_t)gy * q.W + gx);
-            at[j] = r * PA + cc;
+        for (int j = 0; j < kRows; ++j) {
+          const int r = r0 + j * kWarps;
+          if (r < rows) {
+            const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+            v[j] = __ldg(reinterpret_cast<const float2*>(row + x_org) + lane);
+            hv[j] = has_h ? __ldg(row + gxh) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+          const int r = r0 + j * kWarps;
+          if (r < rows) {
+            float* a = A + r * PA;
+            a[rx + 2 * lane] = v[j].x;
+            a[rx + 2 * lane + 1] = v[j].y;
+            if (has_h) a[hc0] = hv[j];
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j)
-        if (at[j] >= 0) A[at[j]] = v[j];
+      if (2 * rx > 32) {   // wide kernels: the rest of the halo, element by element
+        for (int r = wrp; r < rows; r += kWarps) {
+          const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+          for (int hc = 32 + lane; hc < 2 * rx; hc += 32) {
+            const int cc = hc < rx ? hc : hc + kBlTile;
+            A[r * PA + cc] = __ldg(row + reflect_index(x_org - rx + cc, q.W));
+          }
+        }
+      }
+    } else {
+      for (int r = wrp; r < rows; r += kWarps) {
+        const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+        for (int cc = lane; cc < cols; cc += 32)
+          A[r * PA + cc] = __ldg(row + reflect_index(x_org - rx + cc, q.W));
+      }
     }
   }
   // slack elements read (and discarded) by the last slide of every task
