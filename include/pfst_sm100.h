@@ -387,7 +387,7 @@ int pfst_argmax_confusion(const float* logits, int64_t n_images, int32_t C, int6
  * in/out: (n_images, C, H, W) fp32, out != in. ksize_*: odd, ksize/2 < size (reflect).
  * sigma_host: HOST array of n_images floats (one sigma per image, both axes, as the call
  * site draws them); it is copied into the launch parameters, so the call is asynchronous
- * and needs no staging buffer. Taps below 2^-40 of the centre weight are not evaluated.   */
+ * and needs no staging buffer. Taps below 2^-30 of the centre weight are not evaluated.   */
 int pfst_gaussian_blur(const float* in, float* out, int64_t n_images, int32_t C, int32_t H,
                        int32_t W, int32_t ksize_y, int32_t ksize_x, const float* sigma_host,
                        void* stream);

@@ -11,10 +11,10 @@
 //
 // Exactness notes:
 //   * the weights are normalised by the sum over ALL k taps, like kornia;
-//   * taps whose weight is below 2^-40 of the centre tap (|x| > 7.4465 sigma) are skipped: their
-//     total contribution (< 1e-10 relative) is far below one fp32 rounding of the sum, and for
+//   * taps whose weight is below 2^-30 of the centre tap (|x| > 6.449 sigma) are skipped: their
+//     total contribution (< 3e-9 relative) is a twentieth of one fp32 rounding of the sum, and for
 //     |x| > 14.4 sigma kornia's own fp32 weights are exactly zero. For the reference's sigma
-//     range that leaves <= 17 of the 51 taps;
+//     range that leaves <= 15 of the 51 taps;
 //   * accumulation is fp32 FMA in tap order, horizontal pass first (kornia's separable order).
 //
 // Tiling: a block owns a 64x64 output tile of one (image, channel) plane. The tile plus its
@@ -32,8 +32,8 @@ constexpr int kBlTile = 64;        // output tile edge
 constexpr int kBlOut = 8;          // outputs per thread and task
 constexpr int kBlMaxImages = 64;   // sigmas carried in the launch parameters
 constexpr int kBlMaxTaps = 2 * 80 + 1;
-// taps with |x| > kBlCutoff * sigma weigh less than 2^-40 of the centre tap: sqrt(2 * 40 * ln 2)
-constexpr float kBlCutoff = 7.4465948f;
+// taps with |x| > kBlCutoff * sigma weigh less than 2^-30 of the centre tap: sqrt(2 * 30 * ln 2)
+constexpr float kBlCutoff = 6.4489403f;
 
 struct BlurParams {
   const float* in;
@@ -49,6 +49,11 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
   return min(max(i, 0), n - 1);   // only out-of-tile (masked) positions can still be outside
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 // Normalised weights of the taps |x| <= r of a k-tap Gaussian (one warp).
@@ -121,64 +126,45 @@ gaussian_blur_kernel(const BlurParams q) {
   if (tid < 32) blur_weights(wx, q.kx, rxi, sigma);
   else if (tid < 64) blur_weights(wy, q.ky, ryi, sigma);
 
-  // stage the tile and its halo (reflect border). One warp per row: the row index is reflected
-  // once, the 64 interior columns are one aligned 64-bit load per lane and the 2*rx halo columns one
-  // scalar load per lane — ~10 instructions per row and thread (a flat element loop spends ~45
-  // integer instructions per element on division, two reflections and 64-bit addressing, which
-  // made the staging, not the convolution, the bulk of the kernel).
+  // stage the tile and its halo (reflect border) with 4-byte cp.async copies: global -> shared
+  // without a register round trip, every row of the tile in flight at once, ONE wait per block.
+  // One warp per row: the row index is reflected once, a lane copies two interior columns and one
+  // of the first 32 halo columns (their reflected x is row-invariant) — ~18 instructions per row
+  // and thread. (A flat element loop spends ~45 integer instructions per element on a division,
+  // two reflections and 64-bit addressing, which made the staging the bulk of the kernel; register
+  // staging pays one DRAM latency per batch of rows.)
   {
     const int lane = tid & 31, wrp = tid >> 5;
-    constexpr int kWarps = kBlThreads / 32, kRows = 4;   // rows in flight per warp
-    const bool fast = (q.W % 2 == 0) && (x_org + kBlTile <= q.W) &&
-                      ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+    constexpr int kWarps = kBlThreads / 32;
+    const bool fast = x_org + kBlTile <= q.W;
     if (fast) {
-      // halo column of this lane (first 32 halo columns; wider halos loop below)
       const int hc0 = lane < rx ? lane : lane + kBlTile;        // left halo [0,rx), right [rx+64, cols)
       const bool has_h = lane < 2 * rx;
       const int gxh = reflect_index(x_org - rx + hc0, q.W);
-      for (int r0 = wrp; r0 < rows; r0 += kWarps * kRows) {
-        float2 v[kRows];
-        float hv[kRows];
-#pragma unroll
-        for (int j = 0; j < kRows; ++j) {
-          const int r = r0 + j * kWarps;
-          if (r < rows) {
-            const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
-            v[j] = __ldg(reinterpret_cast<const float2*>(row + x_org) + lane);
-            hv[j] = has_h ? __ldg(row + gxh) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < kRows; ++j) {
-          const int r = r0 + j * kWarps;
-          if (r < rows) {
-            float* a = A + r * PA;
-            a[rx + 2 * lane] = v[j].x;
-            a[rx + 2 * lane + 1] = v[j].y;
-            if (has_h) a[hc0] = hv[j];
-          }
-        }
-      }
-      if (2 * rx > 32) {   // wide kernels: the rest of the halo, element by element
-        for (int r = wrp; r < rows; r += kWarps) {
-          const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
-          for (int hc = 32 + lane; hc < 2 * rx; hc += 32) {
-            const int cc = hc < rx ? hc : hc + kBlTile;
-            A[r * PA + cc] = __ldg(row + reflect_index(x_org - rx + cc, q.W));
-          }
+      for (int r = wrp; r < rows; r += kWarps) {
+        const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+        float* a = A + r * PA;
+        cp_async4(a + rx + lane, row + x_org + lane);
+        cp_async4(a + rx + 32 + lane, row + x_org + 32 + lane);
+        if (has_h) cp_async4(a + hc0, row + gxh);
+        for (int hc = 32 + lane; hc < 2 * rx; hc += 32) {       // wide kernels only
+          const int cc = hc < rx ? hc : hc + kBlTile;
+          cp_async4(a + cc, row + reflect_index(x_org - rx + cc, q.W));
         }
       }
     } else {
       for (int r = wrp; r < rows; r += kWarps) {
         const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
         for (int cc = lane; cc < cols; cc += 32)
-          A[r * PA + cc] = __ldg(row + reflect_index(x_org - rx + cc, q.W));
+          cp_async4(A + r * PA + cc, row + reflect_index(x_org - rx + cc, q.W));
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // slack elements read (and discarded) by the last slide of every task
   for (int r = tid; r < rows; r += kBlThreads) A[r * PA + cols] = 0.f;
   for (int i = tid; i < PB; i += kBlThreads) Bm[rows * PB + i] = 0.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // horizontal pass: task = (row, 8-column chunk); lanes of a warp take consecutive rows
@@ -219,7 +205,7 @@ static size_t blur_smem_bytes(int ry, int rx) {
   return ((size_t)rows * PA + 8 + (size_t)(rows + 1) * (kBlTile + 1)) * sizeof(float);
 }
 
-// taps with |x| <= r are evaluated: weights below 2^-40 of the centre are dropped
+// taps with |x| <= r are evaluated: weights below 2^-30 of the centre are dropped
 static int blur_radius(int k, float sigma_max) {
   const int half = k / 2;
   const double r = floor((double)kBlCutoff * (double)sigma_max) + 1.0;   // >= the kernel's per-image floorf

@@ -52,7 +52,7 @@ def test_blur_reference_sigma_range_and_image_statistics(cuda):
 
 
 def test_blur_cfg2_batch_at_the_largest_reference_sigma(cuda):
-    # B=8 x 512^2, sigma at the top of the reference's range: 19 of 51 taps, ~49 KB of shared memory
+    # B=8 x 512^2, sigma at the top of the reference range: 15 of 51 taps, ~45 KB of shared memory
     # (the size at which the launch needs the opt-in above the 48 KB default)
     g = torch.Generator().manual_seed(8)
     x = torch.randn((8, 3, 512, 512), generator=g)
@@ -65,7 +65,7 @@ def test_blur_cfg2_batch_at_the_largest_reference_sigma(cuda):
 
 
 def test_blur_wide_sigma_uses_every_tap(cuda):
-    # sigma large against the kernel: no tap is below the 2^-40 cut-off, reflect border fully used
+    # sigma large against the kernel: no tap is below the 2^-30 cut-off, reflect border fully used
     g = torch.Generator().manual_seed(4)
     x = torch.randn((2, 3, 96, 80), generator=g)
     _check(cuda, x, [3.0, 10.0], ksize=(21, 31))
