@@ -32,6 +32,7 @@ constexpr int kBlTile = 64;        // output tile edge
 constexpr int kBlOut = 8;          // outputs per thread and task
 constexpr int kBlMaxImages = 64;   // sigmas carried in the launch parameters
 constexpr int kBlMaxTaps = 2 * 80 + 1;
+constexpr int kBlSlack = 4;        // finite values behind every staged row / column (see blur_slide)
 // taps with |x| > kBlCutoff * sigma weigh less than 2^-30 of the centre tap: sqrt(2 * 30 * ln 2)
 constexpr float kBlCutoff = 6.4489403f;
 
@@ -51,12 +52,12 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
   return min(max(i, 0), n - 1);   // only out-of-tile (masked) positions can still be outside
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-// Normalised weights of the taps |x| <= r of a k-tap Gaussian (one warp).
+// Normalised weights of the taps |x| <= r of a k-tap Gaussian, zero-padded to a multiple of four
+// taps (one warp).
 __device__ __forceinline__ void blur_weights(float* w, int k, int r, float sigma) {
   const int lane = threadIdx.x & 31;
   const float inv = 1.0f / (2.0f * sigma * sigma);
@@ -67,46 +68,57 @@ __device__ __forceinline__ void blur_weights(float* w, int k, int r, float sigma
     part += expf(-(x * x) * inv);
   }
   const float total = warp_sum(part);
-  for (int t = lane; t <= 2 * r; t += 32) {
+  const int taps = 2 * r + 1, taps4 = (taps + 3) & ~3;
+  for (int t = lane; t < taps4; t += 32) {
     const float x = (float)(t - r);
-    w[t] = expf(-(x * x) * inv) / total;
+    w[t] = t < taps ? expf(-(x * x) * inv) / total : 0.f;
   }
 }
 
-// acc[j] = sum_t w[t] * p[(j + t) * stride], j < 8, with an 8-value register window
+// acc[j] = sum_t w[t] * p[(j + t) * stride], j < 8, four taps per iteration over a register window
+// of 8 + 4 values (taps4 is a multiple of four, the padding weights are zero; the window reads up
+// to four finite slack values behind the last real one).
 template <int STRIDE_IS_ONE>
 __device__ __forceinline__ void blur_slide(const float* __restrict__ p, int stride, const float* __restrict__ w,
-                                           int taps, float (&acc)[kBlOut]) {
-  float win[kBlOut];
+                                           int taps4, float (&acc)[kBlOut]) {
+  const int st = STRIDE_IS_ONE ? 1 : stride;
+  float ext[kBlOut + 4];
 #pragma unroll
   for (int j = 0; j < kBlOut; ++j) {
     acc[j] = 0.f;
-    win[j] = p[STRIDE_IS_ONE ? j : j * stride];
+    ext[j] = p[j * st];
   }
-  const float* nxt = p + (STRIDE_IS_ONE ? kBlOut : kBlOut * stride);
-#pragma unroll 8
-  for (int t = 0; t < taps; ++t) {
-    const float wt = w[t];
+  const float* nxt = p + kBlOut * st;
+#pragma unroll 2
+  for (int t = 0; t < taps4; t += 4) {
+    const float4 wt = *reinterpret_cast<const float4*>(w + t);
 #pragma unroll
-    for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt, win[j], acc[j]);
+    for (int k = 0; k < 4; ++k) ext[kBlOut + k] = nxt[k * st];
+    nxt += 4 * st;
 #pragma unroll
-    for (int j = 0; j < kBlOut - 1; ++j) win[j] = win[j + 1];
-    win[kBlOut - 1] = *nxt;           // one element of slack behind every row / column (see smem sizing)
-    nxt += STRIDE_IS_ONE ? 1 : stride;
+    for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt.x, ext[j], acc[j]);
+#pragma unroll
+    for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt.y, ext[j + 1], acc[j]);
+#pragma unroll
+    for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt.z, ext[j + 2], acc[j]);
+#pragma unroll
+    for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt.w, ext[j + 3], acc[j]);
+#pragma unroll
+    for (int j = 0; j < kBlOut; ++j) ext[j] = ext[j + 4];
   }
 }
 
 __global__ void __launch_bounds__(kBlThreads)
 gaussian_blur_kernel(const BlurParams q) {
   extern __shared__ __align__(16) float bl_smem[];
-  __shared__ float wy[kBlMaxTaps], wx[kBlMaxTaps];
+  __shared__ __align__(16) float wy[kBlMaxTaps + 3], wx[kBlMaxTaps + 3];
   const int tid = threadIdx.x;
   const int rx = q.rx, ry = q.ry;
   const int cols = kBlTile + 2 * rx, rows = kBlTile + 2 * ry;
-  const int PA = (cols + 1) | 1;        // odd pitches: conflict-free row walks; >= cols + 1 (slack)
+  const int PA = (cols + kBlSlack) | 1; // odd pitches: conflict-free row walks; >= cols + slack
   constexpr int PB = kBlTile + 1;
   float* A = bl_smem;                   // rows x PA  input tile + halo
-  float* Bm = bl_smem + rows * PA + 8;  // (rows + 1) x PB  horizontally blurred (+ slack row)
+  float* Bm = bl_smem + rows * PA + 8;  // (rows + slack) x PB  horizontally blurred
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -136,34 +148,45 @@ gaussian_blur_kernel(const BlurParams q) {
   {
     const int lane = tid & 31, wrp = tid >> 5;
     constexpr int kWarps = kBlThreads / 32;
+    const unsigned As = (unsigned)__cvta_generic_to_shared(A);
     const bool fast = x_org + kBlTile <= q.W;
     if (fast) {
       const int hc0 = lane < rx ? lane : lane + kBlTile;        // left halo [0,rx), right [rx+64, cols)
       const bool has_h = lane < 2 * rx;
       const int gxh = reflect_index(x_org - rx + hc0, q.W);
+      const unsigned o0 = 4u * (unsigned)(rx + lane), oh = 4u * (unsigned)hc0;
+      const float* __restrict__ in0 = src + x_org + lane;
+      const float* __restrict__ inh = src + gxh;
+#pragma unroll 2
       for (int r = wrp; r < rows; r += kWarps) {
-        const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
-        float* a = A + r * PA;
-        cp_async4(a + rx + lane, row + x_org + lane);
-        cp_async4(a + rx + 32 + lane, row + x_org + 32 + lane);
-        if (has_h) cp_async4(a + hc0, row + gxh);
-        for (int hc = 32 + lane; hc < 2 * rx; hc += 32) {       // wide kernels only
-          const int cc = hc < rx ? hc : hc + kBlTile;
-          cp_async4(a + cc, row + reflect_index(x_org - rx + cc, q.W));
+        const int64_t goff = (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+        const unsigned a = As + 4u * (unsigned)(r * PA);
+        cp_async4(a + o0, in0 + goff);
+        cp_async4(a + o0 + 128u, in0 + goff + 32);
+        if (has_h) cp_async4(a + oh, inh + goff);
+      }
+      if (2 * rx > 32) {   // wide kernels: the rest of the halo, element by element
+        for (int r = wrp; r < rows; r += kWarps) {
+          const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
+          for (int hc = 32 + lane; hc < 2 * rx; hc += 32) {
+            const int cc = hc < rx ? hc : hc + kBlTile;
+            cp_async4(As + 4u * (unsigned)(r * PA + cc), row + reflect_index(x_org - rx + cc, q.W));
+          }
         }
       }
     } else {
       for (int r = wrp; r < rows; r += kWarps) {
         const float* __restrict__ row = src + (int64_t)reflect_index(y_org - ry + r, q.H) * q.W;
         for (int cc = lane; cc < cols; cc += 32)
-          cp_async4(A + r * PA + cc, row + reflect_index(x_org - rx + cc, q.W));
+          cp_async4(As + 4u * (unsigned)(r * PA + cc), row + reflect_index(x_org - rx + cc, q.W));
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  // slack elements read (and discarded) by the last slide of every task
-  for (int r = tid; r < rows; r += kBlThreads) A[r * PA + cols] = 0.f;
-  for (int i = tid; i < PB; i += kBlThreads) Bm[rows * PB + i] = 0.f;
+  // zero slack behind every row of A and below Bm: read by the last slide of a task, multiplied by
+  // the zero padding weights (must be finite)
+  for (int i = tid; i < rows * kBlSlack; i += kBlThreads) A[(i / kBlSlack) * PA + cols + (i % kBlSlack)] = 0.f;
+  for (int i = tid; i < kBlSlack * PB; i += kBlThreads) Bm[rows * PB + i] = 0.f;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -173,7 +196,7 @@ gaussian_blur_kernel(const BlurParams q) {
     for (int t = tid; t < tasks; t += kBlThreads) {
       const int chunk = t / rows, r = t - chunk * rows;
       float acc[kBlOut];
-      blur_slide<1>(A + r * PA + chunk * kBlOut + (rx - rxi), 1, wx, 2 * rxi + 1, acc);
+      blur_slide<1>(A + r * PA + chunk * kBlOut + (rx - rxi), 1, wx, (2 * rxi + 4) & ~3, acc);
 #pragma unroll
       for (int j = 0; j < kBlOut; ++j) Bm[r * PB + chunk * kBlOut + j] = acc[j];
     }
@@ -186,7 +209,7 @@ gaussian_blur_kernel(const BlurParams q) {
     for (int t = tid; t < tasks; t += kBlThreads) {
       const int chunk = t / kBlTile, cc = t - chunk * kBlTile;
       float acc[kBlOut];
-      blur_slide<0>(Bm + (chunk * kBlOut + (ry - ryi)) * PB + cc, PB, wy, 2 * ryi + 1, acc);
+      blur_slide<0>(Bm + (chunk * kBlOut + (ry - ryi)) * PB + cc, PB, wy, (2 * ryi + 4) & ~3, acc);
       const int gx = x_org + cc;
       if (gx < q.W) {
 #pragma unroll
@@ -201,8 +224,8 @@ gaussian_blur_kernel(const BlurParams q) {
 
 static size_t blur_smem_bytes(int ry, int rx) {
   const int cols = kBlTile + 2 * rx, rows = kBlTile + 2 * ry;
-  const int PA = (cols + 1) | 1;
-  return ((size_t)rows * PA + 8 + (size_t)(rows + 1) * (kBlTile + 1)) * sizeof(float);
+  const int PA = (cols + kBlSlack) | 1;
+  return ((size_t)rows * PA + 8 + (size_t)(rows + kBlSlack) * (kBlTile + 1)) * sizeof(float);
 }
 
 // taps with |x| <= r are evaluated: weights below 2^-30 of the centre are dropped
