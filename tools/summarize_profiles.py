@@ -2,6 +2,7 @@
 gpurun_out/<tag>_step_full.ncu-rep (ncu --set full) into the tracked summaries under profiles/.
 
     python tools/summarize_profiles.py <tag> <out-name>
+    python tools/summarize_profiles.py --rep <file.ncu-rep> <out-name>     # any --set full capture; leaves traffic.json alone
 """
 import csv
 import io
@@ -12,7 +13,11 @@ from collections import defaultdict
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-tag, out = sys.argv[1], sys.argv[2]
+only_rep = None
+if sys.argv[1] == "--rep":
+    only_rep, tag, out = Path(sys.argv[2]), "", sys.argv[3]
+else:
+    tag, out = sys.argv[1], sys.argv[2]
 src = ROOT / "gpurun_out"
 dst = ROOT / "profiles"
 dst.mkdir(exist_ok=True)
@@ -24,12 +29,14 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct",
         "smsp__average_warp_latency_issue_stalled_short_scoreboard.pct",
         "smsp__average_warp_latency_issue_stalled_barrier.pct",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor"]
 
 for lc, suffix, title in ((src / f"{tag}_bench_launches.csv", "bench_launches",
                            "python bench.py --steps 2 --warmup 3 --no-cpu-baseline (device leg, then the e2e leg)"),
                           (src / f"{tag}_launches.csv", "launches", "tools/one_step.py cfg2 2 (eager launches of two steps)")):
-    if not lc.exists():
+    if only_rep is not None or not lc.exists():
         continue
     lines = [l for l in lc.read_text().splitlines() if l.startswith('"')]
     rows = list(csv.DictReader(io.StringIO("\n".join(lines))))
@@ -46,7 +53,7 @@ for lc, suffix, title in ((src / f"{tag}_bench_launches.csv", "bench_launches",
     (dst / f"{out}_{suffix}.csv").write_text("\n".join(lines) + "\n")
     print("\n".join(md))
 
-rep = src / f"{tag}_step_full.ncu-rep"
+rep = only_rep or src / f"{tag}_step_full.ncu-rep"
 if rep.exists():
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -70,6 +77,9 @@ if rep.exists():
         except (KeyError, ValueError):
             pass
     (dst / f"{out}_full_summary.json").write_text(json.dumps({"units": dict(zip(hdr, rows[1])), "kernels": table}, indent=1))
-    (dst / "traffic.json").write_text(json.dumps(traffic, indent=1))
+    if only_rep is None:
+        (dst / "traffic.json").write_text(json.dumps(traffic, indent=1))
+    else:
+        (dst / f"{out}_traffic.json").write_text(json.dumps(traffic, indent=1))
     for rec in table:
         print(rec)
