@@ -22,3 +22,9 @@ python tools/one_step.py cfg2 1 > gpurun_out/${tag}_one_step.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:kernel \
     -o gpurun_out/${tag}_step_full python tools/one_step.py cfg2 1 > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+python tools/eval_sweep.py --mode labels > gpurun_out/${tag}_eval_sweep.jsonl 2>&1; python tools/eval_sweep.py --mode logits --maps 1250 >> gpurun_out/${tag}_eval_sweep.jsonl 2>&1
+echo "eval sweep rc=$?"
+python tools/ncu_new.py > gpurun_out/${tag}_ncu_new.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"gaussian_blur|argmax_confusion" --launch-skip 2 -c 2 \
+    -o gpurun_out/${tag}_new_kernels python tools/ncu_new.py > gpurun_out/${tag}_ncu_new_full.log 2>&1
+echo "ncu new kernels rc=$?"
