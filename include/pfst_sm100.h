@@ -392,6 +392,24 @@ int pfst_gaussian_blur(const float* in, float* out, int64_t n_images, int32_t C,
                        int32_t W, int32_t ksize_y, int32_t ksize_x, const float* sigma_host,
                        void* stream);
 
+/* ---- strong augmentation: photometric distortion of uint8 images ------
+ * Replaces StrongAugmentation.__call__, rsiseg/datasets/pipelines/transforms.py:1062-1145
+ * (brightness / contrast = convert(alpha, beta), saturation and hue through mmcv.bgr2hsv /
+ * hsv2bgr = cv2.cvtColor on uint8), given the distortions the host drew: for image i the ops
+ * op_codes_host[4 i + k], k = 0..3, are applied in order (0 = none) with parameters
+ * op_params_host[2 (4 i + k) + {0, 1}] = (alpha, beta) for PFST_SA_CONVERT, (alpha, -) for
+ * PFST_SA_SATURATION, (integer hue delta, -) for PFST_SA_HUE. in/out: (n_images, H, W, 3) uint8
+ * BGR, HWC as the pipeline holds them; in == out is allowed. Both HOST arrays are copied into the
+ * launch parameters (asynchronous, no staging buffer). Results are bit-identical to OpenCV 4.13's
+ * uint8 conversions, including its layout dependence: HSV->BGR truncates inside the simd_width-pixel
+ * blocks of a row and rounds in the row's tail (simd_width = 32 on AVX2 hosts; 0 = no tail).     */
+#define PFST_SA_CONVERT 1
+#define PFST_SA_SATURATION 2
+#define PFST_SA_HUE 3
+int pfst_photometric_u8(const uint8_t* in, uint8_t* out, int64_t n_images, int32_t H, int32_t W,
+                        const int32_t* op_codes_host, const float* op_params_host,
+                        int32_t simd_width, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,122 @@ def gaussian_blur(blur: float, data: torch.Tensor, rng=np.random, dtype=None):
     sigma = draw_sigma(rng)
     ks = (kernel_size(data.shape[2]), kernel_size(data.shape[3]))
     return gaussian_blur2d(data, ks, (sigma, sigma), dtype), sigma
+
+
+# --------------------------------------------------------------------------------------------
+# StrongAugmentation — the data-pipeline photometric distortion that produces
+# `target_img_strong_aug` (rsiseg/datasets/pipelines/transforms.py:1062-1145, used by every shipped
+# dataset config, e.g. configs/_base_/datasets/pots_irrg2vaih_irrg.py:39).
+#
+# The class's own arithmetic (`convert`, the hue shift, the draw order) is restated from the
+# reference lines. Its colour-space conversions are `mmcv.bgr2hsv` / `mmcv.hsv2bgr`, i.e.
+# `cv2.cvtColor(img, cv2.COLOR_BGR2HSV / COLOR_HSV2BGR)` on uint8 images — third-party code that is
+# not under /root/reference and not version-pinned by it, but IS installed in this image
+# (opencv-python 4.13.0): the two restatements below are PINNED bit-exactly against it over all
+# 2^24 BGR triples and all 180*256*256 HSV triples (tests/test_oracle_pins.py), and the whole class
+# against the reference class compiled from its source with cv2 standing in for mmcv.
+#
+# What the brute force established about cv2 4.13 (x86-64, AVX2 dispatch), uint8 images:
+#   * BGR->HSV is OpenCV's integer algorithm (12-bit fixed-point division tables), layout-free;
+#   * HSV->BGR is computed in fp32: s,v scaled by 1/255, h by 6/180, sector = floor(h),
+#     tab = {v, v*(1-s), v*fma(-s,f,1), v*fma(-s,1-f,1)}, result*255 converted to uint8 by
+#     TRUNCATION inside the 32-pixel SIMD blocks of a row and by ROUND-HALF-EVEN in the scalar tail
+#     (the last W % 32 pixels of every row). The rule is part of the observable behaviour of the
+#     reference on such a host; `simd` below is that block width (0 = whole rows vectorised).
+_HSV_SHIFT = 12
+_SDIV = np.zeros(256, np.int64)
+_HDIV = np.zeros(256, np.int64)
+for _i in range(1, 256):
+    _SDIV[_i] = int(np.rint((255 << _HSV_SHIFT) / (1.0 * _i)))
+    _HDIV[_i] = int(np.rint((180 << _HSV_SHIFT) / (6.0 * _i)))
+_SECTOR = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+
+
+def bgr2hsv_u8(img: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(img, cv2.COLOR_BGR2HSV) for uint8 (...,3) images (H in [0,180))."""
+    b, g, r = (img[..., k].astype(np.int64) for k in range(3))
+    v = np.maximum(np.maximum(b, g), r)
+    diff = v - np.minimum(np.minimum(b, g), r)
+    vr = np.where(v == r, -1, 0)
+    vg = np.where(v == g, -1, 0)
+    s = (diff * _SDIV[v] + (1 << (_HSV_SHIFT - 1))) >> _HSV_SHIFT
+    h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))))
+    h = (h * _HDIV[diff] + (1 << (_HSV_SHIFT - 1))) >> _HSV_SHIFT
+    h = h + np.where(h < 0, 180, 0)
+    return np.stack([h, s, v], -1).astype(np.uint8)
+
+
+def _fma32(a, b, c):
+    # fused multiply-add of float32 operands: the product is exact in float64
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def hsv2bgr_u8(hsv: np.ndarray, simd: int = 32) -> np.ndarray:
+    """cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR) for uint8 (H,W,3) images with H < 180."""
+    f32 = np.float32
+    h = hsv[..., 0].astype(f32) * f32(6.0 / 180.0)
+    s = hsv[..., 1].astype(f32) * f32(1.0 / 255.0)
+    v = hsv[..., 2].astype(f32) * f32(1.0 / 255.0)
+    sector = np.floor(h).astype(np.int64)
+    fr = h - sector.astype(f32)
+    one = f32(1.0)
+    tab = np.stack([v, v * (one - s), v * _fma32(-s, fr, one), v * _fma32(-s, one - fr, one)], -1)
+    bgr = np.take_along_axis(tab, _SECTOR[np.clip(sector, 0, 5)], -1)
+    bgr = np.where((hsv[..., 1] == 0)[..., None], v[..., None], bgr) * f32(255.0)
+    W = hsv.shape[-2]
+    tail = np.arange(W) >= (W - W % simd if simd else W)           # scalar-tail columns of every row
+    out = np.where(tail[:, None], np.rint(bgr), np.trunc(bgr))
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def convert_u8(img: np.ndarray, alpha=1, beta=0) -> np.ndarray:
+    """StrongAugmentation.convert, transforms.py:1075-1079."""
+    img = img.astype(np.float32) * alpha + beta
+    img = np.clip(img, 0, 255)
+    return img.astype(np.uint8)
+
+
+# op codes shared with the CUDA kernel: (code, p0, p1)
+OP_CONVERT, OP_SATURATION, OP_HUE = 1, 2, 3
+
+
+def draw_strong_aug(rng=np.random, brightness_delta=32, contrast_range=(0.5, 1.5),
+                    saturation_range=(0.5, 1.5), hue_delta=18):
+    """The random draws of StrongAugmentation.__call__ in the reference's order
+    (transforms.py:1081-1141) -> list of (code, p0, p1) in application order."""
+    ops = []
+
+    def contrast():
+        if rng.randint(2):
+            ops.append((OP_CONVERT, rng.uniform(contrast_range[0], contrast_range[1]), 0))
+
+    if rng.randint(2):                                                     # brightness :1081-1089
+        ops.append((OP_CONVERT, 1, rng.uniform(-brightness_delta, brightness_delta)))
+    mode = rng.randint(2)                                                  # :1133
+    if mode == 1:
+        contrast()
+    if rng.randint(2):                                                     # saturation :1100-1110
+        ops.append((OP_SATURATION, rng.uniform(saturation_range[0], saturation_range[1]), 0))
+    if rng.randint(2):                                                     # hue :1112-1121
+        ops.append((OP_HUE, rng.randint(-hue_delta, hue_delta), 0))
+    if mode == 0:
+        contrast()
+    return ops
+
+
+def apply_strong_aug(img: np.ndarray, ops, simd: int = 32) -> np.ndarray:
+    """Applies the drawn distortions to a uint8 (H,W,3) BGR image, step by step as the reference."""
+    for code, p0, p1 in ops:
+        if code == OP_CONVERT:
+            img = convert_u8(img, alpha=p0, beta=p1)
+        elif code == OP_SATURATION:
+            hsv = bgr2hsv_u8(img)
+            hsv[:, :, 1] = convert_u8(hsv[:, :, 1], alpha=p0)
+            img = hsv2bgr_u8(hsv, simd)
+        elif code == OP_HUE:
+            hsv = bgr2hsv_u8(img)
+            hsv[:, :, 0] = (hsv[:, :, 0].astype(int) + int(p0)) % 180
+            img = hsv2bgr_u8(hsv, simd)
+        else:
+            raise ValueError(code)
+    return img

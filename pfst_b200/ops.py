@@ -287,6 +287,42 @@ def argmax_confusion(seg_logits: torch.Tensor, label: Optional[torch.Tensor], nu
     return conf, pred
 
 
+# ------------------------------------- strong augmentation: photometric distortion (uint8)
+SA_CONVERT, SA_SATURATION, SA_HUE = 1, 2, 3
+SA_MAX_OPS = 4
+
+
+def photometric_u8(imgs: torch.Tensor, op_lists: Sequence[Sequence[tuple]], simd: int = 32,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """StrongAugmentation's distortions (transforms.py:1075-1141) on uint8 BGR images (N,H,W,3), one
+    launch. op_lists[i] = up to four (code, p0, p1) in application order: (SA_CONVERT, alpha, beta),
+    (SA_SATURATION, alpha, _), (SA_HUE, integer delta, _). Bit-identical to the reference's
+    numpy + cv2 arithmetic (simd = SIMD block width of cv2's HSV->BGR on the reference host)."""
+    _dev(imgs, "imgs", torch.uint8)
+    if imgs.dim() != 4 or imgs.shape[3] != 3:
+        raise ValueError("imgs must be (N,H,W,3) uint8")
+    N, H, W, _ = imgs.shape
+    if len(op_lists) != N:
+        raise ValueError(f"need one op list per image ({N}), got {len(op_lists)}")
+    codes = (C.c_int32 * max(N * SA_MAX_OPS, 1))()
+    params = (C.c_float * max(2 * N * SA_MAX_OPS, 1))()
+    for i, ol in enumerate(op_lists):
+        if len(ol) > SA_MAX_OPS:
+            raise ValueError("at most four distortions per image")
+        for k, (code, p0, p1) in enumerate(ol):
+            j = i * SA_MAX_OPS + k
+            codes[j] = int(code)
+            params[2 * j] = float(p0)      # c_float rounds to float32 exactly like numpy's weak-scalar cast
+            params[2 * j + 1] = float(p1)
+    if out is None:
+        out = torch.empty_like(imgs)
+    elif out.shape != imgs.shape:
+        raise ValueError("out must have the shape of imgs")
+    _lib.call("pfst_photometric_u8", imgs.data_ptr(), _dev(out, "out", torch.uint8), N, H, W, codes, params,
+              int(simd), _stream())
+    return out
+
+
 # --------------------------------------------- strong augmentation: Gaussian blur
 def blur_kernel_size(n: int) -> int:
     """dacs_transforms.py:94-101: int(floor(ceil(0.1 n) - 0.5 + ceil(0.1 n) % 2)) (always odd)."""

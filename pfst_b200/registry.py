@@ -45,6 +45,7 @@ MODELS = Registry("models")
 UDA = MODELS
 LOSSES = MODELS
 SEGMENTORS = MODELS
+PIPELINES = Registry("pipeline")       # rsiseg/datasets/builder.py: PIPELINES = Registry('pipeline')
 
 
 def build_loss(cfg):

@@ -269,7 +269,32 @@ def gen_eval_logits():
     np.savez_compressed(OUT / "eval_logits.npz", **out)
 
 
+def strong_aug_cases():
+    """(seed, H, W): image = RandomState(seed).randint(0, 256, (H, W, 3)), draws from np.random.seed(seed + 1000)"""
+    return [(s, *[(40, 52), (33, 47), (24, 96), (17, 120), (8, 31), (64, 64)][s % 6]) for s in range(24)]
+
+
+def strong_aug_image(seed, H, W):
+    return np.random.RandomState(seed).randint(0, 256, (H, W, 3)).astype(np.uint8)
+
+
+def gen_strong_aug():
+    """The reference's StrongAugmentation class (compiled from its source, cv2 standing in for
+    mmcv.bgr2hsv/hsv2bgr exactly as mmcv defines them) on seeded random uint8 images."""
+    aug = R.strong_augmentation_cls()()
+    out = {}
+    for seed, H, W in strong_aug_cases():
+        np.random.seed(seed + 1000)
+        res = aug(dict(img=strong_aug_image(seed, H, W), img_fields=['img']))
+        out[f"out_{seed}"] = res['img_strong_aug']
+        out[f"next_{seed}"] = np.array(np.random.random())        # stream position after the draws
+    np.savez_compressed(OUT / "strong_aug.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "strong_aug":
+        gen_strong_aug()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "weighted_ce":
         gen_weighted_ce()
         sys.exit(0)
@@ -279,7 +304,7 @@ if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits):
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug):
         fn()
         print("wrote", fn.__name__)
     for p in sorted(OUT.glob("*.npz")):

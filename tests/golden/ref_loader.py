@@ -162,6 +162,26 @@ def simple_test_on_logits(seg_logits):
     return seg_pred
 
 
+def strong_augmentation_cls():
+    """-> the reference's StrongAugmentation class compiled straight from its source
+    (rsiseg/datasets/pipelines/transforms.py:1061-1155; the module imports mmcv and skimage).
+    `mmcv.bgr2hsv` / `mmcv.hsv2bgr` are what mmcv defines them as: cv2.cvtColor with
+    COLOR_BGR2HSV / COLOR_HSV2BGR (mmcv/image/colorspace.py convert_color_factory)."""
+    if "strongaug" not in _cache:
+        import ast
+        import cv2
+        import numpy as np
+        tree = ast.parse((REF_ROOT / "rsiseg/datasets/pipelines/transforms.py").read_text())
+        cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "StrongAugmentation")
+        cls.decorator_list = []
+        mmcv = types.SimpleNamespace(bgr2hsv=lambda img: cv2.cvtColor(img, cv2.COLOR_BGR2HSV),
+                                     hsv2bgr=lambda img: cv2.cvtColor(img, cv2.COLOR_HSV2BGR))
+        ns = {"np": np, "random": np.random, "mmcv": mmcv}       # transforms.py:4 `from numpy import random`
+        exec(compile(ast.Module(body=[cls], type_ignores=[]), "ref:transforms.py:StrongAugmentation", "exec"), ns)
+        _cache["strongaug"] = ns["StrongAugmentation"]
+    return _cache["strongaug"]
+
+
 class cpu_cuda_identity:
     """Context manager: make Tensor.cuda() the identity on a CUDA-less host."""
 

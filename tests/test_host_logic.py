@@ -125,3 +125,29 @@ def test_eval_logits_argument_validation_needs_no_gpu():
     from pfst_b200.evaluation import metrics as M
     with pytest.raises(PfstError):
         M.seg_argmax(z)
+
+
+def test_strong_augmentation_draws_like_the_reference_and_registers():
+    """The drop-in's draws must consume the global numpy stream exactly like
+    StrongAugmentation.__call__ (transforms.py:1081-1141); no GPU needed for the draw."""
+    from oracle import strong_aug as osa
+    from pfst_b200.pipelines import StrongAugmentation
+    aug = registry.PIPELINES.build(dict(type="StrongAugmentation", hue_delta=10, contrast_range=(0.8, 1.2)))
+    assert isinstance(aug, StrongAugmentation) and "hue_delta=10" in repr(aug)
+    for seed in range(40):
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        assert aug.draw(a) == osa.draw_strong_aug(b, 32, (0.8, 1.2), (0.5, 1.5), 10)
+        assert a.random_sample() == b.random_sample()
+    if R.available():
+        pytest.importorskip("cv2")
+        ref = R.strong_augmentation_cls()(hue_delta=10, contrast_range=(0.8, 1.2))
+        img = np.zeros((4, 4, 3), np.uint8)
+        for seed in range(20):
+            np.random.seed(seed)
+            ref(dict(img=img.copy(), img_fields=[]))
+            after = np.random.random()
+            np.random.seed(seed)
+            aug.draw()
+            assert after == np.random.random()
+    with pytest.raises(PfstError):
+        ops.photometric_u8(torch.zeros((1, 4, 4, 3), dtype=torch.uint8), [[]])

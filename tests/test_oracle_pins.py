@@ -220,3 +220,64 @@ def test_eval_logits_oracle_equals_reference_live():
         got = om.pre_eval(logits, list(gt.numpy()), C, 255)
         for a, b in zip(got, want):
             assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+# ------------------------------------------------------------------ StrongAugmentation (data pipeline)
+def _cv2():
+    return pytest.importorskip("cv2")
+
+
+def test_hsv_restatements_equal_cv2_on_every_colour():
+    """mmcv.bgr2hsv / hsv2bgr are cv2.cvtColor on uint8: the oracle's two restatements must equal
+    cv2 for ALL 2^24 BGR triples and ALL 180*256*256 HSV triples, in the vectorised body of a row
+    (truncating) and in its scalar tail (rounding)."""
+    cv2 = _cv2()
+    from oracle import strong_aug as SA
+    a = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([a & 255, (a >> 8) & 255, (a >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(SA.bgr2hsv_u8(img), cv2.cvtColor(img, cv2.COLOR_BGR2HSV))
+    del img, a
+    H, S, V = np.meshgrid(np.arange(180), np.arange(256), np.arange(256), indexing="ij")
+    allhsv = np.stack([H, S, V], -1).astype(np.uint8).reshape(-1, 3)
+    for W in (256, 31):                                   # all-SIMD rows, all-tail rows
+        pad = (-allhsv.shape[0]) % W
+        hsv = np.concatenate([allhsv, np.zeros((pad, 3), np.uint8)]).reshape(-1, W, 3)
+        assert np.array_equal(SA.hsv2bgr_u8(hsv), cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)), W
+    rs = np.random.RandomState(0)
+    for W in (120, 100, 33, 7):                           # mixed rows: body + tail
+        hsv = np.stack([rs.randint(0, 180, (50, W)), rs.randint(0, 256, (50, W)), rs.randint(0, 256, (50, W))],
+                       -1).astype(np.uint8)
+        assert np.array_equal(SA.hsv2bgr_u8(hsv), cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)), W
+
+
+def test_strong_aug_oracle_vs_golden():
+    from oracle import strong_aug as SA
+    from tests.golden.make_golden import strong_aug_cases, strong_aug_image
+    z = load("strong_aug.npz")
+    n_ops = 0
+    for seed, H, W in strong_aug_cases():
+        rs = np.random.RandomState(seed + 1000)
+        ops_ = SA.draw_strong_aug(rs)
+        n_ops += len(ops_)
+        assert rs.random_sample() == float(z[f"next_{seed}"]), seed       # same stream consumption
+        assert np.array_equal(SA.apply_strong_aug(strong_aug_image(seed, H, W), ops_), z[f"out_{seed}"]), seed
+    assert n_ops >= 30
+
+
+@needs_ref
+def test_strong_aug_oracle_equals_reference_class_live():
+    _cv2()
+    from oracle import strong_aug as SA
+    aug = R.strong_augmentation_cls()(brightness_delta=20, contrast_range=(0.7, 1.3), saturation_range=(0.4, 1.6),
+                                      hue_delta=10)
+    rs = np.random.RandomState(5)
+    for it in range(60):
+        H, W = [(64, 64), (33, 47), (120, 120), (16, 100)][it % 4]
+        img = rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        np.random.seed(it)
+        ref = aug(dict(img=img.copy(), img_fields=['img']))['img_strong_aug']
+        after = np.random.random()
+        np.random.seed(it)
+        ops_ = SA.draw_strong_aug(np.random, 20, (0.7, 1.3), (0.4, 1.6), 10)
+        assert after == np.random.random()
+        assert np.array_equal(SA.apply_strong_aug(img.copy(), ops_), ref), it
