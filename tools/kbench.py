@@ -284,6 +284,21 @@ def main():
                           ("sigma 0.15 (1 tap)", [0.15] * B)):
             report("gaussian_blur " + name, 8 * 3 * P, lambda i: ops.gaussian_blur(imgs[i], sig, out=outs[i]))
         del imgs, outs
+    keep.clear()
+
+    if want("sa"):
+        # StrongAugmentation on uint8 HWC images: 3 B read + 3 B written per pixel
+        from pfst_b200.pipelines import StrongAugmentation
+        from pfst_b200 import ops as _ops
+        u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(R)]
+        o8 = [torch.empty_like(u8[0]) for _ in range(R)]
+        full = [[(_ops.SA_CONVERT, 1, 12.5), (_ops.SA_SATURATION, 1.3, 0), (_ops.SA_HUE, 9, 0),
+                 (_ops.SA_CONVERT, 1.2, 0)]] * B
+        light = [[(_ops.SA_CONVERT, 1, 12.5)]] * B
+        aug = StrongAugmentation()
+        report("photometric_u8 (all four distortions)", 6 * P, lambda i: aug.apply_batch(u8[i], full, out=o8[i]))
+        report("photometric_u8 (brightness only)", 6 * P, lambda i: aug.apply_batch(u8[i], light, out=o8[i]))
+        del u8, o8
     print(json.dumps({"peak_gbs": peak, "workload": wl.name, "graph": not args.no_graph}))
 
 
