@@ -410,6 +410,20 @@ int pfst_photometric_u8(const uint8_t* in, uint8_t* out, int64_t n_images, int32
                         const int32_t* op_codes_host, const float* op_params_host,
                         int32_t simd_width, void* stream);
 
+/* ---- strong augmentation: colour jitter of the mixed image -------------
+ * Replaces color_jitter, rsiseg/models/utils/dacs_transforms.py:56-85:
+ *   denorm_(data, mean, std); kornia.augmentation.ColorJitter(s, s, s, s)(data); renorm_(...)
+ * given the factors and the order the host drew (kornia: third-party, unpinned; 0.6-series
+ * arithmetic restated in oracle/strong_aug.py, parity unpinned). in/out: (n_images, 3, HW) fp32
+ * planar, in == out allowed. factors_host[4 i + {0,1,2,3}] = brightness, contrast, saturation, hue
+ * factor of image i; order_host[4 i + k] = k-th transform to apply (0 brightness, 1 contrast,
+ * 2 saturation, 3 hue, -1 none). denorm = 1: (x*std + mean)/255 before and (x*255 - mean)/std after
+ * (mean_host/std_host: 3 floats), 0: data already in [0,1]. HOST arrays travel in the launch
+ * parameters (asynchronous, no staging buffer).                                              */
+int pfst_color_jitter(const float* in, float* out, int64_t n_images, int64_t HW,
+                      const float* factors_host, const int32_t* order_host,
+                      const float* mean_host, const float* std_host, int32_t denorm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

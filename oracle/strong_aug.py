@@ -182,3 +182,121 @@ def apply_strong_aug(img: np.ndarray, ops, simd: int = 32) -> np.ndarray:
         else:
             raise ValueError(code)
     return img
+
+
+# --------------------------------------------------------------------------------------------
+# Colour jitter of the mixed image — the `color_jitter` step of strong_transform,
+# rsiseg/models/utils/dacs_transforms.py:56-85.
+#
+# PARITY UNPINNED. The reference's own lines (restated in `color_jitter` below) only decide whether
+# the jitter runs and (de)normalise the image; the sampler and the arithmetic are
+# `kornia.augmentation.ColorJitter(brightness=s, contrast=s, saturation=s, hue=s)` — third-party, not
+# under /root/reference, not installed here, not version-pinned by the reference. What follows
+# restates kornia's published implementation as of the 0.6 series (the releases current when the
+# reference was written; `ColorJitter` of that series = additive brightness, multiplicative contrast):
+#   generator  (kornia/augmentation/random_generator/_2d/color_jitter.py): factors drawn in the order
+#              brightness, contrast, hue, saturation as low + (high - low) * torch.rand(B), then
+#              order = torch.randperm(4); ranges: brightness/contrast/saturation [max(0, 1-s), 1+s]
+#              (brightness capped at 2), hue [-s, s] (capped at +-0.5);
+#   transforms (kornia/enhance/adjust.py, kornia/color/hsv.py), applied in `order`:
+#              0 brightness: clamp(x + (f - 1), 0, 1)      1 contrast: clamp(x * f, 0, 1)
+#              2 saturation: hsv, s = clamp(s * f, 0, 1)   3 hue: hsv, h = fmod(h + 2 pi f, 2 pi)
+# Whether the torch RNG stream of an actual kornia install is consumed identically is NOT
+# established; the arithmetic given the factors is what the CUDA kernel is tested against.
+import math
+
+
+def rgb_to_hsv(image: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """kornia.color.rgb_to_hsv: (...,3,H,W) in [0,1] -> h in [0, 2 pi), s, v."""
+    max_rgb, argmax_rgb = image.max(-3)
+    min_rgb = image.min(-3)[0]
+    deltac = max_rgb - min_rgb
+    v = max_rgb
+    s = deltac / (max_rgb + eps)
+    deltac = torch.where(deltac == 0, torch.ones_like(deltac), deltac)
+    rc, gc, bc = torch.unbind((max_rgb.unsqueeze(-3) - image), dim=-3)
+    h1 = bc - gc
+    h2 = (rc - bc) + 2.0 * deltac
+    h3 = (gc - rc) + 4.0 * deltac
+    h = torch.stack((h1, h2, h3), dim=-3) / deltac.unsqueeze(-3)
+    h = torch.gather(h, dim=-3, index=argmax_rgb.unsqueeze(-3)).squeeze(-3)
+    h = (h / 6.0) % 1.0
+    h = 2.0 * math.pi * h
+    return torch.stack((h, s, v), dim=-3)
+
+
+def hsv_to_rgb(image: torch.Tensor) -> torch.Tensor:
+    """kornia.color.hsv_to_rgb."""
+    h = image[..., 0, :, :] / (2 * math.pi)
+    s = image[..., 1, :, :]
+    v = image[..., 2, :, :]
+    hi = torch.floor(h * 6) % 6
+    f = ((h * 6) % 6) - hi
+    one = torch.tensor(1.0, dtype=image.dtype)
+    p = v * (one - s)
+    q = v * (one - f * s)
+    t = v * (one - (one - f) * s)
+    hi = hi.long()
+    indices = torch.stack([hi, hi + 6, hi + 12], dim=-3)
+    out = torch.stack((v, q, p, p, t, v, t, v, v, q, p, p, p, p, t, v, v, q), dim=-3)
+    return torch.gather(out, -3, indices)
+
+
+def jitter_ranges(s):
+    """kornia `_range_bound` for ColorJitter(brightness=s, contrast=s, saturation=s, hue=s) or a dict."""
+    if not isinstance(s, dict):
+        s = dict(brightness=s, contrast=s, saturation=s, hue=s)
+    b, c, sa, h = (float(s.get(k, 0.0)) for k in ("brightness", "contrast", "saturation", "hue"))
+    clamp = lambda lo, hi, a, bnd: (min(max(lo, a), bnd), min(max(hi, a), bnd))
+    return dict(brightness=clamp(1 - b, 1 + b, 0.0, 2.0), contrast=clamp(1 - c, 1 + c, 0.0, float("inf")),
+                saturation=clamp(1 - sa, 1 + sa, 0.0, float("inf")), hue=clamp(-h, h, -0.5, 0.5))
+
+
+def draw_jitter(s, batch: int = 1, generator=None):
+    """ColorJitterGenerator.forward: brightness, contrast, hue, saturation factors, then the order."""
+    r = jitter_ranges(s)
+    u = lambda lo_hi: lo_hi[0] + (lo_hi[1] - lo_hi[0]) * torch.rand((batch,), generator=generator)
+    out = dict(brightness=u(r["brightness"]), contrast=u(r["contrast"]), hue=u(r["hue"]),
+               saturation=u(r["saturation"]))
+    out["order"] = torch.randperm(4, generator=generator)
+    return out
+
+
+def apply_jitter(data: torch.Tensor, params) -> torch.Tensor:
+    """ColorJitter.apply_transform on (N,3,H,W) images in [0,1]; per-image factors, one shared order."""
+    f = lambda k: params[k].to(data.dtype).view(-1, 1, 1, 1)
+
+    def saturation(img):
+        hsv = rgb_to_hsv(img)
+        s_out = torch.clamp(hsv[:, 1:2] * f("saturation"), min=0, max=1)
+        return hsv_to_rgb(torch.cat([hsv[:, 0:1], s_out, hsv[:, 2:3]], dim=1))
+
+    def hue(img):
+        hsv = rgb_to_hsv(img)
+        h_out = torch.fmod(hsv[:, 0:1] + f("hue") * 2 * math.pi, 2 * math.pi)
+        return hsv_to_rgb(torch.cat([h_out, hsv[:, 1:2], hsv[:, 2:3]], dim=1))
+
+    transforms = [lambda img: torch.clamp(img + (f("brightness") - 1), min=0.0, max=1.0),
+                  lambda img: torch.clamp(img * f("contrast"), min=0.0, max=1.0),
+                  saturation, hue]
+    out = data
+    for idx in params["order"].tolist():
+        out = transforms[idx](out)
+    return out
+
+
+def color_jitter(color_jitter, mean, std, data=None, target=None, s=.25, p=.2, denorm_type='mean_std',
+                 generator=None):
+    """dacs_transforms.py:56-85 for one (1,3,H,W) mixed image; mean/std (1,3,1,1). -> (data, target, params)."""
+    params = None
+    if data is not None and data.shape[1] == 3 and color_jitter > p:
+        if denorm_type not in ('mean_std', 'none'):
+            raise ValueError('No such denorm type!')
+        data = data.clone()
+        if denorm_type == 'mean_std':
+            data.mul_(std).add_(mean).div_(255.0)                       # denorm_ :48-49
+        params = draw_jitter(s, data.shape[0], generator)
+        data = apply_jitter(data, params)
+        if denorm_type == 'mean_std':
+            data.mul_(255.0).sub_(mean).div_(std)                       # renorm_ :52-53
+    return data, target, params

@@ -69,6 +69,8 @@ SIGNATURES: dict[str, tuple] = {
                                        _i32, _vp]),
     "pfst_gaussian_blur": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp]),
     "pfst_photometric_u8": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f32), _i32, _vp]),
+    "pfst_color_jitter": (C.c_int, [_vp, _vp, _i64, _i64, C.POINTER(_f32), C.POINTER(_i32), C.POINTER(_f32),
+                                    C.POINTER(_f32), _i32, _vp]),
     "pfst_argmax_confusion": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _i32,
                                         _vp]),
 }

@@ -323,6 +323,42 @@ def photometric_u8(imgs: torch.Tensor, op_lists: Sequence[Sequence[tuple]], simd
     return out
 
 
+# --------------------------------------------- strong augmentation: colour jitter
+def color_jitter(data: torch.Tensor, factors: Sequence[Sequence[float]], orders: Sequence[Sequence[int]],
+                 mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """kornia ColorJitter arithmetic (0.6 series) on data (N,3,H,W) fp32 with host-drawn parameters:
+    factors[i] = (brightness, contrast, saturation, hue), orders[i] = transform indices in application
+    order (0 brightness, 1 contrast, 2 saturation, 3 hue). mean/std given: the reference's
+    denorm_/renorm_ around it (dacs_transforms.py:48-53); None: data is already in [0,1]."""
+    _dev(data, "data", torch.float32)
+    if data.dim() != 4 or data.shape[1] != 3:
+        raise ValueError("data must be (N,3,H,W)")
+    N, _, H, W = data.shape
+    if len(factors) != N or len(orders) != N:
+        raise ValueError(f"need one (factors, order) per image ({N})")
+    fa = (C.c_float * max(4 * N, 1))()
+    oa = (C.c_int32 * max(4 * N, 1))()
+    for i in range(N):
+        if len(factors[i]) != 4 or len(orders[i]) > 4:
+            raise ValueError("four factors and at most four transforms per image")
+        for k in range(4):
+            fa[4 * i + k] = float(factors[i][k])
+            oa[4 * i + k] = int(orders[i][k]) if k < len(orders[i]) else -1
+    if (mean is None) != (std is None):
+        raise ValueError("give both mean and std, or neither")
+    m = s = None
+    if mean is not None:
+        m, s = (C.c_float * 3)(*[float(x) for x in mean]), (C.c_float * 3)(*[float(x) for x in std])
+    if out is None:
+        out = torch.empty_like(data)
+    elif out.shape != data.shape:
+        raise ValueError("out must have the shape of data")
+    _lib.call("pfst_color_jitter", data.data_ptr(), _dev(out, "out", torch.float32), N, H * W, fa, oa, m, s,
+              int(mean is not None), _stream())
+    return out
+
+
 # --------------------------------------------- strong augmentation: Gaussian blur
 def blur_kernel_size(n: int) -> int:
     """dacs_transforms.py:94-101: int(floor(ceil(0.1 n) - 0.5 + ceil(0.1 n) % 2)) (always odd)."""

@@ -38,7 +38,7 @@ from .. import ops
 from .._lib import PfstError
 from ..prototypes import PrototypeBank, proto_dist_loss
 from ..registry import UDA, build_loss
-from ..utils.dacs_transforms import ClassMixPlan, gaussian_blur_batch, get_mean_std
+from ..utils.dacs_transforms import ClassMixPlan, draw_color_jitter, gaussian_blur_batch, get_mean_std
 from .uda_decorator import UDADecorator, build_model, get_module
 
 
@@ -88,7 +88,7 @@ class PFGST(UDADecorator):
                             "B200 hot path; every shipped config sets it to 0 (_base_/uda/pfst.py:13)")
         # B200-path extras (absent keys = reference behaviour)
         self.pseudo_threshold_per_class = cfg.get('pseudo_threshold_per_class', None)   # north_star S2'
-        self.kornia_aug = cfg.get('kornia_aug', 'error')       # 'error' | 'skip'
+        self.kornia_aug = cfg.get('kornia_aug', 'error')       # 'error' | 'skip' | 'builtin'
         self.compute_vis = cfg.get('compute_vis', True)
         proto_cfg = cfg.get('prototypes', None)
 
@@ -161,14 +161,18 @@ class PFGST(UDADecorator):
         return 0.0, self._thr_vec
 
     def _check_kornia(self, color_jitter):
+        """-> True when the built-in colour jitter must run for this iteration."""
         if not (color_jitter > self.color_jitter_p):
-            return
-        msg = ("the kornia ColorJitter (set color_jitter_probability=1.0) branch of strong_transform is "
-               "third-party arithmetic with its own random sampler, outside the B200 hot path (SURVEY.md §8c)")
+            return False
+        if self.kornia_aug == 'builtin':
+            return True
+        msg = ("the kornia ColorJitter branch of strong_transform is third-party arithmetic with its own random "
+               "sampler (SURVEY.md §8c): kornia_aug='builtin' runs the built-in restatement (parity unpinned), "
+               "color_jitter_probability=1.0 disables the branch")
         if self.kornia_aug == 'skip':
             warnings.warn(msg + "; skipped (kornia_aug='skip')", stacklevel=3)
-        else:
-            raise PfstError(msg)
+            return False
+        raise PfstError(msg)
 
     def forward_train(self, img, img_metas, gt_semantic_seg, target_img, target_img_metas,
                       target_img_strong_aug):
@@ -189,7 +193,7 @@ class PFGST(UDADecorator):
         means, stds = get_mean_std(img_metas, dev)
         color_jitter = random.uniform(0, 1)
         blur = random.uniform(0, 1) if self.blur else 0
-        self._check_kornia(color_jitter)
+        jitter = self._check_kornia(color_jitter)
 
         # ClassMix needs the batch's class set: start the presence kernel + 36-byte D2H now,
         # read it after the two network passes have been enqueued
@@ -238,6 +242,17 @@ class PFGST(UDADecorator):
             ignore_top=self.psweight_ignore_top, ignore_bottom=self.psweight_ignore_bottom)
         # gaussian_blur of strong_transform (dacs_transforms.py:88-107): B sigma draws in image
         # order on the global numpy stream (after the ClassMix draws, as in the reference loop)
+        if jitter:
+            # color_jitter of strong_transform (dacs_transforms.py:56-85): one kornia-style draw per image
+            # from the torch CPU generator, in image order; denorm/renorm with the first image's statistics
+            # like the reference (`means[0]`, pfgst.py:218-219)
+            draws = [draw_color_jitter(self.color_jitter_s) for _ in range(batch_size)]
+            dn = self.strong_aug_denorm_type == 'mean_std'
+            if self.strong_aug_denorm_type not in ('mean_std', 'none'):
+                raise ValueError('No such denorm type!')
+            mixed_img = ops.color_jitter(mixed_img, [d[0] for d in draws], [d[1] for d in draws],
+                                         img_metas[0]['img_norm_cfg']['mean'] if dn else None,
+                                         img_metas[0]['img_norm_cfg']['std'] if dn else None)
         mixed_img = gaussian_blur_batch(blur, mixed_img)
 
         # ⑧ student on the mixed batch (pfgst.py:303-310)

@@ -193,18 +193,59 @@ def gaussian_blur_batch(blur, mixed_img: torch.Tensor, rng=np.random) -> torch.T
     return ops.gaussian_blur(mixed_img.contiguous(), sigmas)
 
 
+def _jitter_ranges(s):
+    """kornia `_range_bound` of ColorJitter(brightness=s, contrast=s, saturation=s, hue=s) (or a dict)."""
+    if not isinstance(s, dict):
+        s = dict(brightness=s, contrast=s, saturation=s, hue=s)
+    b, c, sa, h = (float(s.get(k, 0.0)) for k in ("brightness", "contrast", "saturation", "hue"))
+    clamp = lambda lo, hi, a, bnd: (min(max(lo, a), bnd), min(max(hi, a), bnd))
+    return (clamp(1 - b, 1 + b, 0.0, 2.0), clamp(1 - c, 1 + c, 0.0, float("inf")),
+            clamp(1 - sa, 1 + sa, 0.0, float("inf")), clamp(-h, h, -0.5, 0.5))
+
+
+def draw_color_jitter(s, generator=None):
+    """One kornia ColorJitterGenerator draw (0.6 series, restated — see oracle/strong_aug.py): factors in the
+    order brightness, contrast, hue, saturation from the torch CPU generator, then randperm(4).
+    -> ((brightness, contrast, saturation, hue), order)."""
+    rb, rc, rs, rh = _jitter_ranges(s)
+    u = lambda r: float(r[0] + (r[1] - r[0]) * torch.rand((1,), generator=generator))
+    fb, fc, fh, fs = u(rb), u(rc), u(rh), u(rs)
+    return (fb, fc, fs, fh), torch.randperm(4, generator=generator).tolist()
+
+
+def _host3(x):
+    return [float(v) for v in (x.flatten().tolist() if isinstance(x, torch.Tensor) else x)][:3]
+
+
+def color_jitter(color_jitter, mean, std, data=None, target=None, s=.25, p=.2, denorm_type='mean_std'):
+    """dacs_transforms.py:56-85, same signature. The jitter itself is the built-in restatement of
+    kornia's ColorJitter (csrc/color_jitter.cu; third-party arithmetic and sampler, PARITY UNPINNED);
+    one draw for the whole `data` batch like a kornia module call with same_on_batch=False would make
+    per image — the reference always passes one image."""
+    if data is not None and data.shape[1] == 3 and color_jitter > p:
+        if denorm_type not in ('mean_std', 'none'):
+            raise ValueError('No such denorm type!')
+        draws = [draw_color_jitter(s) for _ in range(data.shape[0])]
+        dn = denorm_type == 'mean_std'
+        data = ops.color_jitter(data.contiguous(), [d[0] for d in draws], [d[1] for d in draws],
+                                _host3(mean) if dn else None, _host3(std) if dn else None)
+    return data, target
+
+
 def strong_transform(param, data=None, target=None):
-    """dacs_transforms.py:12-27: one_mix -> color_jitter -> gaussian_blur. The colour jitter is
-    kornia.augmentation.ColorJitter (third-party, version unpinned, random parameters drawn from
-    kornia's own torch-RNG sampler — SURVEY.md §8c) and is NOT part of this path: requesting it
-    raises instead of silently skipping."""
+    """dacs_transforms.py:12-27: one_mix -> color_jitter -> gaussian_blur. The colour jitter is kornia's
+    sampler + arithmetic (third-party, version unpinned): by default requesting it raises
+    instead of silently skipping; param['kornia_aug'] = 'builtin' runs the built-in restatement."""
     assert (data is not None) or (target is not None)
     if "mix" in param:
         data, target = one_mix(mask=param["mix"], data=data, target=target)
-    if data is not None and data.shape[1] == 3:
-        if param.get("color_jitter", 0) > param.get("color_jitter_p", 1.0):
-            raise PfstError("kornia ColorJitter branch is outside the B200 hot path "
-                            "(set color_jitter_probability=1.0)")
+    if data is not None and data.shape[1] == 3 and param.get("color_jitter", 0) > param.get("color_jitter_p", 1.0):
+        if param.get("kornia_aug", "error") != "builtin":
+            raise PfstError("the kornia ColorJitter branch runs only as the built-in restatement "
+                            "(param['kornia_aug']='builtin'); set color_jitter_probability=1.0 to disable it")
+        data, target = color_jitter(color_jitter=param["color_jitter"], s=param["color_jitter_s"],
+                                    p=param["color_jitter_p"], mean=param["mean"], std=param["std"],
+                                    data=data, target=target, denorm_type=param.get("denorm_type", "mean_std"))
     data, target = gaussian_blur(blur=param.get("blur", 0), data=data, target=target)
     return data, target
 

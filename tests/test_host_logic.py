@@ -151,3 +151,32 @@ def test_strong_augmentation_draws_like_the_reference_and_registers():
             assert after == np.random.random()
     with pytest.raises(PfstError):
         ops.photometric_u8(torch.zeros((1, 4, 4, 3), dtype=torch.uint8), [[]])
+
+
+def test_colour_jitter_restatement_properties_and_draw_order():
+    """Oracle restatement of kornia's ColorJitter (parity unpinned): neutral factors are the identity, the HSV
+    pair round-trips, factors land in kornia's ranges, and the host mirror draws exactly like the oracle."""
+    from oracle import strong_aug as osa
+    from pfst_b200.utils import dacs_transforms as T
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((2, 3, 24, 24), generator=g)
+    assert float((osa.hsv_to_rgb(osa.rgb_to_hsv(x)) - x).abs().max()) < 2e-6
+    neutral = dict(brightness=torch.ones(2), contrast=torch.ones(2), saturation=torch.ones(2), hue=torch.zeros(2),
+                   order=torch.tensor([3, 1, 0, 2]))
+    assert float((osa.apply_jitter(x, neutral) - x).abs().max()) < 2e-6
+    r = osa.jitter_ranges(0.2)
+    assert r["brightness"] == (0.8, 1.2) and r["hue"] == (-0.2, 0.2)
+    assert osa.jitter_ranges(dict(brightness=1.5, hue=0.7))["brightness"] == (0.0, 2.0)
+    assert osa.jitter_ranges(dict(brightness=1.5, hue=0.7))["hue"] == (-0.5, 0.5)
+    for seed in range(10):
+        torch.manual_seed(seed)
+        fac, order = T.draw_color_jitter(0.2)
+        torch.manual_seed(seed)
+        p = osa.draw_jitter(0.2, 1)
+        assert fac == (float(p["brightness"]), float(p["contrast"]), float(p["saturation"]), float(p["hue"]))
+        assert order == p["order"].tolist() and sorted(order) == [0, 1, 2, 3]
+        assert 0.8 <= fac[0] <= 1.2 and -0.2 <= fac[3] <= 0.2
+    # the jitter stays opt-in: default strong_transform refuses it, loudly (no GPU needed for the refusal)
+    param = dict(color_jitter=0.9, color_jitter_s=0.2, color_jitter_p=0.2, blur=0, mean=None, std=None)
+    with pytest.raises(PfstError):
+        T.strong_transform(param, data=x)
