@@ -2,11 +2,9 @@
 kornia's 0.6-series ColorJitter (oracle/strong_aug.py — third-party sampler and arithmetic, PARITY UNPINNED).
 Tolerance: 1e-5 of the data scale (the kernel repeats the torch expressions operation by operation).
 
-NOT YET RUN ON A GPU: the kernel was written after round 1's GPU budget was spent. The module is opt-in
-(`kornia_aug='builtin'`) and these tests only run with PFST_TEST_UNVERIFIED=1 until a B200 run has confirmed
-them (first call of round 2); the default `-m gpu` suite therefore never depends on unverified code."""
+First confirmed on a B200 in capture r1v (profiles/r1v_pytest_color_jitter.log). The module stays opt-in
+(`kornia_aug='builtin'`) because its parity against kornia itself cannot be pinned."""
 import itertools
-import os
 
 import numpy as np
 import pytest
@@ -16,9 +14,7 @@ from oracle import strong_aug as osa
 from pfst_b200 import ops
 from pfst_b200.utils import dacs_transforms as T
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PFST_TEST_UNVERIFIED") != "1",
-                                 reason="colour-jitter kernel not yet confirmed on a GPU (set PFST_TEST_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _params(factors, order):
