@@ -299,6 +299,16 @@ def main():
         report("photometric_u8 (all four distortions)", 6 * P, lambda i: aug.apply_batch(u8[i], full, out=o8[i]))
         report("photometric_u8 (brightness only)", 6 * P, lambda i: aug.apply_batch(u8[i], light, out=o8[i]))
         del u8, o8
+        # colour jitter of the mixed image (kornia ColorJitter restated): 12 B read + 12 B written per pixel
+        fimg = [inp["img"].to(dev) + 0.0 for _ in range(R)]
+        fout = [torch.empty_like(fimg[0]) for _ in range(R)]
+        fac, order = [(0.9, 1.1, 1.15, 0.1)] * B, [[2, 0, 3, 1]] * B
+        mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+        report("color_jitter (four transforms, denorm/renorm)", 24 * P,
+               lambda i: _ops.color_jitter(fimg[i], fac, order, mean, std, out=fout[i]))
+        report("color_jitter (brightness + contrast only)", 24 * P,
+               lambda i: _ops.color_jitter(fimg[i], fac, [[0, 1]] * B, mean, std, out=fout[i]))
+        del fimg, fout
     print(json.dumps({"peak_gbs": peak, "workload": wl.name, "graph": not args.no_graph}))
 
 
