@@ -180,3 +180,25 @@ def test_colour_jitter_restatement_properties_and_draw_order():
     param = dict(color_jitter=0.9, color_jitter_s=0.2, color_jitter_p=0.2, blur=0, mean=None, std=None)
     with pytest.raises(PfstError):
         T.strong_transform(param, data=x)
+
+
+def test_softmax_space_argmax_shortcut_holds_on_the_cpu_softmax():
+    """csrc/eval_argmax.cu evaluates the soft-max only for pixels with an EARLIER logit within 3e-4 of the
+    maximum; everywhere else it returns the first arg-max of the logits (0 when the row holds a NaN after the
+    max subtraction). The same statement must hold for torch's own soft-max -> arg-max (encoder_decoder.py:311,332)."""
+    g = torch.Generator().manual_seed(0)
+    for C in (2, 6, 12, 33):
+        x = torch.randn((4, C, 48, 48), generator=g) * 3
+        x[1] = 2.0 + 1e-4 * torch.randint(0, 3, (C, 48, 48), generator=g)   # many near and exact ties
+        x[0, 1, 0, :8] = float('nan'); x[0, 0, 1, :8] = float('inf'); x[0, C - 1, 2, :8] = float('inf')
+        x[0, :, 3, :8] = float('-inf'); x[0, 0, 4, :8] = float('-inf')
+        ref = torch.softmax(x, 1).argmax(1)
+        m, am = x.max(1)                                                 # first index of the maximum
+        first = (x == m.unsqueeze(1)).float().argmax(1)
+        d = x - m.unsqueeze(1)
+        nan_row = torch.isnan(d).any(1)
+        earlier = torch.arange(C).view(1, C, 1, 1) < first.unsqueeze(1)
+        near = ((d > -3.0e-4) & earlier).any(1)
+        shortcut = torch.where(nan_row, torch.zeros_like(first), first)
+        assert torch.equal(shortcut[~near], ref[~near]), C
+        assert int(near.sum()) > 0 and int(nan_row.sum()) >= 32
