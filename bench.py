@@ -334,7 +334,11 @@ def run_ours(args, wl, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms = times.tolist()
-    step.release_graphs()          # the graphs hold NCCL work: drop them before the process group goes
+    reduce_mode = "peer-board (one-shot NVLink all-reduce inside proto_finalize)" if step.bank.peer is not None else \
+        ("nccl all-reduce" if world > 1 else "none (single rank)")
+    if step.bank.peer is not None:
+        step.bank.peer.check()
+    step.close()                   # collective: graphs and peer boards go before the process group
     if rank != 0:
         return
     px = wl.B * wl.H * wl.W
@@ -354,7 +358,7 @@ def run_ours(args, wl, rank, world, local_rank):
                        "feature_dim": wl.D, "params": n_params,
                        "l2": "no flush: per-step working set (params 349 MB + maps 0.5 GB) exceeds the 126 MB L2",
                        "step": "EMA + pseudo-label + ClassMix + PFGST loss fwd/bwd + prototypes fwd/bwd (+ all-reduce)",
-                       "cuda_graphs": not args.no_graphs},
+                       "cuda_graphs": not args.no_graphs, "proto_reduce": reduce_mode},
             "iters_per_s": world * args.steps / (ms * 1e-3) / world,
             "step_bytes": sum(ab.values()), "step_gbs_per_gpu": sum(ab.values()) / (ms / args.steps * 1e-3) / 1e9,
             "step_frac_of_peak": sum(ab.values()) / (ms / args.steps * 1e-3) / 1e9 / peak,

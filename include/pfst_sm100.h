@@ -293,6 +293,40 @@ int pfst_proto_finalize_dev(float* packed, int32_t C, int32_t D, const float* mu
                             float* mu_out, int64_t* cnt_out, uint8_t* seen_out,
                             int32_t reset_packed, void* stream);
 
+/* ---- P2 across ranks: one-shot all-reduce over NVLink peer memory, fused into the finalise ----
+ * north_star: "only the prototype sums and counts ... are reduced" across the data-parallel
+ * ranks. The reference's only cross-rank reduction of per-iteration quantities is
+ * BaseSegmentor._parse_losses' dist.all_reduce (rsiseg/models/segmentors/base.py:214-218);
+ * prototypes are the north_star extension (P1-P3). Instead of a collective call between
+ * two kernels, every rank owns a "board" (inbox[2][nranks][stride] fp32 + flags[nranks][C]
+ * u64) that all peers map through a CUDA IPC handle; pfst_proto_finalize_peer pushes this
+ * rank's packed [sums|counts] into every board, waits for the peers' step tokens and sums the
+ * inbox in rank order (bit-identical prototypes on every rank), then finalises like
+ * pfst_proto_finalize_dev (which it equals for nranks = 1).
+ *
+ * Set-up entry points (called once; these DO allocate / synchronise):
+ *   pfst_peer_board_bytes  size of a board; also returns the inbox stride (floats) and the
+ *                          byte offset of the flags;
+ *   pfst_peer_alloc        cudaMalloc + zero + IPC handle (64 bytes, host) of a board;
+ *   pfst_peer_open/close   map / unmap a peer's board from its IPC handle;
+ *   pfst_peer_free         release a board obtained from pfst_peer_alloc.                  */
+int64_t pfst_peer_board_bytes(int32_t C, int32_t D, int32_t nranks, int64_t* stride_out,
+                              int64_t* flag_offset_out);
+int pfst_peer_alloc(int64_t bytes, void** ptr_out, void* ipc_handle64_host);
+int pfst_peer_open(const void* ipc_handle64_host, void** ptr_out);
+int pfst_peer_close(void* ptr);
+int pfst_peer_free(void* ptr);
+
+/* boards: device uint64[nranks] = base address of every rank's board as mapped in THIS
+ * process (entry `rank` = the local board). status: device int64[2] = {1 if a wait for a peer
+ * exceeded timeout_ns (that step's prototypes are invalid), last completed token}.
+ * Asynchronous, no allocation, graph-capturable; every rank must launch it once per step.  */
+int pfst_proto_finalize_peer(float* packed, int32_t C, int32_t D, const float* mu_prev,
+                             const uint8_t* seen_prev, double alpha, int64_t* iter_state,
+                             float* mu_out, int64_t* cnt_out, uint8_t* seen_out,
+                             const uint64_t* boards, int32_t rank, int32_t nranks,
+                             int64_t* status, int64_t timeout_ns, void* stream);
+
 /* loss = mean over valid pixels of ||feats[:,n] - mu[label_n]||_2 (masked_feat_dist
  * with f2 = mu[label]); valid = label in [0,C) and seen[label] (seen may be NULL).
  * dist: (B,h,w) per-pixel distances (0 where invalid), kept for the backward.

@@ -23,9 +23,68 @@ def _lab3(labels: torch.Tensor) -> torch.Tensor:
     return labels.contiguous()
 
 
+class PeerBoard:
+    """The multi-rank side of P2: every rank's prototype "board" (inbox + flags) in NVLink peer
+    memory, mapped into this process through CUDA IPC handles exchanged over the process group
+    (plumbing only: one all_gather_object at construction). `PrototypeBank.finalize_captured`
+    then runs pfst_proto_finalize_peer — push, token wait, rank-ordered sum and finalise in ONE
+    kernel (csrc/peer.cu) — so no collective call sits on the step's critical path."""
+
+    def __init__(self, num_classes: int, dim: int, device, group=None, timeout_s: float = 10.0):
+        import ctypes as C
+        import torch.distributed as dist
+        self.device = torch.device(device)
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.timeout_ns = int(timeout_s * 1e9)
+        lib = _lib.load()
+        nbytes = int(lib.pfst_peer_board_bytes(num_classes, dim, self.world, None, None))
+        if nbytes <= 0:
+            raise PfstError(f"peer board: unsupported C={num_classes}, D={dim}, ranks={self.world}")
+        with torch.cuda.device(self.device):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _lib.call("pfst_peer_alloc", nbytes, C.byref(ptr), handle)
+            self._own = ptr.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (self.rank, bytes(handle.raw)), group=group)
+            self._opened, bases = [], []
+            for r, h in sorted(handles):
+                if r == self.rank:
+                    bases.append(self._own)
+                    continue
+                q = C.c_void_p()
+                _lib.call("pfst_peer_open", C.create_string_buffer(h, 64), C.byref(q))
+                self._opened.append(q.value)
+                bases.append(q.value)
+        self.boards = torch.tensor(bases, dtype=torch.int64, device=self.device)
+        self.status = torch.zeros(2, dtype=torch.int64, device=self.device)
+        dist.barrier(group=group)          # every board is mapped everywhere before the first push
+
+    def check(self) -> None:
+        """Synchronises; raises if a peer's token did not arrive in time during any step so far."""
+        if int(self.status[0].item()) != 0:
+            raise PfstError("peer all-reduce: a rank did not publish its prototype chunk within the timeout; "
+                            "the prototypes of that step are invalid")
+
+    def close(self) -> None:
+        """Collective teardown: nobody unmaps or frees a board a peer may still push into."""
+        import torch.distributed as dist
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for q in self._opened:
+                _lib.call("pfst_peer_close", q)
+            _lib.call("pfst_peer_free", self._own)
+        self._opened, self._own = [], None
+
+
 class PrototypeBank:
     def __init__(self, num_classes: int, dim: int, device, alpha: float = 0.999, group=None,
                  comm_stream: Optional[torch.cuda.Stream] = None):
+        self.peer = None             # PeerBoard: finalize_captured then includes the cross-rank sum
         self.C, self.D = int(num_classes), int(dim)
         self.device = torch.device(device)
         self.alpha = float(alpha)
@@ -92,6 +151,8 @@ class PrototypeBank:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return None
+        if self.peer is not None:          # the finalise kernel itself sums over the ranks
+            return None
         return dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     # P2
@@ -106,7 +167,21 @@ class PrototypeBank:
         self.iter += 1
         return self.mu
 
-    def finalize_captured(self, stream: int) -> None:
+    def attach_peer_board(self, timeout_s: float = 10.0) -> "PeerBoard":
+        """Collective (every rank of `group` calls it): from now on `finalize_captured` sums the
+        packed buffers of all ranks over NVLink peer memory inside the finalise kernel."""
+        if self.peer is None:
+            self.peer = PeerBoard(self.C, self.D, self.device, self.group, timeout_s)
+        return self.peer
+
+    def finalize_captured(self, stream: int, local_only: bool = False) -> None:
+        if self.peer is not None and not local_only:
+            pb = self.peer
+            _lib.call("pfst_proto_finalize_peer", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
+                      self.seen.data_ptr(), float(self.alpha), self.iter_state.data_ptr(), self.mu.data_ptr(),
+                      self.counts.data_ptr(), self.seen.data_ptr(), pb.boards.data_ptr(), pb.rank, pb.world,
+                      pb.status.data_ptr(), pb.timeout_ns, stream)
+            return
         _lib.call("pfst_proto_finalize_dev", self.packed.data_ptr(), self.C, self.D, self.mu.data_ptr(),
                   self.seen.data_ptr(), float(self.alpha), self.iter_state.data_ptr(), self.mu.data_ptr(),
                   self.counts.data_ptr(), self.seen.data_ptr(), 1, stream)

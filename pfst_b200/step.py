@@ -103,6 +103,9 @@ class SelfTrainingStep:
         self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
         self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
         self.nccl_in_graph = os.environ.get("PFST_NCCL_IN_GRAPH", "1") != "0"
+        # multi-rank P2: one-shot all-reduce over NVLink peer memory inside the finalise kernel
+        # (csrc/peer.cu); PFST_PEER_REDUCE=0 falls back to ncclAllReduce between two kernels
+        self.peer_reduce = os.environ.get("PFST_PEER_REDUCE", "1") != "0"
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
@@ -188,6 +191,8 @@ class SelfTrainingStep:
                 # first use on every rank (they construct and step symmetrically): one eager collective
                 # so that NCCL's lazy communicator set-up never happens inside a graph capture
                 dist.all_reduce(torch.zeros(1, device=self.device), group=self.bank.group)
+                if self.peer_reduce:
+                    self.bank.attach_peer_board()          # collective: IPC handles exchanged once
         return self._world > 1
 
     def _whole_step(self, b, args_a, args_b, reduce: bool = False):
@@ -197,7 +202,7 @@ class SelfTrainingStep:
         neigh_dots(x_src); only the prototype distance waits for them."""
         self._segment_a(b, *args_a)
         if not reduce:
-            self.bank.finalize_captured(ops._stream())
+            self.bank.finalize_captured(ops._stream(), local_only=True)
             self._segment_b(b, *args_b, part="all")
             return
         import torch.distributed as dist
@@ -206,7 +211,9 @@ class SelfTrainingStep:
         fork.record(main)
         self._comm.wait_event(fork)
         with torch.cuda.stream(self._comm):
-            dist.all_reduce(self.bank.packed, op=dist.ReduceOp.SUM, group=self.bank.group)
+            if self.bank.peer is None:
+                dist.all_reduce(self.bank.packed, op=dist.ReduceOp.SUM, group=self.bank.group)
+            # peer board: push + token wait + rank-ordered sum + finalise in this ONE kernel
             self.bank.finalize_captured(self._comm.cuda_stream)
             mu_ready.record(self._comm)
         self._segment_b(b, *args_b, part="all", mu_ready=mu_ready)
@@ -252,6 +259,14 @@ class SelfTrainingStep:
         graphs = sets
         self._graphs[key] = graphs
         return graphs
+
+    def close(self) -> None:
+        """Collective teardown on multi-rank runs (every rank calls it, before
+        destroy_process_group): drops the graphs, then unmaps / frees the peer boards."""
+        self.release_graphs()
+        if self.bank.peer is not None:
+            self.bank.peer.close()
+            self.bank.peer = None
 
     def release_graphs(self) -> None:
         """Drop the captured CUDA graphs. On multi-rank runs they contain NCCL work: release them
@@ -317,8 +332,8 @@ class SelfTrainingStep:
         split = self._multi_rank() if self.split_for_allreduce is None else bool(self.split_for_allreduce)
         # multi-rank: one graph with the collective inside ("reduce"), or three graphs around an
         # eagerly issued all-reduce ("b1","b2") when NCCL graph capture is switched off
-        parts = (("reduce",) if self.graphs and self.nccl_in_graph and self._multi_rank() else ("b1", "b2")) if split \
-            else ("all",)
+        in_one = self._multi_rank() and (self.bank.peer is not None or (self.graphs and self.nccl_in_graph))
+        parts = (("reduce",) if in_one else ("b1", "b2")) if split else ("all",)
         graphs = None
         if self.graphs:
             pkey = skey + parts + tuple(t.data_ptr() for t in (img, trg_img, gt, ema_logits, logits_trg, x_src, x_ema))

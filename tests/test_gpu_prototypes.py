@@ -115,3 +115,40 @@ def test_single_launch_accumulate_equals_the_split_form(cuda, B, D, h, w, C, H, 
     pa, pb = a.packed.cpu(), b.packed.cpu()
     assert torch.equal(pa[C * D:], pb[C * D:])
     assert (pa[:C * D] - pb[:C * D]).abs().max() <= 1e-5 * pb[:C * D].abs().max()
+
+
+def test_peer_board_single_rank_equals_local_finalize(cuda):
+    """csrc/peer.cu with one rank (push into the own board, token wait, sum of one chunk) is
+    bit-identical to proto_finalize_kernel over several iterations (EMA of the prototypes, device-
+    resident iteration, packed re-zeroed). The N > 1 exchange is tests/test_gpu_multi_rank.py."""
+    import socket
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+        created = True
+    try:
+        B, D, h, w, C, H, W = 2, 48, 16, 16, 7, 128, 128
+        local, peer = P.PrototypeBank(C, D, cuda), P.PrototypeBank(C, D, cuda)
+        board = peer.attach_peer_board(timeout_s=2.0)
+        assert board.world == 1
+        for it in range(4):
+            feats, labels = _case(B, D, h, w, C, H, W, seed=20 + it)
+            if it == 2:
+                labels[labels == 3] = 255            # a class without pixels keeps its prototype
+            for bank in (local, peer):
+                bank.accumulate(feats.to(cuda), labels.to(cuda))
+                bank.finalize()
+            assert torch.equal(local.mu, peer.mu), it
+            assert torch.equal(local.seen, peer.seen) and torch.equal(local.counts, peer.counts)
+            assert torch.equal(local.iter_state, peer.iter_state)
+            assert float(peer.packed.abs().sum()) == 0.0
+        board.check()
+        assert int(board.status[1]) == 4
+        board.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
