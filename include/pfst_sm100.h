@@ -458,6 +458,24 @@ int pfst_color_jitter(const float* in, float* out, int64_t n_images, int64_t HW,
                       const float* factors_host, const int32_t* order_host,
                       const float* mean_host, const float* std_host, int32_t denorm, void* stream);
 
+/* ---- log variables without host round trips ------------------------------
+ * Replaces the arithmetic of BaseSegmentor._parse_losses
+ * (rsiseg/models/segmentors/base.py:177-222): `loss = sum(v for k, v in log_vars if 'loss' in k)`
+ * (left-to-right fp32 adds from 0), and per variable `v.div_(world)` before the all-reduce and
+ * `.item()`. ptrs_host: HOST array of n <= 32 DEVICE pointers to fp32 scalars; weights_host:
+ * HOST array of n multipliers applied inside the sum (NULL = all 1). row_out (nullable):
+ * row_out[i] = v_i / divisor, row_out[n] = sum / divisor. total_out (nullable): the undivided
+ * sum over the entries whose bit is set in sum_mask. One single-thread launch.               */
+int pfst_gather_scalars(const float* const* ptrs_host, const float* weights_host, int32_t n,
+                        uint32_t sum_mask, float divisor, float* row_out, float* total_out,
+                        void* stream);
+
+/* out[i] = *ptrs_host[i] * weights_host[i] (0 where the pointer is NULL; weights NULL = 1),
+ * i < n <= 32: packs separate 0-dim device scalars — e.g. the upstream gradients autograd hands
+ * to the backward of the six PFGSTLoss terms and the prototype distance — into one vector.  */
+int pfst_pack_scalars(const float* const* ptrs_host, const float* weights_host, int32_t n,
+                      float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,7 @@ class SelfTrainingStep:
         self._world = None        # world size, resolved on first use
         self._prefetched = None   # data_ptr of the gt whose presence bits are in flight
         self._step_count = 0
+        self._ema_it = None       # iteration whose EMA update_teacher() has already launched
 
     # ------------------------------------------------------------------ segments
     def _segment_a(self, b: _Buffers, ema_logits, x_ema, geo):
@@ -286,7 +287,20 @@ class SelfTrainingStep:
             self._ev[7].record(wait_stream)
             self._aux.wait_event(self._ev[7])
         self.plan.start(gt, self._aux)
-        self._prefetched = gt.data_ptr()
+        self._prefetched = (gt.data_ptr(), tuple(gt.shape))
+
+    def update_teacher(self, it: int) -> None:
+        """E1/E2 of iteration `it` — call it BEFORE the teacher forward of that iteration, as the
+        reference does (pfgst.py:203-208 precede the teacher pass :255); `teacher_ready()` then makes
+        the current stream wait for it. run(it, ...) joins the same launch instead of issuing its
+        own. Without this call run() launches the update itself, which is only correct when the
+        teacher outputs passed to run() did not come from a forward of this iteration's teacher
+        (synthetic network outputs, as in bench.py)."""
+        self._launch_ema(it, torch.cuda.current_stream())
+        self._ema_it = it
+
+    def teacher_ready(self) -> None:
+        torch.cuda.current_stream().wait_event(self._ev[6])
 
     def _launch_ema(self, it: int, main) -> None:
         """E2 on its own stream (bounded persistent grid): independent of everything else in the
@@ -323,7 +337,8 @@ class SelfTrainingStep:
         b, geo = ent
         main = torch.cuda.current_stream()
         # M1: presence bits (prefetched, or computed now on the auxiliary stream), host draw, H2D
-        if self._prefetched != gt.data_ptr():
+        if self._prefetched != (gt.data_ptr(), tuple(gt.shape)):
+            self.plan.drop_pending()                   # a prefetch for another batch must not shift the FIFO
             self.prefetch(gt, wait_stream=main)
         self._prefetched = None
         args_a = (ema_logits, x_ema, geo)
@@ -341,7 +356,9 @@ class SelfTrainingStep:
             graphs = sets[self._step_count % len(sets)]
         self._step_count += 1
         self.plan.choose(rng)                          # waits for the 36-byte copy only
-        self._launch_ema(it, main)                     # E2 on its own stream, joined below
+        if self._ema_it != it:                         # not already issued by update_teacher(it)
+            self._launch_ema(it, main)                 # E2 on its own stream, joined below
+        self._ema_it = None
         if len(parts) == 1:
             # S1/S2, L2(x_ema), P1 -> (all-reduce) P2 -> M2, L2(x_src), P3, L1/L3-L6, backward
             if graphs:
@@ -370,17 +387,18 @@ class SelfTrainingStep:
 
 
 def algorithmic_bytes(B: int, C: int, H: int, W: int, D: int, h: int, w: int, n_params: int) -> dict:
-    """Algorithmic HBM bytes per step and per kernel."""
+    """Algorithmic HBM bytes per step and per kernel family — exactly SURVEY.md §8(d)'s figures
+    (cfg2: 1.3115 GB): K_ema 12 B/param; K_pl (4C+12) B/px; K_mask+K_mix 84 B/px (presence read 8
+    + mix reads 44 + writes 32); K_sim fwd two feature tensors; K_loss bwd read x_src + write grad;
+    K_proto one feature read + the labels; K_dist fwd+bwd 3 feature-sized passes. The small loss
+    maps (dots, coefficient maps, ~3.7 MB at cfg2) are not counted."""
     P, p = B * H * W, B * h * w
     return {
         "ema": 12 * n_params,
         "pseudo_label": (4 * C + 12) * P,
-        "class_presence": 8 * P,
-        "class_mix": 80 * P,                 # thre_type='all': the incoming weight is a scalar
+        "class_presence_and_mix": 84 * P,
         "neigh_dots": 2 * 4 * D * p,
-        "proto_accum": 4 * D * p + 8 * P // 64,
-        "loss_maps": (2 * 5 * 4 + 9 * 4 * 2) * p,
-        "proto_dist_fwd": 4 * D * p,
+        "proto_accum": 4 * D * p + 8 * p,
         "neigh_grad": 2 * 4 * D * p,
-        "proto_dist_bwd": 3 * 4 * D * p,
+        "proto_dist_fwd_bwd": 3 * 4 * D * p,
     }

@@ -47,6 +47,22 @@ WORKLOADS = {
 }
 
 
+@dataclass(frozen=True)
+class EvalWorkload:
+    name: str
+    maps: int       # label maps in the whole sweep (sharded over the ranks)
+    C: int
+    H: int
+    W: int
+
+
+EVAL_WORKLOADS = {
+    # BASELINE.json configs[4]
+    "cfg5": EvalWorkload("miou_eval_sweep_10000x1024x1024_C6", 10000, 6, 1024, 1024),
+    "tiny_eval": EvalWorkload("tiny_eval_8x64x64_C6", 8, 6, 64, 64),
+}
+
+
 def blocky_labels(B: int, H: int, W: int, C: int, gen: torch.Generator, ignore_frac: float = 0.05,
                   min_rect: int = 8, max_rect: int = 128) -> torch.Tensor:
     """(B,1,H,W) int64: random rectangles of random classes, 255 border padding."""

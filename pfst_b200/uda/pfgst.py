@@ -36,9 +36,12 @@ from torch.nn.modules.dropout import _DropoutNd
 from .. import losses as _losses  # noqa: F401  (registers PFGSTLoss in LOSSES)
 from .. import ops
 from .._lib import PfstError
+from ..engine import LOSS_KEYS, AuxTailFn, PluginEngine
+from ..losses.pfgst_loss import PFGSTLoss
 from ..prototypes import PrototypeBank, proto_dist_loss
 from ..registry import UDA, build_loss
 from ..utils.dacs_transforms import ClassMixPlan, draw_color_jitter, gaussian_blur_batch, get_mean_std
+from .log_ledger import ledger_for
 from .uda_decorator import UDADecorator, build_model, get_module
 
 
@@ -88,7 +91,16 @@ class PFGST(UDADecorator):
                             "B200 hot path; every shipped config sets it to 0 (_base_/uda/pfst.py:13)")
         # B200-path extras (absent keys = reference behaviour)
         self.pseudo_threshold_per_class = cfg.get('pseudo_threshold_per_class', None)   # north_star S2'
-        self.kornia_aug = cfg.get('kornia_aug', 'error')       # 'error' | 'skip' | 'builtin'
+        # kornia's ColorJitter in strong_transform (dacs_transforms.py:56-85): 'builtin' (default) runs the
+        # in-tree restatement of kornia 0.6 (parity unpinned: kornia is not installed where this was
+        # built), 'skip' leaves the image unjittered, 'error' raises when the branch is drawn
+        self.kornia_aug = cfg.get('kornia_aug', 'builtin')
+        if self.kornia_aug not in ('builtin', 'skip', 'error'):
+            raise ValueError(f"kornia_aug {self.kornia_aug!r}")
+        if self.kornia_aug == 'builtin' and self.color_jitter_p < 1.0:
+            warnings.warn("PFGST (B200 path): the colour jitter of strong_transform runs the built-in restatement of "
+                          "kornia.augmentation.ColorJitter (0.6 series); it has not been compared with an installed "
+                          "kornia (kornia_aug='error' refuses the branch instead, 'skip' drops it)", stacklevel=2)
         self.compute_vis = cfg.get('compute_vis', True)
         proto_cfg = cfg.get('prototypes', None)
 
@@ -110,6 +122,10 @@ class PFGST(UDADecorator):
         self._thr_vec = None
         self.proto_cfg = proto_cfg
         self.proto_bank = None
+        self._engine = None            # PluginEngine: the fused launch groups (built on first use)
+        self._aux_stream = None        # high-priority stream of the class-presence read
+        self._teacher_eval_modules = None
+        self.fused = cfg.get('fused_hot_path', True)
 
     # ------------------------------------------------------------------ accessors
     def get_ema_model(self):
@@ -174,33 +190,78 @@ class PFGST(UDADecorator):
             return False
         raise PfstError(msg)
 
+    # ------------------------------------------------------------------ fused launch groups
+    def _fused_loss_module(self):
+        """The PFGSTLoss module when the auxiliary-loss section can run as the engine's fused launch
+        groups (exactly one PFGSTLoss on a single decoded-feature map), else None -> generic path."""
+        if not self.fused or not self.apply_aux or len(self.aux_losses) != 1:
+            return None
+        mod = self.aux_losses[0]
+        return mod if type(mod) is PFGSTLoss and mod.feat_level is None else None
+
+    def _get_engine(self, dev, loss_module) -> PluginEngine:
+        if self._engine is None or self._engine.device != dev:
+            self._engine = PluginEngine(dev, self.num_classes, None if loss_module is None else loss_module._cfg,
+                                        self.proto_cfg, alpha=self.alpha)
+        return self._engine
+
+    def _freeze_teacher_dropout(self):
+        """pfgst.py:247-251; the module list is collected once (the model structure is static)."""
+        if self._teacher_eval_modules is None:
+            self._teacher_eval_modules = [m for m in self.get_ema_model().modules()
+                                          if isinstance(m, _DropoutNd) or type(m).__name__ == 'DropPath']
+        for m in self._teacher_eval_modules:
+            m.training = False
+
+    def d2h_bytes(self) -> int:
+        """Bytes this module has copied device->host so far (log-variable ledger reads + the
+        36-byte class-presence reads of ClassMix)."""
+        n = 0
+        for p in self.parameters():
+            n = ledger_for(p.device).d2h_bytes
+            break
+        return n + (0 if self._mix_plan is None else 36 * self._mix_plan._started)
+
+    def close(self) -> None:
+        """Collective on multi-rank runs, before destroy_process_group(): drops the captured graphs
+        and unmaps the NVLink peer boards of the prototype exchange."""
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
     def forward_train(self, img, img_metas, gt_semantic_seg, target_img, target_img_metas,
                       target_img_strong_aug):
         """pfgst.py:179-356."""
         log_vars = {}
         vis_states = {}
-        total_loss = 0
         batch_size = img.shape[0]
         dev = img.device
+        loss_mod = self._fused_loss_module()
+        eng = self._get_engine(dev, loss_mod)
+        ledger = ledger_for(dev)
+        ledger.begin()
+        parts, part_w = [], []
 
-        # ① EMA teacher (pfgst.py:203-208)
+        # ① EMA teacher (pfgst.py:203-208): own stream, joined right before the teacher pass ④
         if self.local_iter == 0:
-            self._init_ema_weights()
-        if self.local_iter > 0:
-            self._update_ema(self.local_iter)
+            for param in self.get_ema_model().parameters():
+                param.detach_()
+        eng.launch_ema(self._table(), self.local_iter)
 
         # ② host RNG draws, in the reference's order (pfgst.py:212-222)
-        means, stds = get_mean_std(img_metas, dev)
         color_jitter = random.uniform(0, 1)
         blur = random.uniform(0, 1) if self.blur else 0
         jitter = self._check_kornia(color_jitter)
 
-        # ClassMix needs the batch's class set: start the presence kernel + 36-byte D2H now,
-        # read it after the two network passes have been enqueued (SURVEY.md §7)
+        # ClassMix needs the batch's class set: presence kernel + 36-byte D2H on a high-priority
+        # stream now, read after the two network passes have been enqueued (SURVEY.md §7)
         gt_semantic_seg = gt_semantic_seg.contiguous()
         if self._mix_plan is None or self._mix_plan.device != dev or batch_size > self._mix_plan._chosen.shape[0]:
             self._mix_plan = ClassMixPlan(dev, max_batch=max(batch_size, 64))
-        self._mix_plan.start(gt_semantic_seg)
+            self._aux_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._mix_plan.drop_pending()          # an exception in an earlier iteration must not shift the FIFO
+        self._aux_stream.wait_stream(torch.cuda.current_stream())
+        self._mix_plan.start(gt_semantic_seg, self._aux_stream)
 
         # ③ student on source (pfgst.py:225-236)
         clean_losses = self.get_model().forward_train(
@@ -212,23 +273,32 @@ class PFGST(UDADecorator):
         src_logits = clean_losses.pop('logits')
         clean_loss, clean_log_vars = self._parse_losses(clean_losses)
         log_vars.update(clean_log_vars)
-        total_loss += clean_loss
+        parts.append(clean_loss); part_w.append(1.0)
 
-        # ④ teacher on target (pfgst.py:247-257)
-        for m in self.get_ema_model().modules():
-            if isinstance(m, _DropoutNd):
-                m.training = False
-            if type(m).__name__ == 'DropPath':
-                m.training = False
+        # ④ teacher on target (pfgst.py:247-257) — after the EMA update of this iteration
+        self._freeze_teacher_dropout()
+        eng.wait_ema()
         ema_logits, ema_states = self.get_ema_model().encode_decode(target_img, target_img_metas)
         ema_feats = ema_states['feats']
         if self.use_decoded_feats:
             ema_feats = ema_states['decoded_features']
 
-        # ⑤ pseudo labels (pfgst.py:259-277): one kernel, count stays on the device
+        # ⑤ pseudo labels (pfgst.py:259-277) ║ neighbourhood dots of x_ema -> prototypes (P1/P2)
         thr, thr_vec = self._threshold_args(dev)
-        pseudo_label, pseudo_prob, count, weight_part = ops.pseudo_label(
-            ema_logits.detach().contiguous(), thr, thr_vec, want_part_weight=self.thre_type == 'part')
+        single_feats = isinstance(ema_feats, torch.Tensor) and isinstance(src_feats, torch.Tensor)
+        fused = loss_mod is not None and single_feats
+        if self.proto_cfg is not None and not single_feats:
+            raise PfstError("prototypes need use_decoded_feats=True (a single (B,D,h,w) feature map)")
+        geo = None
+        if fused:
+            geo = ops.LossGeometry(src_logits.shape, src_feats.shape, gt_semantic_seg.shape, loss_mod.downscale,
+                                   loss_mod.dilation)
+            if ema_feats.shape != src_feats.shape:
+                raise PfstError("PFGSTLoss: x_ema / x_src shape mismatch")
+        x_ema = ema_feats.detach().contiguous() if (fused or self.proto_cfg is not None) else None
+        pseudo_label, pseudo_prob, count, weight_part = eng.teacher_outputs(
+            ema_logits.detach().contiguous(), x_ema, thr, thr_vec,
+            self.thre_type == 'part', geo)
         ps_size = pseudo_label.numel()
 
         # ⑥⑦ ClassMix (pfgst.py:281-300): host draw, then ONE fused launch
@@ -263,32 +333,48 @@ class PFGST(UDADecorator):
         mix_losses = add_prefix(mix_losses, 'mix')
         mix_loss, mix_log_vars = self._parse_losses(mix_losses)
         log_vars.update(mix_log_vars)
-        total_loss += mix_loss * self.trg_loss_weight
+        parts.append(mix_loss); part_w.append(float(self.trg_loss_weight))
 
-        tensors = dict(
-            img_src=img, img_src_metas=img_metas, img_trg=mixed_img, img_mixed=mixed_img,
-            img_metas_trg=target_img_metas, gt_src=gt_semantic_seg, x_src=src_feats, x_ema=ema_feats,
-            x_trg=mixed_feats, logits_src=src_logits, logits_trg=mixed_logits, logits_ema=ema_logits,
-            mix_masks=mix_masks, pseudo_weight=pseudo_weight)
-
-        # ⑨ auxiliary losses (pfgst.py:333-342)
-        if self.apply_aux:
-            aux_losses = self._get_aux_losses(tensors=tensors)
-            vis_states.update({k: v for k, v in aux_losses.items() if k.startswith('vis|')})
-            for name in vis_states.keys():
-                aux_losses.pop(name)
-            aux_loss, aux_log_vars = self._parse_losses(aux_losses)
+        # ⑨ auxiliary losses (pfgst.py:333-342) + P3
+        if fused:
+            outs = AuxTailFn.apply(mixed_logits.contiguous(), src_feats.contiguous(), eng, gt_semantic_seg,
+                                   mix_masks, geo, self.compute_vis)
+            aux_loss, aux_log_vars = self._parse_losses({k: outs[i] for i, k in enumerate(LOSS_KEYS)})
             log_vars.update(aux_log_vars)
-            total_loss += aux_loss
+            parts.append(aux_loss); part_w.append(1.0)
+            if self.compute_vis:
+                fb = eng._fwd["b"]
+                vis_states['vis|density_sim_feat'] = (mixed_img, fb["density"].clone(), fb["eroded"].bool())
+            if self.proto_cfg is not None:
+                self.proto_bank = eng.bank
+                p_loss, p_log_vars = self._parse_losses({'loss_proto_dist': outs[6]})
+                log_vars.update(p_log_vars)
+                parts.append(p_loss); part_w.append(1.0)
+        else:
+            tensors = dict(
+                img_src=img, img_src_metas=img_metas, img_trg=mixed_img, img_mixed=mixed_img,
+                img_metas_trg=target_img_metas, gt_src=gt_semantic_seg, x_src=src_feats, x_ema=ema_feats,
+                x_trg=mixed_feats, logits_src=src_logits, logits_trg=mixed_logits, logits_ema=ema_logits,
+                mix_masks=mix_masks, pseudo_weight=pseudo_weight)
+            if self.apply_aux:
+                aux_losses = self._get_aux_losses(tensors=tensors)
+                vis_states.update({k: v for k, v in aux_losses.items() if k.startswith('vis|')})
+                for name in vis_states.keys():
+                    aux_losses.pop(name)
+                aux_loss, aux_log_vars = self._parse_losses(aux_losses)
+                log_vars.update(aux_log_vars)
+                parts.append(aux_loss); part_w.append(1.0)
+            if self.proto_cfg is not None:       # prototypes were accumulated / finalised in group 1
+                self.proto_bank = eng.bank
+                proto_loss = proto_dist_loss(src_feats, gt_semantic_seg, eng.bank.mu, eng.bank.seen) \
+                    * self.proto_cfg.get('weight', 0.1)
+                p_loss, p_log_vars = self._parse_losses({'loss_proto_dist': proto_loss})
+                log_vars.update(p_log_vars)
+                parts.append(p_loss); part_w.append(1.0)
 
-        # P1-P3 (north_star extension; off unless cfg['prototypes'] is given)
-        if self.proto_cfg is not None:
-            proto_loss = self._prototype_step(ema_feats, pseudo_label, pseudo_prob, src_feats, gt_semantic_seg)
-            p_loss, p_log_vars = self._parse_losses({'loss_proto_dist': proto_loss})
-            log_vars.update(p_log_vars)
-            total_loss += p_loss
-
-        # ⑩ backward (pfgst.py:344)
+        # ⑩ backward (pfgst.py:344): total = 0 + clean + mix*w + aux (+ proto), one launch
+        total_loss = ledger.weighted_total(parts, part_w)
+        ledger.end()
         total_loss.backward()
 
         # ⑪ vis states (pfgst.py:346-352)
@@ -302,19 +388,6 @@ class PFGST(UDADecorator):
 
         self.local_iter += 1
         return log_vars, vis_states
-
-    def _prototype_step(self, ema_feats, pseudo_label, pseudo_prob, src_feats, gt):
-        cfg = self.proto_cfg
-        if isinstance(ema_feats, (list, tuple)) or isinstance(src_feats, (list, tuple)):
-            raise PfstError("prototypes need use_decoded_feats=True (a single (B,D,h,w) feature map)")
-        if self.proto_bank is None:
-            self.proto_bank = PrototypeBank(self.num_classes, ema_feats.shape[1], ema_feats.device,
-                                            alpha=cfg.get('alpha', self.alpha))
-        conf_thr = cfg.get('conf_threshold', None)
-        mu = self.proto_bank.update(ema_feats.detach().contiguous(), pseudo_label,
-                                    pseudo_prob if conf_thr is not None else None,
-                                    conf_thr if conf_thr is not None else 0.0)
-        return proto_dist_loss(src_feats, gt, mu, self.proto_bank.seen) * cfg.get('weight', 0.1)
 
     def _get_aux_losses(self, tensors):
         """pfgst.py:358-368."""

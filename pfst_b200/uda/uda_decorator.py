@@ -4,14 +4,13 @@ mmcv-style dict (built through pfst_b200.registry / an mmcv registry), an
 nn.Module instance, or a zero-argument factory returning one."""
 from __future__ import annotations
 
-from collections import OrderedDict
 from copy import deepcopy
 
 import torch
-import torch.distributed as dist
 import torch.nn as nn
 
 from ..registry import build_segmentor
+from .log_ledger import ledger_for
 
 
 def get_module(module):
@@ -78,31 +77,17 @@ class UDADecorator(nn.Module):
 
     @staticmethod
     def _parse_losses(losses):
-        """BaseSegmentor._parse_losses, rsiseg/models/segmentors/base.py:177-222 — same
-        values, keys and ordering; the ~N per-variable `.item()` syncs (and per-variable
-        all-reduces) of the reference are batched into ONE device vector, one all-reduce
-        and one D2H copy."""
-        log_vars = OrderedDict()
-        for name, value in losses.items():
-            if isinstance(value, torch.Tensor):
-                log_vars[name] = value.mean()
-            elif isinstance(value, list):
-                log_vars[name] = sum(_l.mean() for _l in value)
-            else:
-                raise TypeError(f'{name} is not a tensor or list of tensors')
-        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
-        distributed = dist.is_available() and dist.is_initialized()
-        if distributed:
-            n = torch.tensor(len(log_vars), device=loss.device)
-            dist.all_reduce(n)
-            assert n == len(log_vars) * dist.get_world_size(), \
-                'loss log variables are different across GPUs!\n' + \
-                f'rank {dist.get_rank()} len(log_vars): {len(log_vars)} keys: ' + ','.join(log_vars.keys())
-        log_vars['loss'] = loss
-        flat = torch.stack([v.detach().float().reshape(()) for v in log_vars.values()])
-        if distributed:
-            flat = flat / dist.get_world_size()
-            dist.all_reduce(flat)
-        for k, v in zip(list(log_vars.keys()), flat.tolist()):
-            log_vars[k] = v
-        return loss, log_vars
+        """BaseSegmentor._parse_losses, rsiseg/models/segmentors/base.py:177-222 — same keys,
+        ordering and values (`loss` = left-to-right fp32 sum of the entries whose key contains
+        'loss'; log values = mean over ranks). The reference's per-variable `.item()` syncs and
+        per-variable all-reduces are gone: one single-thread gather kernel per call writes the
+        scalars into a persistent device ledger, ONE all-reduce per iteration reduces the row, and
+        the returned log values are `LazyScalar`s that copy the ledger to the host once, when a
+        value is first read (uda/log_ledger.py)."""
+        dev = None
+        for value in losses.values():
+            t = value[0] if isinstance(value, list) and value else value
+            if isinstance(t, torch.Tensor):
+                dev = t.device
+                break
+        return ledger_for(dev if dev is not None else "cpu").parse(losses)

@@ -91,6 +91,14 @@ class ClassMixPlan:
             self._presence_host[slot].copy_(self._presence, non_blocking=True)
         self._events[slot].record(stream)
 
+    def drop_pending(self) -> int:
+        """Forget start() calls that were never matched by choose() (an exception between the two,
+        or a prefetch for a batch that was not run): the next start()/choose() pair is aligned
+        again. Returns the number of dropped slots."""
+        n = self._started - self._chosen_count
+        self._chosen_count = self._started
+        return n
+
     def choose(self, rng=np.random) -> torch.Tensor:
         if self._chosen_count >= self._started:
             raise PfstError("ClassMixPlan.choose() without a matching start()")

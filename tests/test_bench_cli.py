@@ -42,3 +42,24 @@ def test_product_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_both_arms_describe_the_workload_with_the_same_config_dict():
+    """The driver compares the `config` of the product arm with the reference arm's."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from pfst_b200.synthetic import EVAL_WORKLOADS, WORKLOADS
+    for name in ("cfg1", "cfg2", "cfg3", "cfg4"):
+        c = bench.config_dict(WORKLOADS[name])
+        assert c["workload"] == WORKLOADS[name].name and c["params"] > 43_000_000
+    assert bench.config_dict(WORKLOADS["cfg2"])["params"] == 43579868
+    assert bench.eval_config_dict(EVAL_WORKLOADS["cfg5"])["maps"] == 10000
+
+
+def test_eval_sweep_reference_arm():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "tiny_eval"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["metric"] == "miou_eval_sweep_throughput" and d["scaling"] == "strong" and d["dtype"] == "int64"
+    assert d["value"] > 0 and d["config"]["maps"] == 8

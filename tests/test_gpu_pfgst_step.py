@@ -71,7 +71,7 @@ def test_ema_of_the_module_is_bit_exact_given_identical_students(cuda):
 
 def test_kornia_branches_fail_loudly_or_skip(cuda):
     batch = _to(next(iter(step_batches(1))), cuda)
-    m = _build(cuda, blur=True, color_jitter_probability=0.0)
+    m = _build(cuda, blur=True, color_jitter_probability=0.0, kornia_aug='error')
     with pytest.raises(ops.PfstError):
         for _ in range(8):                      # blur is active with probability 1/2 per draw
             m.forward_train(**batch)
@@ -114,3 +114,73 @@ def test_part_threshold_and_prototype_extension(cuda):
     log_vars, _ = m.forward_train(**batch)
     assert np.isfinite(log_vars['loss'])
     assert int(m.proto_bank.seen.sum()) >= 1 and m.proto_bank.iter == 2
+
+
+def _run_steps(m, cuda, n_iters, seed=3):
+    opt = torch.optim.SGD(m.model.parameters(), lr=0.01)
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    logs = []
+    batches = list(step_batches(2))
+    for it in range(n_iters):
+        out = m.train_step(_to(batches[it % 2], cuda), opt)
+        logs.append(out['log_vars'])
+    torch.cuda.synchronize()
+    params = torch.cat([p.detach().reshape(-1) for p in m.model.parameters()]).cpu()
+    ema = torch.cat([p.detach().reshape(-1) for p in m.ema_model.parameters()]).cpu()
+    return logs, params, ema
+
+
+@pytest.mark.parametrize("protos", [False, True])
+def test_fused_launch_groups_equal_the_generic_module_path(cuda, protos, monkeypatch):
+    """The engine's fused groups (CUDA-graph replay from the third pass on) against the generic
+    path — PFGSTLoss autograd module + proto_dist_loss, every kernel launched eagerly: same log
+    variables, same student and teacher after 6 optimizer steps."""
+    extra = dict(prototypes=dict(weight=0.1)) if protos else {}
+    res = {}
+    for name, fused, graphs in (("fused", True, "1"), ("fused_eager", True, "0"), ("generic", False, "0")):
+        monkeypatch.setenv("PFST_PLUGIN_GRAPHS", graphs)
+        m = _build(cuda, fused_hot_path=fused, **extra)
+        res[name] = _run_steps(m, cuda, 6)
+        if name == "fused":
+            assert m._engine._gb.graphs or m._engine._gb.misses > 2     # replay (or moving inputs: eager)
+        m.close()
+    keys = list(res["generic"][0][0].keys())
+    assert 'loss_sim_pos' in keys and ('loss_proto_dist' in keys) == protos
+    for other in ("fused", "fused_eager"):
+        for it, (a, b) in enumerate(zip(res[other][0], res["generic"][0])):
+            assert list(a.keys()) == list(b.keys())
+            for k in a:
+                assert abs(float(a[k]) - float(b[k])) <= 2e-5 * abs(float(b[k])) + 1e-7, (other, it, k, float(a[k]), float(b[k]))
+        assert (res[other][1] - res["generic"][1]).abs().max() <= 1e-5
+        assert (res[other][2] - res["generic"][2]).abs().max() <= 1e-6
+    # graph replay vs eager launches of the same groups: identical kernels on identical inputs
+    for a, b in zip(res["fused"][0], res["fused_eager"][0]):
+        assert [float(v) for v in a.values()] == [float(v) for v in b.values()]
+
+
+def test_log_vars_are_lazy_and_equal_the_reference_arithmetic(cuda):
+    """_parse_losses on device scalars: no host sync until a value is read; `loss` is the
+    left-to-right fp32 sum of the 'loss' keys (base.py:200-202); values equal the tensors."""
+    from pfst_b200.uda.log_ledger import LazyScalar, ledger_for
+    from pfst_b200.uda.uda_decorator import UDADecorator
+    g = torch.Generator().manual_seed(5)
+    vals = torch.randn(5, generator=g)
+    losses = {"decode.loss_ce": vals[0].to(cuda).requires_grad_(True), "decode.acc_seg": vals[1].to(cuda),
+              "aux.loss_ce": (vals[2:4].to(cuda)).requires_grad_(True), "loss_list": [vals[4].to(cuda), vals[0].to(cuda)]}
+    led = ledger_for(cuda)
+    before = led.d2h_bytes
+    loss, lv = UDADecorator._parse_losses(losses)
+    assert led.d2h_bytes == before and all(isinstance(v, LazyScalar) for v in lv.values())
+    want = {"decode.loss_ce": vals[0], "decode.acc_seg": vals[1], "aux.loss_ce": vals[2:4].mean(),
+            "loss_list": vals[4] + vals[0]}
+    ref_loss = sum(v for k, v in want.items() if 'loss' in k)
+    assert list(lv) == list(want) + ["loss"]
+    for k, v in want.items():
+        assert float(lv[k]) == float(v), k
+    assert float(lv["loss"]) == float(ref_loss) == float(loss)
+    assert led.d2h_bytes > before
+    loss.backward()
+    assert float(losses["decode.loss_ce"].grad) == 1.0
+    assert torch.equal(losses["aux.loss_ce"].grad.cpu(), torch.tensor([0.5, 0.5]))
+    tot = led.weighted_total([loss.detach(), losses["decode.acc_seg"]], [1.0, 0.25])
+    assert float(tot) == float(torch.tensor(0.) + ref_loss + vals[1] * 0.25)

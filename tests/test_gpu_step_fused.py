@@ -143,3 +143,51 @@ def test_graph_replay_is_bit_identical_to_eager(cuda):
     for a, b in zip(*outs):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_update_teacher_precedes_the_teacher_forward(cuda):
+    """pfgst.py:203-208 update the EMA teacher BEFORE the teacher pass of the same iteration
+    (:255). With `update_teacher(it)` + `teacher_ready()` in front of a teacher forward that
+    really reads the teacher's weights, two iterations equal the oracle loop in that order."""
+    from oracle import ema as oema
+    wl = WORKLOADS["tiny"]
+    host = step_inputs(wl, 77)
+    g = torch.Generator().manual_seed(8)
+    shapes = [(wl.C,), (33,)]
+    student = [torch.randn(s, generator=g) for s in shapes]
+    teacher = [torch.randn(s, generator=g) for s in shapes]
+    d_student, d_teacher = [p.to(cuda) for p in student], [p.to(cuda) for p in teacher]
+    inp = {k: v.to(cuda) for k, v in host.items()}
+    step = SelfTrainingStep(d_teacher, d_student, wl.C, wl.D, cuda, dilation=wl.dilation, downscale=wl.downscale)
+
+    def teacher_forward(params, base):          # a 'network' whose output depends on the teacher's weights
+        return (base + 3.0 * params[0].view(1, -1, 1, 1)).contiguous()
+
+    state = None
+    for it in range(3):
+        with torch.no_grad():                                     # the optimizer moved the student
+            for p, q in zip(student, d_student):
+                p.add_(0.1 * (it + 1))
+                q.add_(0.1 * (it + 1))
+        step.update_teacher(it)
+        step.teacher_ready()
+        ema_logits = teacher_forward(d_teacher, inp["ema_logits"])
+        np.random.seed(300 + it)
+        out = step.run(it, inp["img"], inp["target_img_strong_aug"], inp["gt"], ema_logits, inp["logits_trg"],
+                       inp["x_src"], inp["x_ema"])
+        # oracle, reference order: EMA first, then the teacher pass, then the rest of the step
+        if it == 0:
+            oema.ema_init(teacher, student)
+        else:
+            oema.ema_update(teacher, student, it, 0.999)
+        h = dict(host)
+        h["ema_logits"] = teacher_forward(teacher, host["ema_logits"])
+        frozen = [t.clone() for t in teacher]
+        ref = ostep.hot_path_step(it, frozen, [t.clone() for t in frozen], h, wl.C, proto_state=state,
+                                  rng=np.random.RandomState(300 + it))    # (its own EMA of identical tensors is a no-op)
+        state = ref["proto_state"]
+        torch.cuda.synchronize()
+        for a, b in zip(d_teacher, teacher):
+            assert torch.equal(a.cpu(), b)
+        assert torch.equal(out["pseudo_label"].cpu(), ref["pseudo_label"]), it
+        assert torch.equal(out["mixed_lbl"].cpu(), ref["mixed_lbl"])

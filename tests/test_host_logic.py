@@ -94,7 +94,9 @@ def test_algorithmic_bytes_match_the_survey_table():
     assert ab["ema"] == 522958416                                         # 12 B x 43 579 868 params
     assert ab["pseudo_label"] == (4 * 6 + 12) * 8 * 512 * 512              # 75.5 MB
     assert ab["neigh_dots"] == 2 * 4 * 512 * 8 * 64 * 64                   # 134.2 MB
-    assert 1.30e9 < sum(ab.values()) < 1.45e9                              # ~1.31 GB + loss maps
+    assert ab["class_presence_and_mix"] == 84 * 8 * 512 * 512              # 176.2 MB (presence inside 84 P)
+    assert ab["proto_dist_fwd_bwd"] == 3 * 4 * 512 * 8 * 64 * 64           # 201 MB for fwd+bwd together
+    assert abs(sum(ab.values()) - 1.3115e9) < 1e6                          # 1.31 GB, nothing else
 
 
 def test_blur_kernel_size_rule_and_sigma_stream():
