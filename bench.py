@@ -402,7 +402,7 @@ def run_ours(args, wl, rank, world, local_rank):
     e2e_steps = max(3, min(args.steps, 20))
     feed.used = [False, False]
     feed.issue(0)
-    for _ in range(3):
+    for _ in range(8):                            # both feed slots: two eager passes + graph capture each
         float(e2e_step()["loss"])
     barrier()
     feed.bytes_copied = 0

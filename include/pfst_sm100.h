@@ -470,6 +470,17 @@ int pfst_gather_scalars(const float* const* ptrs_host, const float* weights_host
                         uint32_t sum_mask, float divisor, float* row_out, float* total_out,
                         void* stream);
 
+/* All _parse_losses calls of one PFGST.forward_train iteration in ONE launch. Entry i (n <= 32)
+ * belongs to the current segment (= one call, entries in call order); flags_host[i] bit0: its key
+ * contains 'loss' (it enters the segment's sum), bit1: last entry of the segment. row_out receives
+ * every entry / divisor and, behind the last entry of each segment, the segment's sum / divisor
+ * (that call's 'loss' log variable): n + (number of segments) floats. total_out (nullable) =
+ * 0 + sum over segments of weights_host[last entry of the segment] * segment sum, left to right
+ * in fp32 — total_loss of rsiseg/models/uda/pfgst.py:237,310,342.                             */
+int pfst_gather_segments(const float* const* ptrs_host, const float* weights_host,
+                         const uint8_t* flags_host, int32_t n, float divisor, float* row_out,
+                         float* total_out, void* stream);
+
 /* out[i] = *ptrs_host[i] * weights_host[i] (0 where the pointer is NULL; weights NULL = 1),
  * i < n <= 32: packs separate 0-dim device scalars — e.g. the upstream gradients autograd hands
  * to the backward of the six PFGSTLoss terms and the prototype distance — into one vector.  */

@@ -193,6 +193,15 @@ class PluginEngine:
     def aux_forward(self, logits_trg, x_src, gt, mix_masks, geo: ops.LossGeometry, want_vis: bool):
         """Loss statistics (+ prototype distance) of this iteration. -> (losses fp32[6] buffer,
         weighted prototype loss fp32[1] buffer | None, density | None, eroded | None)."""
+        plan = self.aux_plan(logits_trg, x_src, gt, mix_masks, geo, want_vis)
+        self.aux_run(plan)
+        b = plan["b"]
+        return b["losses"], (b["ploss_w"] if plan["bank"] is not None else None), b["density"], b["eroded"]
+
+    def aux_plan(self, logits_trg, x_src, gt, mix_masks, geo: ops.LossGeometry, want_vis: bool) -> dict:
+        """Validates the inputs and binds the launch group to its (persistent) output buffers without
+        launching anything: plan['b']['losses'] (fp32[6]) and plan['b']['ploss_w'] (fp32[1]) are where
+        `aux_run(plan)` will leave the six losses and the weighted prototype distance."""
         cfg = self.loss_cfg
         a = self._a
         if a is None or a["dots"] is None:
@@ -214,6 +223,8 @@ class PluginEngine:
                      ploss_w=e((1,), torch.float32),
                      density=e((geo.B, 1, geo.gh, geo.gw), torch.float32) if want_vis else None,
                      eroded=e((geo.B, 1, geo.gh, geo.gw), torch.uint8) if want_vis else None)
+            b["loss_views"] = [b["losses"][i] for i in range(6)]      # 0-dim views handed to the log ledger
+            b["ploss_view"] = b["ploss_w"][0]
             self._bufs[skey] = b
         H, W = gt.shape[-2], gt.shape[-1]
         dots, ks = a["dots"], a["ks"]
@@ -246,13 +257,17 @@ class PluginEngine:
 
         key = skey + (logits_trg.data_ptr(), x_src.data_ptr(), gt.data_ptr(), mix_masks.data_ptr(), dots.data_ptr(),
                       bank is not None)
-        self._gb.run(key, launch)
-        self._token += 1
-        self._fwd = dict(token=self._token, common=common, w6=w6, b=b, geo=geo, bank=bank,
-                         shapes=(Bf, D, h, w, H, W))
-        return b["losses"], (b["ploss_w"] if bank is not None else None), b["density"], b["eroded"]
+        return dict(key=key, launch=launch, common=common, w6=w6, b=b, geo=geo, bank=bank, keep=(pw, pp),
+                    shapes=(Bf, D, h, w, H, W))
 
-    def aux_backward(self, token: int, grads, logits_trg, x_src, gt, need_logits: bool, need_x: bool):
+    def aux_run(self, plan: dict) -> None:
+        self._gb.run(plan["key"], plan["launch"])
+        self._token += 1
+        plan["token"] = self._token
+        self._fwd = plan
+
+    def aux_backward(self, token: int, grads, logits_trg, x_src, gt, need_logits: bool, need_x: bool,
+                     scale=(1.0, 1.0)):
         """grads: 7 upstream gradients (0-dim CUDA fp32 tensors or None) of the six losses and of
         the weighted prototype loss. -> (grad_logits | None, grad_x | None), fresh tensors."""
         f = self._fwd
@@ -270,7 +285,9 @@ class PluginEngine:
             keep.append(g)
             ptrs[i] = g.data_ptr()
         bank, b, geo = f["bank"], f["b"], f["geo"]
-        wts = (C.c_float * 7)(1, 1, 1, 1, 1, 1, float(self.proto_cfg.get('weight', 0.1)) if bank is not None else 0.0)
+        wa, wp = float(scale[0]), float(scale[1])
+        wts = (C.c_float * 7)(wa, wa, wa, wa, wa, wa,
+                              wp * float(self.proto_cfg.get('weight', 0.1)) if bank is not None else 0.0)
         _lib.call("pfst_pack_scalars", ptrs, wts, 7, self._gout.data_ptr(), s)
         Bf, D, h, w, H, W = f["shapes"]
         coef = torch.empty((Bf, 9, h, w), dtype=torch.float32, device=self.device)
@@ -299,24 +316,41 @@ class PluginEngine:
             self.bank.peer = None
 
 
-class AuxTailFn(torch.autograd.Function):
-    """(logits_trg, x_src) -> seven 0-dim values: the six PFGSTLoss terms and the weighted
-    prototype distance (0 without prototypes). Gradients flow to logits_trg (through p only, q
-    detached — detach_unfold=True) and x_src exactly as in the reference's autograd graph."""
+class StepTotalFn(torch.autograd.Function):
+    """total_loss of one PFGST.forward_train iteration (pfgst.py:237,310,342,344) as ONE autograd
+    node: forward = the auxiliary launch group (loss statistics + prototype distance) followed by
+    ONE gather launch that writes every log variable of the iteration into the ledger row and
+    forms total = 0 + clean + mix * trg_loss_weight + aux (+ proto); backward hands the upstream
+    gradient to the loss scalars of the segmentor and runs the auxiliary backward kernels for
+    logits_trg / x_src."""
 
     @staticmethod
-    def forward(ctx, logits_trg, x_src, eng, gt, mix_masks, geo, want_vis):
-        losses, ploss_w, density, eroded = eng.aux_forward(logits_trg, x_src, gt, mix_masks, geo, want_vis)
-        ctx.eng, ctx.token = eng, eng._token
-        ctx.save_for_backward(logits_trg, x_src, gt)
-        ctx.vis = (density, eroded)
-        outs = [losses[i] for i in range(6)]
-        outs.append(ploss_w[0] if ploss_w is not None else losses.new_zeros(()))
-        return tuple(outs)
+    def forward(ctx, eng, rec, plan, gt, idx, logits_trg, x_src, *vals):
+        if plan is not None:
+            eng.aux_run(plan)
+        total = torch.empty((), dtype=torch.float32, device=eng.device)
+        rec.launch(total)
+        ctx.eng, ctx.rec, ctx.idx = eng, rec, idx
+        ctx.token = plan["token"] if plan is not None else None
+        ctx.gt = gt
+        if plan is not None:
+            ctx.save_for_backward(logits_trg, x_src)
+        return total
 
     @staticmethod
-    def backward(ctx, *grads):
-        logits_trg, x_src, gt = ctx.saved_tensors
-        glog, gx = ctx.eng.aux_backward(ctx.token, grads, logits_trg, x_src, gt, ctx.needs_input_grad[0],
-                                        ctx.needs_input_grad[1])
-        return glog, gx, None, None, None, None, None
+    def backward(ctx, g):
+        rec = ctx.rec
+        out = []
+        for j, i in enumerate(ctx.idx):
+            if not ctx.needs_input_grad[7 + j]:
+                out.append(None)
+                continue
+            w = rec.segment_weight(i)
+            out.append(g if w == 1.0 else g * w)
+        glog = gx = None
+        if ctx.token is not None:
+            logits_trg, x_src = ctx.saved_tensors
+            w_aux, w_proto = rec.aux_weights
+            glog, gx = ctx.eng.aux_backward(ctx.token, [g] * 7, logits_trg, x_src, ctx.gt, ctx.needs_input_grad[5],
+                                            ctx.needs_input_grad[6], scale=(w_aux, w_proto))
+        return (None, None, None, None, None, glog, gx, *out)

@@ -197,27 +197,65 @@ class SelfTrainingStep:
         return self._world > 1
 
     def _whole_step(self, b, args_a, args_b, reduce: bool = False):
-        """Segment A, proto_finalize (device-resident iteration) and segment B as one stream-ordered
-        sequence — ONE CUDA graph per step. reduce=True (multi-rank): the NCCL all-reduce of the
-        packed [sums|counts] buffer and proto_finalize run on a forked branch next to ClassMix and
-        neigh_dots(x_src); only the prototype distance waits for them."""
-        self._segment_a(b, *args_a)
-        if not reduce:
-            self.bank.finalize_captured(ops._stream(), local_only=True)
-            self._segment_b(b, *args_b, part="all")
-            return
-        import torch.distributed as dist
+        """The whole step as ONE stream-ordered DAG (one CUDA graph per step) with its true data
+        dependencies — three branches forked from the current stream:
+
+          side    neigh_dots(x_ema) -> neigh_dots(x_src)                      (inputs only)
+          proto   [pseudo_label] -> label sort -> proto_accum(x_ema) -> (cross-rank sum) ->
+                  proto_finalize -> proto_dist_fwd(x_src)                     P1, P2, P3 forward
+          main    pseudo_label -> class_mix -> [dots] -> loss prep/fwd -> loss bwd ->
+                  [proto] -> neigh_grad + proto_dist_bwd                      S, M2, L, backward
+
+        ClassMix and the loss statistics never wait for the prototypes; only the fused backward pass
+        does. reduce=True (multi-rank): the cross-rank sum is the peer-board exchange inside the
+        finalise kernel (csrc/peer.cu) or, without a board, an ncclAllReduce in front of it."""
+        ema_logits, x_ema, geo = args_a
+        img, trg_img, gt, chosen, logits_trg, x_src, _ = args_b
+        B, C, H, W = ema_logits.shape
+        Bf, D, h, w = x_src.shape
+        bank = self.bank
         main = torch.cuda.current_stream()
-        fork, mu_ready = self._ev[8], self._ev[9]
+        s = main.cuda_stream
+        fork, dots_ema, dots_src, pl_done, proto_done = (self._ev[i] for i in (0, 1, 2, 3, 4))
         fork.record(main)
-        self._comm.wait_event(fork)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
+            dots_ema.record(self._side)
+            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
+            dots_src.record(self._side)
+        _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
+                  b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
+        pl_done.record(main)
+        self._comm.wait_event(pl_done)
         with torch.cuda.stream(self._comm):
-            if self.bank.peer is None:
-                dist.all_reduce(self.bank.packed, op=dist.ReduceOp.SUM, group=self.bank.group)
-            # peer board: push + token wait + rank-ordered sum + finalise in this ONE kernel
-            self.bank.finalize_captured(self._comm.cuda_stream)
-            mu_ready.record(self._comm)
-        self._segment_b(b, *args_b, part="all", mu_ready=mu_ready)
+            bank.order(b.label, Bf, h, w)                             # label sort: 1 block / tile
+            self._comm.wait_event(dots_ema)
+            bank.accumulate_ordered(x_ema)                            # x_ema again: L2 hits
+            if reduce and bank.peer is None:
+                import torch.distributed as dist
+                dist.all_reduce(bank.packed, op=dist.ReduceOp.SUM, group=bank.group)
+            bank.finalize_captured(self._comm.cuda_stream, local_only=not reduce)
+            self._comm.wait_event(dots_src)
+            _lib.call("pfst_proto_dist_fwd", x_src.data_ptr(), Bf, D, h, w, gt.data_ptr(), H, W,
+                      bank.mu.data_ptr(), bank.seen.data_ptr(), self.C, b.dist.data_ptr(), b.acc.data_ptr(),
+                      b.ploss.data_ptr(), self._comm.cuda_stream)
+            proto_done.record(self._comm)
+        _lib.call("pfst_class_mix", gt.data_ptr(), chosen.data_ptr(), img.data_ptr(), trg_img.data_ptr(),
+                  b.label.data_ptr(), None, b.count.data_ptr(), b.label.numel(), 0, 0, B, img.shape[1], H, W,
+                  b.mixed_img.data_ptr(), b.mixed_lbl.data_ptr(), b.weight.data_ptr(), b.mix_mask.data_ptr(), s)
+        main.wait_event(dots_src)
+        w6 = ops._w6(self.w6)
+        common = (b.dots.data_ptr(), b.ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C,
+                  geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h,
+                  geo.gt_w, geo.dilation, int(self.top_k), w6, b.ws.data_ptr(), b.stats.data_ptr())
+        _lib.call("pfst_pfgst_loss_fwd", *common, b.losses.data_ptr(), None, None, s)
+        _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
+                  b.grad_logits.data_ptr(), s)
+        main.wait_event(proto_done)
+        _lib.call("pfst_neigh_grad_proto", x_src.data_ptr(), b.coef.data_ptr(), Bf, D, h, w,
+                  geo.dilation // geo.up, gt.data_ptr(), H, W, bank.mu.data_ptr(), bank.seen.data_ptr(),
+                  self.C, b.dist.data_ptr(), b.acc.data_ptr(), self.gproto.data_ptr(), b.grad_x.data_ptr(), s)
 
     def _captured(self, key, b, args_a, args_b, parts):
         """CUDA graphs for one set of input addresses, captured after a warm-up pass on a side

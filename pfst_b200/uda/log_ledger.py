@@ -289,6 +289,67 @@ class LogLedger:
         return float(row[idx])
 
 
+class StepRecord:
+    """The _parse_losses calls of ONE forward_train iteration, gathered by a single launch
+    (`pfst_gather_segments`): `add()` only registers pointers and returns the lazy log values;
+    `launch()` — issued by engine.StepTotalFn once every scalar has been produced — writes the
+    ledger row and the iteration's total loss."""
+
+    def __init__(self, ledger: "LogLedger"):
+        self.ledger = ledger
+        self.tensors, self.flags, self.weights, self.seg_of = [], [], [], []
+        self.n_seg = 0
+        self.seg_weights = []
+        self.aux_weights = (1.0, 1.0)      # segment weights of the PFGSTLoss terms / the prototype distance
+        self.base = ledger.fill
+
+    def add(self, losses, weight: float = 1.0):
+        led = self.ledger
+        names = []
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                v = value if value.dim() == 0 and value.dtype == torch.float32 else value.mean()
+            elif isinstance(value, list):
+                v = sum(_l.mean() for _l in value)
+            else:
+                raise TypeError(f'{name} is not a tensor or list of tensors')
+            if v.dtype != torch.float32:
+                v = v.float()
+            if not v.is_cuda or v.numel() != 1:
+                raise TypeError("_parse_losses: log variables must be CUDA scalars on the fused path")
+            names.append(name)
+            self.tensors.append(v)
+            self.flags.append(1 if 'loss' in name else 0)
+            self.weights.append(0.0)
+            self.seg_of.append(self.n_seg)
+        if not names:
+            raise ValueError("_parse_losses: empty loss dict")
+        if len(self.tensors) > MAX_SCALARS or led.fill + len(self.tensors) + self.n_seg + 1 > led.rows.shape[1]:
+            raise ValueError("_parse_losses: too many log variables in one iteration")
+        led._length_check(names, self.tensors[-1].device)
+        self.flags[-1] |= 2
+        self.weights[-1] = float(weight)
+        self.seg_weights.append(float(weight))
+        first = self.base + len(self.tensors) - len(names) + self.n_seg
+        self.n_seg += 1
+        log_vars = OrderedDict((n, LazyScalar(led, led.seq, first + i)) for i, n in enumerate(names))
+        log_vars['loss'] = LazyScalar(led, led.seq, first + len(names))
+        return log_vars
+
+    def segment_weight(self, i: int) -> float:
+        return self.seg_weights[self.seg_of[i]] if self.flags[i] & 1 else 0.0
+
+    def launch(self, total: torch.Tensor) -> None:
+        led, n = self.ledger, len(self.tensors)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self.tensors])
+        w = (C.c_float * n)(*self.weights)
+        fl = (C.c_uint8 * n)(*self.flags)
+        row = led.rows[led.seq % led.ROWS]
+        _lib.call("pfst_gather_segments", ptrs, w, fl, n, float(led.world), row.data_ptr() + 4 * self.base,
+                  total.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        led.fill = self.base + n + self.n_seg
+
+
 _ledgers: dict = {}
 
 

@@ -36,12 +36,12 @@ from torch.nn.modules.dropout import _DropoutNd
 from .. import losses as _losses  # noqa: F401  (registers PFGSTLoss in LOSSES)
 from .. import ops
 from .._lib import PfstError
-from ..engine import LOSS_KEYS, AuxTailFn, PluginEngine
+from ..engine import LOSS_KEYS, PluginEngine, StepTotalFn
 from ..losses.pfgst_loss import PFGSTLoss
 from ..prototypes import PrototypeBank, proto_dist_loss
 from ..registry import UDA, build_loss
 from ..utils.dacs_transforms import ClassMixPlan, draw_color_jitter, gaussian_blur_batch, get_mean_std
-from .log_ledger import ledger_for
+from .log_ledger import StepRecord, ledger_for
 from .uda_decorator import UDADecorator, build_model, get_module
 
 
@@ -125,6 +125,7 @@ class PFGST(UDADecorator):
         self._engine = None            # PluginEngine: the fused launch groups (built on first use)
         self._aux_stream = None        # high-priority stream of the class-presence read
         self._teacher_eval_modules = None
+        self._geo_cache = {}
         self.fused = cfg.get('fused_hot_path', True)
 
     # ------------------------------------------------------------------ accessors
@@ -135,12 +136,30 @@ class PFGST(UDADecorator):
         return get_module(self.imnet_model)
 
     # ------------------------------------------------------------------------ EMA
+    TABLE_RECHECK = 64     # iterations between full pointer checks of the 2 x 214 parameter tensors
+
     def _table(self):
+        """The (teacher, student) pointer table of the multi-tensor EMA kernel. Parameter objects and
+        their storage are stable while an optimizer updates them in place, so the table is built once;
+        every call spot-checks the first and last tensor, every TABLE_RECHECK-th call (and any call
+        after the module was moved or cast through `_apply`) re-walks all parameters."""
+        t = self._ema_table
+        self._table_calls = getattr(self, "_table_calls", 0) + 1
+        if t is not None and self._table_calls % self.TABLE_RECHECK:
+            (e0, e1), (p0, p1) = self._table_spot
+            if (e0.data_ptr(), e1.data_ptr(), p0.data_ptr(), p1.data_ptr()) == self._table_spot_ptrs:
+                return t
         ema_p = list(self.get_ema_model().parameters())
         stu_p = list(self.get_model().parameters())
-        if self._ema_table is None or self._ema_table.stale(ema_p, stu_p):
-            self._ema_table = ops.EmaTable(ema_p, stu_p)
-        return self._ema_table
+        if t is None or t.stale(ema_p, stu_p):
+            self._ema_table = t = ops.EmaTable(ema_p, stu_p)
+        self._table_spot = ((ema_p[0], ema_p[-1]), (stu_p[0], stu_p[-1]))
+        self._table_spot_ptrs = (ema_p[0].data_ptr(), ema_p[-1].data_ptr(), stu_p[0].data_ptr(), stu_p[-1].data_ptr())
+        return t
+
+    def _apply(self, fn, *args, **kwargs):
+        self._ema_table = None          # .to() / .cuda() / .half() re-allocate the parameters
+        return super()._apply(fn, *args, **kwargs)
 
     def _init_ema_weights(self):
         """pfgst.py:105-114 — teacher <- student, one launch."""
@@ -271,9 +290,15 @@ class PFGST(UDADecorator):
         if self.use_decoded_feats:
             src_feats = clean_losses.pop('decoded_features')
         src_logits = clean_losses.pop('logits')
-        clean_loss, clean_log_vars = self._parse_losses(clean_losses)
-        log_vars.update(clean_log_vars)
-        parts.append(clean_loss); part_w.append(1.0)
+        single_feats = isinstance(src_feats, torch.Tensor)
+        fused = loss_mod is not None and single_feats
+        rec = StepRecord(ledger) if fused else None     # fused path: ONE gather launch for the whole iteration
+        if fused:
+            log_vars.update(rec.add(clean_losses, 1.0))
+        else:
+            clean_loss, clean_log_vars = self._parse_losses(clean_losses)
+            log_vars.update(clean_log_vars)
+            parts.append(clean_loss); part_w.append(1.0)
 
         # ④ teacher on target (pfgst.py:247-257) — after the EMA update of this iteration
         self._freeze_teacher_dropout()
@@ -285,14 +310,19 @@ class PFGST(UDADecorator):
 
         # ⑤ pseudo labels (pfgst.py:259-277) ║ neighbourhood dots of x_ema -> prototypes (P1/P2)
         thr, thr_vec = self._threshold_args(dev)
-        single_feats = isinstance(ema_feats, torch.Tensor) and isinstance(src_feats, torch.Tensor)
-        fused = loss_mod is not None and single_feats
+        single_feats = single_feats and isinstance(ema_feats, torch.Tensor)
+        if fused and not single_feats:
+            raise PfstError("PFGSTLoss(feat_level=None) needs single feature maps from both passes")
         if self.proto_cfg is not None and not single_feats:
             raise PfstError("prototypes need use_decoded_feats=True (a single (B,D,h,w) feature map)")
         geo = None
         if fused:
-            geo = ops.LossGeometry(src_logits.shape, src_feats.shape, gt_semantic_seg.shape, loss_mod.downscale,
-                                   loss_mod.dilation)
+            gkey = (src_logits.shape, src_feats.shape, gt_semantic_seg.shape)
+            geo = self._geo_cache.get(gkey)
+            if geo is None:
+                geo = self._geo_cache[gkey] = ops.LossGeometry(src_logits.shape, src_feats.shape,
+                                                               gt_semantic_seg.shape, loss_mod.downscale,
+                                                               loss_mod.dilation)
             if ema_feats.shape != src_feats.shape:
                 raise PfstError("PFGSTLoss: x_ema / x_src shape mismatch")
         x_ema = ema_feats.detach().contiguous() if (fused or self.proto_cfg is not None) else None
@@ -331,25 +361,29 @@ class PFGST(UDADecorator):
         mixed_feats = mix_losses.pop('features')
         mixed_logits = mix_losses.pop('logits')
         mix_losses = add_prefix(mix_losses, 'mix')
-        mix_loss, mix_log_vars = self._parse_losses(mix_losses)
-        log_vars.update(mix_log_vars)
-        parts.append(mix_loss); part_w.append(float(self.trg_loss_weight))
+        if fused:
+            log_vars.update(rec.add(mix_losses, float(self.trg_loss_weight)))
+        else:
+            mix_loss, mix_log_vars = self._parse_losses(mix_losses)
+            log_vars.update(mix_log_vars)
+            parts.append(mix_loss); part_w.append(float(self.trg_loss_weight))
 
         # ⑨ auxiliary losses (pfgst.py:333-342) + P3
         if fused:
-            outs = AuxTailFn.apply(mixed_logits.contiguous(), src_feats.contiguous(), eng, gt_semantic_seg,
-                                   mix_masks, geo, self.compute_vis)
-            aux_loss, aux_log_vars = self._parse_losses({k: outs[i] for i, k in enumerate(LOSS_KEYS)})
-            log_vars.update(aux_log_vars)
-            parts.append(aux_loss); part_w.append(1.0)
-            if self.compute_vis:
-                fb = eng._fwd["b"]
-                vis_states['vis|density_sim_feat'] = (mixed_img, fb["density"].clone(), fb["eroded"].bool())
+            mixed_logits_c, src_feats_c = mixed_logits.contiguous(), src_feats.contiguous()
+            plan = eng.aux_plan(mixed_logits_c, src_feats_c, gt_semantic_seg, mix_masks, geo, self.compute_vis)
+            fb = plan["b"]
+            log_vars.update(rec.add(dict(zip(LOSS_KEYS, fb["loss_views"])), 1.0))
             if self.proto_cfg is not None:
                 self.proto_bank = eng.bank
-                p_loss, p_log_vars = self._parse_losses({'loss_proto_dist': outs[6]})
-                log_vars.update(p_log_vars)
-                parts.append(p_loss); part_w.append(1.0)
+                log_vars.update(rec.add({'loss_proto_dist': fb["ploss_view"]}, 1.0))
+            # ⑩ total = 0 + clean + mix*w + aux (+ proto) (pfgst.py:237,310,342): one autograd node whose
+            # forward is the auxiliary launch group + ONE gather launch for every log variable
+            idx = [i for i, t in enumerate(rec.tensors) if t.requires_grad]
+            total_loss = StepTotalFn.apply(eng, rec, plan, gt_semantic_seg, idx, mixed_logits_c, src_feats_c,
+                                           *[rec.tensors[i] for i in idx])
+            if self.compute_vis:
+                vis_states['vis|density_sim_feat'] = (mixed_img, fb["density"].clone(), fb["eroded"].bool())
         else:
             tensors = dict(
                 img_src=img, img_src_metas=img_metas, img_trg=mixed_img, img_mixed=mixed_img,
@@ -372,8 +406,8 @@ class PFGST(UDADecorator):
                 log_vars.update(p_log_vars)
                 parts.append(p_loss); part_w.append(1.0)
 
-        # ⑩ backward (pfgst.py:344): total = 0 + clean + mix*w + aux (+ proto), one launch
-        total_loss = ledger.weighted_total(parts, part_w)
+            # ⑩ total = 0 + clean + mix*w + aux (+ proto), one launch
+            total_loss = ledger.weighted_total(parts, part_w)
         ledger.end()
         total_loss.backward()
 

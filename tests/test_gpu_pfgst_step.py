@@ -154,8 +154,10 @@ def test_fused_launch_groups_equal_the_generic_module_path(cuda, protos, monkeyp
         assert (res[other][1] - res["generic"][1]).abs().max() <= 1e-5
         assert (res[other][2] - res["generic"][2]).abs().max() <= 1e-6
     # graph replay vs eager launches of the same groups: identical kernels on identical inputs
+    # (the tiny segmentor's cuDNN passes are not bit-reproducible run to run, so not an exact comparison)
     for a, b in zip(res["fused"][0], res["fused_eager"][0]):
-        assert [float(v) for v in a.values()] == [float(v) for v in b.values()]
+        for k in a:
+            assert abs(float(a[k]) - float(b[k])) <= 1e-6 * abs(float(b[k])) + 1e-8, k
 
 
 def test_log_vars_are_lazy_and_equal_the_reference_arithmetic(cuda):
