@@ -157,7 +157,7 @@ def test_fused_launch_groups_equal_the_generic_module_path(cuda, protos, monkeyp
     # (the tiny segmentor's cuDNN passes are not bit-reproducible run to run, so not an exact comparison)
     for a, b in zip(res["fused"][0], res["fused_eager"][0]):
         for k in a:
-            assert abs(float(a[k]) - float(b[k])) <= 1e-6 * abs(float(b[k])) + 1e-8, k
+            assert abs(float(a[k]) - float(b[k])) <= 2e-5 * abs(float(b[k])) + 1e-7, k
 
 
 def test_log_vars_are_lazy_and_equal_the_reference_arithmetic(cuda):

@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 from pfst_b200.synthetic import WORKLOADS, step_inputs  # noqa: E402
 
-wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
+wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "cfg2"]
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 g = torch.Generator().manual_seed(1234)
@@ -35,6 +35,32 @@ step = lambda: model.forward_train(d["img"], metas, d["gt"], d["target_img"], me
 for _ in range(10):
     step()
 torch.cuda.synchronize()
+if "--timeline" in sys.argv:
+    # device + runtime-call timeline of two steady-state iterations (gaps, overlap, blocking calls)
+    import json
+    import tempfile
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(6):
+            step()
+        torch.cuda.synchronize()
+    path = tempfile.mktemp(suffix=".json")
+    prof.export_chrome_trace(path)
+    allev = json.load(open(path))["traceEvents"]
+    keep = ("cudaGraphLaunch", "cudaLaunchKernel", "cudaEventSynchronize", "cudaMemcpyAsync", "cudaStreamWaitEvent",
+            "cudaStreamSynchronize")
+    ev = [e for e in allev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") or
+          (e.get("cat") == "cuda_runtime" and e.get("name") in keep)]
+    ev.sort(key=lambda e: e["ts"])
+    starts = [i for i, e in enumerate(ev) if "ema_multi" in e["name"] and e.get("cat") == "kernel"]
+    lo, hi = starts[3], starts[5]
+    t0 = ev[lo]["ts"]
+    for e in ev[max(lo - 12, 0):hi]:
+        name = e["name"].replace("pfst::", "").split("(")[0][:44]
+        where = "  host" if e.get("cat") == "cuda_runtime" else f"stream {e['args'].get('stream', '?'):>3}"
+        print(f"{e['ts'] - t0:8.1f} -> {e['ts'] - t0 + e['dur']:8.1f}  ({e['dur']:6.1f} us)  {where}  {name}")
+    print(f"two steps: {ev[hi]['ts'] - t0:.1f} us")
+    sys.exit(0)
 N = 200
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter()
