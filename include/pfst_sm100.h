@@ -458,6 +458,33 @@ int pfst_color_jitter(const float* in, float* out, int64_t n_images, int64_t HW,
                       const float* factors_host, const int32_t* order_host,
                       const float* mean_host, const float* std_host, int32_t denorm, void* stream);
 
+/* ---- offline class-wise pseudo-labelling, remaining pieces -------------
+ * pfst_loc_dis: PseudoLabelingHookV4._cal_loc_dis (rsiseg/core/hook/pseudo_labeling_hookv4.py:208-230)
+ *   out[b,y,x,k] = sum_c (feats[b,c,y+dy_k*d,x+dx_k*d] - feats[b,c,y,x])^2, k over the 3x3 taps,
+ *   zero padding (an out-of-image tap reads 0). feats (B,C,H,W) fp32 -> out (B,H,W,9) fp32; the
+ *   nn.Unfold copy (9x the feature map) never exists.
+ * pfst_gather_rows: dst[i,:] = src[idx[i],:] — the random pixel subset `cur_tensor[idx, :]` (:255-256),
+ *   idx drawn on the host from the numpy stream.
+ * pfst_sigma_bisect: the binary search of _cal_sigmas (:262-275) for ONE mean_sim: `steps` times
+ *   sigma = (left+right)/2; mean(exp(-dis / sigma^2)) < mean_sim ? left = sigma : right = sigma
+ *   (the reference's `while abs(left-right) > 1e-6` from [0,1000] is exactly 30 steps). The interval
+ *   lives in state = device double[4] {left, right, scratch, scratch}: one launch per step, no host
+ *   sync inside the search. dis: n fp32 values, 16-byte aligned. Result: state[0] (left).
+ * pfst_loader_pseudo_labels: the label rule of LoadAnnotationsPseudoLabelsV2.__call__
+ *   (rsiseg/datasets/pipelines/loading.py:474-487) for N maps at once: pred = argmax_c logits;
+ *   p = exp(logits)/sum exp(logits) (no max shift, as the loader); H = -sum p log(p + 1e-8);
+ *   label = H < thres[pred] ? pred : 255; reduce_zero_label: 0 -> 255, label-1, 254 -> 255.
+ *   logits (N,C,HW) fp32, thres C fp32 (device) -> labels (N,HW) uint8.                          */
+int pfst_loc_dis(const float* feats, int64_t B, int32_t C, int32_t H, int32_t W, int32_t dilation,
+                 float* out, void* stream);
+int pfst_gather_rows(const float* src, const int64_t* idx, int64_t n, int32_t row_floats, float* dst,
+                     void* stream);
+int pfst_sigma_bisect(const float* dis, int64_t n, float mean_sim, double left0, double right0,
+                      int32_t steps, double* state, void* stream);
+int pfst_loader_pseudo_labels(const float* logits, int64_t N, int32_t C, int64_t HW,
+                              const float* thres, int32_t reduce_zero_label, uint8_t* labels,
+                              void* stream);
+
 /* ---- log variables without host round trips ------------------------------
  * Replaces the arithmetic of BaseSegmentor._parse_losses
  * (rsiseg/models/segmentors/base.py:177-222): `loss = sum(v for k, v in log_vars if 'loss' in k)`

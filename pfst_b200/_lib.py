@@ -69,6 +69,10 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_peer_free": (C.c_int, [_vp]),
     "pfst_proto_finalize_peer": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                            _vp, _i64, _vp]),
+    "pfst_loc_dis": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pfst_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "pfst_sigma_bisect": (C.c_int, [_vp, _i64, _f32, _f64, _f64, _i32, _vp, _vp]),
+    "pfst_loader_pseudo_labels": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp]),
     "pfst_gather_scalars": (C.c_int, [_vp, _vp, _i32, C.c_uint32, _f32, _vp, _vp, _vp]),
     "pfst_gather_segments": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp]),
     "pfst_pack_scalars": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),

@@ -291,7 +291,63 @@ def gen_strong_aug():
     np.savez_compressed(OUT / "strong_aug.npz", **out)
 
 
+def offline_label_cases():
+    """(name, n_images, C_feat, H, W, dilations, mean_sims, sample_ratio, seed)"""
+    return [("a", 3, 16, 16, 16, [1, 2], [0.5, 0.8], 0.5, 0), ("b", 2, 24, 12, 20, [2], [0.6], 1.0, 1)]
+
+
+def offline_label_feats(n, C, H, W, seed):
+    g = torch.Generator().manual_seed(900 + seed)
+    return [[torch.relu(torch.randn((C, H, W), generator=g)), torch.relu(torch.randn((C // 2, H // 2, W // 2), generator=g))]
+            for _ in range(n)]
+
+
+def loader_rule_cases():
+    """(name, C, H, W, reduce_zero_label, seed)"""
+    return [("plain", 6, 24, 20, False, 0), ("rz", 6, 24, 20, True, 1), ("many", 33, 15, 15, False, 2)]
+
+
+def loader_rule_inputs(C, H, W, seed):
+    from pfst_b200.synthetic import teacher_logits
+    g = torch.Generator().manual_seed(700 + seed)
+    logits = (0.5 * teacher_logits(1, C, H, W, g)[0]).numpy()
+    logits[:, 0, 0] = 1.25                       # exact tie: first index
+    thres = (0.2 + 1.2 * torch.rand(C, generator=g)).numpy().astype(np.float32)
+    thres[C - 1] = 0.0                           # a class the hook never saw
+    return logits, thres
+
+
+def gen_offline_labels():
+    """_cal_loc_dis / _cal_sigmas of PseudoLabelingHookV4 and the label rule of
+    LoadAnnotationsPseudoLabelsV2.__call__, compiled from the reference sources."""
+    import types
+    loc, sig = R.hook_sigma_fns()
+    out = {}
+    for name, n, C, H, W, dils, means, ratio, seed in offline_label_cases():
+        me = types.SimpleNamespace(sim_feat_cfg=dict(kernel_size=3, sigmas=None, dilation=dils, mean_sim=means,
+                                                     feat_level=[0, 1]))
+        with R.cpu_cuda_identity():
+            lds = [loc(me, f) for f in offline_label_feats(n, C, H, W, seed)]
+        for i, ld in enumerate(lds):
+            for k, v in ld.items():
+                out[f"{name}_locdis_{i}_{k}"] = v.numpy()
+        np.random.seed(40 + seed)
+        for k, v in sig(me, lds, ratio).items():
+            out[f"{name}_sigma_{k}"] = np.float64(v)
+    cls, reg = R.loader_pseudo_labels_cls()
+    for name, C, H, W, rz, seed in loader_rule_cases():
+        logits, thres = loader_rule_inputs(C, H, W, seed)
+        reg['/golden/x.h5'] = {'seg_logits': logits, 'thre@0.5': thres}
+        res = cls(pseudo_labels_dir='/golden', pseudo_ratio=0.5, reduce_zero_label=rz)(
+            dict(img_info=dict(filename='d/x.png'), seg_fields=[], img_shape=(H, W)))
+        out[f"loader_{name}"] = res['gt_semantic_seg']
+    np.savez_compressed(OUT / "offline_labels.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "offline_labels":
+        gen_offline_labels()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "strong_aug":
         gen_strong_aug()
         sys.exit(0)
@@ -304,7 +360,8 @@ if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug):
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
+               gen_offline_labels):
         fn()
         print("wrote", fn.__name__)
     for p in sorted(OUT.glob("*.npz")):

@@ -127,6 +127,54 @@ def cal_threshold_fn():
     return _cache["calthr"]
 
 
+def hook_sigma_fns():
+    """(PseudoLabelingHookV4._cal_loc_dis, ._cal_sigmas) compiled straight from the reference source
+    (rsiseg/core/hook/pseudo_labeling_hookv4.py:208-277); `tqdm.tqdm` is the identity here."""
+    if "hooksig" not in _cache:
+        import ast
+        import numpy as np
+        import torch
+        tree = ast.parse((REF_ROOT / "rsiseg/core/hook/pseudo_labeling_hookv4.py").read_text())
+        fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in ("_cal_loc_dis", "_cal_sigmas")]
+        ns = {"np": np, "torch": torch, "tqdm": types.SimpleNamespace(tqdm=lambda it, *a, **k: it)}
+        exec(compile(ast.Module(body=fns, type_ignores=[]), "ref:pseudo_labeling_hookv4.py:_cal_sigmas", "exec"), ns)
+        _cache["hooksig"] = (ns["_cal_loc_dis"], ns["_cal_sigmas"])
+    return _cache["hooksig"]
+
+
+class _FakeH5File(dict):
+    """Stands in for h5py.File(path, 'r') in the loader: a dict of datasets registered by path."""
+    registry: dict = {}
+
+    def __init__(self, path, mode='r'):
+        super().__init__(_FakeH5File.registry[path])
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+
+def loader_pseudo_labels_cls():
+    """-> (LoadAnnotationsPseudoLabelsV2 compiled from rsiseg/datasets/pipelines/loading.py:391-526,
+    the registry dict its fake `h5py.File` reads from: {path: {'seg_logits': ..., 'thre@r': ...}})."""
+    if "loadercls" not in _cache:
+        import ast
+        import os.path as osp
+        import numpy as np
+        tree = ast.parse((REF_ROOT / "rsiseg/datasets/pipelines/loading.py").read_text())
+        cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "LoadAnnotationsPseudoLabelsV2")
+        cls.decorator_list = []
+        ns = {"np": np, "osp": osp, "h5py": types.SimpleNamespace(File=_FakeH5File)}
+        exec(compile(ast.Module(body=[cls], type_ignores=[]), "ref:loading.py:LoadAnnotationsPseudoLabelsV2", "exec"), ns)
+        _cache["loadercls"] = (ns["LoadAnnotationsPseudoLabelsV2"], _FakeH5File.registry)
+    return _cache["loadercls"]
+
+
 def simple_test_fns():
     """-> (inference, simple_test): EncoderDecoder.inference / simple_test compiled straight from
     the reference source file (rsiseg/models/segmentors/encoder_decoder.py:283-353; its module

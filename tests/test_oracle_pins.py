@@ -189,6 +189,53 @@ def test_class_threshold_oracle_equals_reference_live():
             assert np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)), k
 
 
+# ------------------------------------------------------------------ offline labels: sigma search, loader rule
+def test_offline_labels_oracle_vs_golden():
+    """oracle.offline_labels vs the fixture written by PseudoLabelingHookV4._cal_loc_dis/_cal_sigmas and
+    LoadAnnotationsPseudoLabelsV2.__call__ (tests/golden/make_golden.py::gen_offline_labels)."""
+    from oracle import offline_labels as OL
+    from tests.golden.make_golden import (loader_rule_cases, loader_rule_inputs, offline_label_cases,
+                                          offline_label_feats)
+    z = load("offline_labels.npz")
+    for name, n, C, H, W, dils, means, ratio, seed in offline_label_cases():
+        lds = [OL.cal_loc_dis(f, 3, dils) for f in offline_label_feats(n, C, H, W, seed)]
+        for i, ld in enumerate(lds):
+            for k, v in ld.items():
+                assert np.array_equal(v.numpy(), z[f"{name}_locdis_{i}_{k}"]), (name, i, k)
+        sig = OL.cal_sigmas(lds, [0, 1], dils, means, ratio, np.random.RandomState(40 + seed))
+        assert len(sig) == 2 * len(dils) * len(means)
+        for k, v in sig.items():
+            assert v == float(z[f"{name}_sigma_{k}"]), (name, k)
+    for name, C, H, W, rz, seed in loader_rule_cases():
+        logits, thres = loader_rule_inputs(C, H, W, seed)
+        assert np.array_equal(OL.loader_pseudo_labels(logits, thres, rz), z[f"loader_{name}"]), name
+
+
+@needs_ref
+def test_offline_labels_oracle_equals_reference_live():
+    import types
+    from oracle import offline_labels as OL
+    loc, sig = R.hook_sigma_fns()
+    g = torch.Generator().manual_seed(11)
+    me = types.SimpleNamespace(sim_feat_cfg=dict(kernel_size=3, sigmas=None, dilation=[1, 3], mean_sim=0.7, feat_level=[0]))
+    with R.cpu_cuda_identity():
+        feats = [[torch.relu(torch.randn((10, 9, 14), generator=g))] for _ in range(2)]
+        a = [loc(me, f) for f in feats]
+    b = [OL.cal_loc_dis(f, 3, [1, 3]) for f in feats]
+    assert all(torch.equal(x[k], y[k]) for x, y in zip(a, b) for k in x)
+    np.random.seed(5)
+    assert sig(me, a, 0.8) == OL.cal_sigmas(b, [0], [1, 3], 0.7, 0.8, np.random.RandomState(5))
+    cls, reg = R.loader_pseudo_labels_cls()
+    logits = (2 * torch.randn((5, 9, 7), generator=g)).numpy()
+    logits[1, 2, 3] = np.nan
+    thres = np.array([0.5, 1.0, 0.2, 0.0, 0.9], dtype=np.float32)
+    for rz in (False, True):
+        reg['/p/q.h5'] = {'seg_logits': logits, 'thre@0.3': thres}
+        res = cls(pseudo_labels_dir='/p', pseudo_ratio=0.3, reduce_zero_label=rz)(
+            dict(img_info=dict(filename='q.tif'), seg_fields=[], img_shape=(9, 7)))
+        assert np.array_equal(res['gt_semantic_seg'], OL.loader_pseudo_labels(logits, thres, rz))
+
+
 # ------------------------------------------------------------------ on-device evaluation path
 def test_eval_logits_oracle_vs_golden():
     """oracle simple_test + pre_eval restatement vs the fixture written by the reference's own
