@@ -171,13 +171,12 @@ class PluginEngine:
                       None if thr_vec is None else thr_vec.data_ptr(), 0, -1, b["label"].data_ptr(),
                       b["conf"].data_ptr(), None if b["wpart"] is None else b["wpart"].data_ptr(),
                       b["count"].data_ptr(), main.cuda_stream)
+            if dots_here:
+                main.wait_event(self._ev[3])             # the label sort never runs next to a TMA dots kernel (step.py)
             if bank is not None:
                 Bf, D, h, w = x_ema.shape
                 bank.order(b["label"], Bf, h, w, b["conf"] if conf_thr is not None else None,
                            conf_thr if conf_thr is not None else 0.0)
-            if dots_here:
-                main.wait_event(self._ev[3])
-            if bank is not None:
                 bank.accumulate_ordered(x_ema)           # x_ema again: L2 hits
                 bank.finalize_captured(main.cuda_stream)
 

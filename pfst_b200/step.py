@@ -131,8 +131,8 @@ class SelfTrainingStep:
             join.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), ops._stream())
+        main.wait_event(join)                                     # the sort never runs next to a TMA dots kernel
         self.bank.order(b.label, x_ema.shape[0], x_ema.shape[2], x_ema.shape[3])   # label sort: 1 block / tile
-        main.wait_event(join)
         self.bank.accumulate_ordered(x_ema)                       # x_ema again: L2 hits
 
     def _segment_b(self, b: _Buffers, img, trg_img, gt, chosen, logits_trg, x_src, geo, part="all", mu_ready=None):
@@ -200,15 +200,21 @@ class SelfTrainingStep:
         """The whole step as ONE stream-ordered DAG (one CUDA graph per step) with its true data
         dependencies — three branches forked from the current stream:
 
-          side    neigh_dots(x_ema) -> neigh_dots(x_src)                      (inputs only)
-          proto   [pseudo_label] -> label sort -> proto_accum(x_ema) -> (cross-rank sum) ->
-                  proto_finalize -> proto_dist_fwd(x_src)                     P1, P2, P3 forward
-          main    pseudo_label -> class_mix -> [dots] -> loss prep/fwd -> loss bwd ->
-                  [proto] -> neigh_grad + proto_dist_bwd                      S, M2, L, backward
+          side    neigh_dots(x_ema) -> [label sort done] -> neigh_dots(x_src)      (inputs only)
+          proto   [pseudo_label, dots(x_ema)] -> label sort -> proto_accum(x_ema) -> (cross-rank sum)
+                  -> proto_finalize -> [dots(x_src)] -> proto_dist_fwd(x_src)      P1, P2, P3 forward
+          main    pseudo_label -> class_mix -> [dots(x_src)] -> loss prep/fwd -> loss bwd ->
+                  [proto] -> neigh_grad + proto_dist_bwd                          S, M2, L, backward
 
         ClassMix and the loss statistics never wait for the prototypes; only the fused backward pass
         does. reduce=True (multi-rank): the cross-rank sum is the peer-board exchange inside the
-        finalise kernel (csrc/peer.cu) or, without a board, an ncclAllReduce in front of it."""
+        finalise kernel (csrc/peer.cu) or, without a board, an ncclAllReduce in front of it.
+
+        Ordering rule found the hard way: the label-sort kernel (`proto_accum_kernel<1>`)
+        must never be resident next to a TMA neighbourhood kernel — launched at the same instant inside a
+        graph, the dots kernel then returns sums with a few channel boxes wrong (reproducible at 1024^2,
+        cause not established). The sort therefore sits BETWEEN the two dots kernels: it waits for
+        dots(x_ema) and dots(x_src) waits for it; tests/test_gpu_step_fused.py checks every replay."""
         ema_logits, x_ema, geo = args_a
         img, trg_img, gt, chosen, logits_trg, x_src, _ = args_b
         B, C, H, W = ema_logits.shape
@@ -216,21 +222,25 @@ class SelfTrainingStep:
         bank = self.bank
         main = torch.cuda.current_stream()
         s = main.cuda_stream
-        fork, dots_ema, dots_src, pl_done, proto_done = (self._ev[i] for i in (0, 1, 2, 3, 4))
+        fork, dots_ema, dots_src, pl_done, proto_done, sort_done = (self._ev[i] for i in (0, 1, 2, 3, 4, 8))
         fork.record(main)
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
             ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
             dots_ema.record(self._side)
-            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
-            dots_src.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
         pl_done.record(main)
         self._comm.wait_event(pl_done)
+        self._comm.wait_event(dots_ema)
         with torch.cuda.stream(self._comm):
             bank.order(b.label, Bf, h, w)                             # label sort: 1 block / tile
-            self._comm.wait_event(dots_ema)
+            sort_done.record(self._comm)
+        self._side.wait_event(sort_done)
+        with torch.cuda.stream(self._side):
+            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
+            dots_src.record(self._side)
+        with torch.cuda.stream(self._comm):
             bank.accumulate_ordered(x_ema)                            # x_ema again: L2 hits
             if reduce and bank.peer is None:
                 import torch.distributed as dist
