@@ -65,6 +65,14 @@ class StrongAugmentation(object):
         if isinstance(img, np.ndarray):
             if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
                 raise PfstError("StrongAugmentation expects a uint8 (H,W,3) image")
+            if torch.cuda._is_in_bad_fork():
+                # mmcv / torch data-loader workers are forked AFTER the trainer initialised CUDA: the
+                # child cannot create a context ("Cannot re-initialize CUDA in forked subprocess")
+                raise PfstError("StrongAugmentation (B200 path) was called in a forked data-loader worker, where "
+                                "CUDA cannot be initialised. Use workers_per_gpu=0 or the 'spawn' start method, or "
+                                "keep this step out of the worker pipeline: call aug.draw() per image there (same "
+                                "numpy stream as the reference) and aug.apply_batch(uint8 images on the GPU, draws) "
+                                "once per batch before normalisation (INTEGRATION.md §2d)")
             if not torch.cuda.is_available():
                 raise PfstError("pfst_b200.pipelines needs a CUDA device (no CPU fallback)")
             if op_list:

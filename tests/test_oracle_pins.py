@@ -189,6 +189,28 @@ def test_class_threshold_oracle_equals_reference_live():
             assert np.array_equal(np.asarray(a[k], dtype=np.float64), np.asarray(b[k], dtype=np.float64)), k
 
 
+# ------------------------------------------------------------------ G1: the anchor of the prototype loss
+@needs_ref
+def test_masked_feat_dist_equals_reference_live():
+    """oracle.prototypes.masked_feat_dist (what proto_dist_loss is built on) == PFGST.masked_feat_dist of
+    the reference class (rsiseg/models/uda/pfgst.py:168-177), values and gradients, with and without a
+    mask; the drop-in's own method is the same function."""
+    from oracle import prototypes as OP
+    ref = R.pfgst().PFGST.masked_feat_dist
+    g = torch.Generator().manual_seed(21)
+    for B, D, h, w in [(2, 16, 8, 8), (1, 512, 5, 7), (3, 4, 15, 15)]:
+        f1 = torch.randn((B, D, h, w), generator=g).requires_grad_(True)
+        f1b = f1.detach().clone().requires_grad_(True)
+        f2 = torch.randn((B, D, h, w), generator=g)
+        mask = torch.rand((B, 1, h, w), generator=g) > 0.4
+        for m in (None, mask):
+            a, b = ref(None, f1, f2, m), OP.masked_feat_dist(f1b, f2, m)
+            assert torch.equal(a, b)
+            a.backward(); b.backward()
+            assert torch.equal(f1.grad, f1b.grad)
+            f1.grad = f1b.grad = None
+
+
 # ------------------------------------------------------------------ offline labels: sigma search, loader rule
 def test_offline_labels_oracle_vs_golden():
     """oracle.offline_labels vs the fixture written by PseudoLabelingHookV4._cal_loc_dis/_cal_sigmas and

@@ -1,3 +1,4 @@
+"""Development aid: replays the one-graph step and compares its dot maps with the TMA dots kernel launched alone."""
 import os, sys
 from pathlib import Path
 import numpy as np, torch
