@@ -305,6 +305,70 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   }
 }
 
+// ---- small planes (h*w <= kPsMaxHw, e.g. SeasonNet's 15x15): one block per (image, 32-channel chunk) --
+// The tile machinery above is built for 4096-pixel tiles: with 225 pixels and 33 classes every class
+// segment is padded to a 32-lane row (a 5x longer walk) and every (class, channel) costs a warp reduction
+// and a global RED. Here the block stages its 32 channel planes — contiguous in NCHW, one coalesced
+// copy — with an odd row stride, rebuilds the per-pixel class from the sorted list of the MODE 1 launch,
+// and each warp adds whole pixels into a warp-private [class][channel] tile (lane = channel: no bank
+// conflicts, no atomics); the eight tiles are merged in fixed order and one RED per (class present,
+// channel) goes to `packed`.
+constexpr int kPsCh = 32;
+constexpr int kPsThreads = 256;
+constexpr int kPsMaxHw = 576;
+
+__host__ __device__ inline size_t ps_smem_bytes(int hw, int C) {
+  const size_t stride = (size_t)(hw | 1);
+  return ((size_t)kPsCh * stride + (size_t)(kPsThreads / 32) * C * kPsCh) * sizeof(float) + (size_t)((hw + 15) / 16) * 16;
+}
+
+__global__ void __launch_bounds__(kPsThreads)
+proto_accum_small_kernel(const float* __restrict__ feats, int D, int hw, int C, const unsigned char* __restrict__ ws,
+                         size_t list_bytes, size_t off_rows, size_t off_seg, float* __restrict__ packed) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  const int stride = hw | 1;
+  float* F = reinterpret_cast<float*>(ps_smem);                          // [32][stride]
+  float* acc = F + (size_t)kPsCh * stride;                               // [8 warps][C][32]
+  uint8_t* lab = reinterpret_cast<uint8_t*>(acc + (size_t)(kPsThreads / 32) * C * kPsCh);
+  const int chunks = (D + kPsCh - 1) / kPsCh;
+  const int b = blockIdx.x / chunks, c0 = (blockIdx.x - b * chunks) * kPsCh;
+  const int nch = min(kPsCh, D - c0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // stage the chunk: nch planes of hw floats, contiguous in global memory
+  const float* src = feats + ((int64_t)b * D + c0) * hw;
+  for (int e = threadIdx.x; e < nch * hw; e += kPsThreads) {
+    const int ch = e / hw, px = e - ch * hw;
+    F[ch * stride + px] = __ldg(src + e);
+  }
+  for (int i = threadIdx.x; i < (kPsThreads / 32) * C * kPsCh; i += kPsThreads) acc[i] = 0.f;
+  for (int i = threadIdx.x; i < hw; i += kPsThreads) lab[i] = 255;
+  __syncthreads();
+  // per-pixel class from the class-sorted list: row r (32 entries) belongs to class rowcls[r]
+  const unsigned char* list = ws + (size_t)b * list_bytes;
+  const uint16_t* order = reinterpret_cast<const uint16_t*>(list);
+  const uint8_t* rowcls = list + off_rows;
+  const int n_entries = reinterpret_cast<const int*>(list + off_seg)[C];
+  for (int i = threadIdx.x; i < n_entries; i += kPsThreads) {
+    const unsigned px = order[i];
+    if (px < (unsigned)hw) lab[px] = rowcls[i >> 5];
+  }
+  __syncthreads();
+  float* mine = acc + (size_t)warp * C * kPsCh;
+  if (lane < nch)
+    for (int px = warp; px < hw; px += kPsThreads / 32) {
+      const unsigned c = lab[px];
+      if (c != 255u) mine[c * kPsCh + lane] += F[lane * stride + px];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * kPsCh; i += kPsThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kPsThreads / 32; ++wv) t += acc[(size_t)wv * C * kPsCh + i];
+    const int c = i / kPsCh, ch = i - c * kPsCh;
+    if (t != 0.f && ch < nch) atomicAdd(packed + (int64_t)c * D + c0 + ch, t);
+  }
+}
+
 // iter_state (nullable): device int64[2] = {prototype-bank iteration, block-completion counter}.
 // When given, the EMA coefficients are derived from the device-resident iteration with the
 // E2 rule (pfgst.py:117, in fp64 like the host) and the last block to finish advances it —
@@ -639,6 +703,21 @@ int pfst_proto_accum_ordered(const float* feats, int64_t B, int32_t D, int32_t h
   if (C > pfst::kPrMaxC || !pfst::aligned16(workspace)) return PFST_ERR_UNSUPPORTED;
   if (B == 0) return PFST_OK;
   PaPlan P;
+  const int hw = h * w;
+  if (hw <= pfst::kPsMaxHw && pfst::ps_smem_bytes(hw, C) <= 200 * 1024 && !getenv("PFST_ACCUM_NO_SMALL")) {
+    // small planes: one block per (image, 32-channel chunk), lists from the MODE 1 launch
+    if (pa_plan(P, nullptr, B, 1, h, w, C, false) != PFST_OK) return PFST_ERR_UNSUPPORTED;
+    const size_t smem = pfst::ps_smem_bytes(hw, C);
+    PFST_CUDA_TRY(cudaFuncSetAttribute(pfst::proto_accum_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem), "pfst_proto_accum_ordered/attr");
+    const int64_t grid = B * ((D + pfst::kPsCh - 1) / pfst::kPsCh);
+    if (grid > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+    pfst::proto_accum_small_kernel<<<(unsigned)grid, pfst::kPsThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        feats, D, hw, C, static_cast<const unsigned char*>(workspace), P.list_bytes, P.L.off_rows - P.L.off_order,
+        P.L.off_seg - P.L.off_order, packed);
+    PFST_CHECK_LAUNCH("pfst_proto_accum_ordered/small");
+    return PFST_OK;
+  }
   const int rc = pa_plan(P, feats, B, D, h, w, C, true);
   if (rc != PFST_OK) return rc;
   return pa_launch<2>(P, feats, B, D, h, w, nullptr, 1, 1, nullptr, 0.f, C, packed, nullptr,
