@@ -229,9 +229,11 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         const float* weights6_host, void* workspace, double* stats,
                         float* losses, float* density, uint8_t* eroded, void* stream);
 
-/* grad_losses: device float[6], upstream gradient of each loss. coef: (B,9,fh,fw)
+/* grad_losses: device float[6], upstream gradient of each loss. coef (nullable): (B,9,fh,fw)
  * for pfst_neigh_grad(x_src, dilation/up). grad_logits (nullable): (B,C,lh,lw),
- * zero-filled here, gradient of the two loss_sim terms.                            */
+ * zero-filled here, gradient of the two loss_sim terms. At least one of the two outputs;
+ * two launches (coef only / grad_logits only) let the coefficient maps — the only part the
+ * x_src gradient pass waits for — leave the critical path early.                    */
 int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
                         int32_t fw, int32_t up, const float* logits, int32_t C,
                         int32_t lh, int32_t lw, float lscale_h, float lscale_w,

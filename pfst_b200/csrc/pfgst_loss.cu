@@ -463,7 +463,7 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
       }
       __syncthreads();     // the shared arrays are rewritten by the next loss pixel
     }
-  if (live) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
+  if (live && coef) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
 }
 
 static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, int fh, int fw, int up,
@@ -544,7 +544,7 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
   const int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
                                    mix, gt_h, gt_w, dilation, top_k, weights6_host, const_cast<void*>(workspace));
   if (rc != PFST_OK) return rc;
-  if (!stats || !grad_losses || !coef) return PFST_ERR_INVALID_ARG;
+  if (!stats || !grad_losses || (!coef && !grad_logits)) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (grad_logits)
     PFST_CUDA_TRY(cudaMemsetAsync(grad_logits, 0, sizeof(float) * (size_t)P.B * C * lh * lw, s),

@@ -106,6 +106,7 @@ class SelfTrainingStep:
         # multi-rank P2: one-shot all-reduce over NVLink peer memory inside the finalise kernel
         # (csrc/peer.cu); PFST_PEER_REDUCE=0 falls back to ncclAllReduce between two kernels
         self.peer_reduce = os.environ.get("PFST_PEER_REDUCE", "1") != "0"
+        self.split_bwd = os.environ.get("PFST_SPLIT_BWD", "0") == "1"    # loss backward as two launches (coef | grad_logits)
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
@@ -231,12 +232,15 @@ class SelfTrainingStep:
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
         pl_done.record(main)
+        unsafe = os.environ.get("PFST_DAG_UNSAFE") == "1"           # reproduces DESIGN.md 3.2 (tools/dots_replay_check.py)
         self._comm.wait_event(pl_done)
-        self._comm.wait_event(dots_ema)
+        if not unsafe:
+            self._comm.wait_event(dots_ema)
         with torch.cuda.stream(self._comm):
             bank.order(b.label, Bf, h, w)                             # label sort: 1 block / tile
             sort_done.record(self._comm)
-        self._side.wait_event(sort_done)
+        if not unsafe:
+            self._side.wait_event(sort_done)
         with torch.cuda.stream(self._side):
             ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
             dots_src.record(self._side)
@@ -260,12 +264,24 @@ class SelfTrainingStep:
                   geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h,
                   geo.gt_w, geo.dilation, int(self.top_k), w6, b.ws.data_ptr(), b.stats.data_ptr())
         _lib.call("pfst_pfgst_loss_fwd", *common, b.losses.data_ptr(), None, None, s)
-        _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
-                  b.grad_logits.data_ptr(), s)
+        if self.split_bwd:
+            # the x_src gradient pass only needs the coefficient maps: grad_logits on the idle side stream
+            stats_done, logits_done = self._ev[9], self._ev[0]
+            stats_done.record(main)
+            self._side.wait_event(stats_done)
+            _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), None, b.grad_logits.data_ptr(),
+                      self._side.cuda_stream)
+            logits_done.record(self._side)
+            _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(), None, s)
+        else:
+            _lib.call("pfst_pfgst_loss_bwd", *common, self.gout.data_ptr(), b.coef.data_ptr(),
+                      b.grad_logits.data_ptr(), s)
         main.wait_event(proto_done)
         _lib.call("pfst_neigh_grad_proto", x_src.data_ptr(), b.coef.data_ptr(), Bf, D, h, w,
                   geo.dilation // geo.up, gt.data_ptr(), H, W, bank.mu.data_ptr(), bank.seen.data_ptr(),
                   self.C, b.dist.data_ptr(), b.acc.data_ptr(), self.gproto.data_ptr(), b.grad_x.data_ptr(), s)
+        if self.split_bwd:
+            main.wait_event(logits_done)
 
     def _captured(self, key, b, args_a, args_b, parts):
         """CUDA graphs for one set of input addresses, captured after a warm-up pass on a side
