@@ -295,6 +295,19 @@ int pfst_proto_finalize_dev(float* packed, int32_t C, int32_t D, const float* mu
                             float* mu_out, int64_t* cnt_out, uint8_t* seen_out,
                             int32_t reset_packed, void* stream);
 
+/* ---- G1: PFGST.masked_feat_dist (rsiseg/models/uda/pfgst.py:168-177) -----------------------
+ * loss = mean over the selected pixels of ||f1[:,n] - f2[:,n]||_2; selected = mask[n] != 0
+ * (mask: (B,1,h,w) uint8 / bool bytes, NULL = every pixel). f1, f2: (B,D,h,w) fp32.
+ * dist: (B,h,w) per-pixel norms (0 where not selected), acc: device double[4] workspace (zeroed
+ * here; acc[1] = number of selected pixels) — both kept for the backward. An empty selection
+ * gives NaN like torch.mean. Backward: grad_f1 = g (f1-f2) / (dist n), 0 where dist = 0 or the
+ * pixel is not selected; grad_f2 = -grad_f1 (either may be NULL).                            */
+int pfst_feat_dist_fwd(const float* f1, const float* f2, const uint8_t* mask, int64_t B, int32_t D,
+                       int32_t h, int32_t w, float* dist, double* acc, float* loss, void* stream);
+int pfst_feat_dist_bwd(const float* f1, const float* f2, const uint8_t* mask, int64_t B, int32_t D,
+                       int32_t h, int32_t w, const float* dist, const double* acc,
+                       const float* grad_loss, float* grad_f1, float* grad_f2, void* stream);
+
 /* ---- P2 across ranks: one-shot all-reduce over NVLink peer memory, fused into the finalise ----
  * north_star: "only the prototype sums and counts ... are reduced" across the data-parallel
  * ranks. The reference's only cross-rank reduction of per-iteration quantities is

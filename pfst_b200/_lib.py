@@ -62,6 +62,8 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_proto_accum_ordered": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pfst_proto_finalize": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "pfst_proto_finalize_dev": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "pfst_feat_dist_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "pfst_feat_dist_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pfst_peer_board_bytes": (_i64, [_i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "pfst_peer_alloc": (C.c_int, [_i64, C.POINTER(_vp), _vp]),
     "pfst_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),

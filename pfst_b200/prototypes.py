@@ -234,3 +234,49 @@ def proto_dist_all(feats: torch.Tensor, mu: torch.Tensor) -> torch.Tensor:
     _lib.call("pfst_proto_dist_all", ops._dev(feats, "feats", torch.float32), B, D, h, w,
               ops._dev(mu, "mu", torch.float32), C, out.data_ptr(), ops._stream())
     return out
+
+
+class _FeatDistFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, mask):
+        f1, f2 = f1.contiguous(), f2.contiguous()
+        B, D, h, w = f1.shape
+        dev = f1.device
+        dist = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+        acc = torch.empty(4, dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("pfst_feat_dist_fwd", ops._dev(f1, "f1", torch.float32), ops._dev(f2, "f2", torch.float32),
+                  None if mask is None else mask.data_ptr(), B, D, h, w, dist.data_ptr(), acc.data_ptr(),
+                  loss.data_ptr(), ops._stream())
+        ctx.save_for_backward(f1, f2, dist, acc)
+        ctx.mask = mask
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        f1, f2, dist, acc = ctx.saved_tensors
+        B, D, h, w = f1.shape
+        g1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty_like(f2) if ctx.needs_input_grad[1] else None
+        g = grad_out.reshape(1).contiguous().float()
+        if g1 is not None or g2 is not None:
+            _lib.call("pfst_feat_dist_bwd", f1.data_ptr(), f2.data_ptr(),
+                      None if ctx.mask is None else ctx.mask.data_ptr(), B, D, h, w, dist.data_ptr(), acc.data_ptr(),
+                      g.data_ptr(), None if g1 is None else g1.data_ptr(), None if g2 is None else g2.data_ptr(),
+                      ops._stream())
+        return g1, g2, None
+
+
+def masked_feat_dist(f1: torch.Tensor, f2: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PFGST.masked_feat_dist (rsiseg/models/uda/pfgst.py:168-177): mean over the masked pixels of
+    ||f1 - f2||_2 along the channel dim; one forward and one backward launch (csrc/feat_dist.cu)."""
+    if f1.shape != f2.shape or f1.dim() != 4:
+        raise ValueError("masked_feat_dist: f1 / f2 must be (B,D,h,w) tensors of the same shape")
+    m = None
+    if mask is not None:
+        B, _, h, w = f1.shape
+        if mask.numel() != B * h * w:
+            raise ValueError("masked_feat_dist: mask must be (B,1,h,w)")
+        m = (mask if mask.dtype in (torch.bool, torch.uint8) else mask != 0).contiguous().view(torch.uint8)
+        ops._dev(m, "mask", torch.uint8)
+    return _FeatDistFn.apply(f1, f2, m)

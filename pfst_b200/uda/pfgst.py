@@ -38,7 +38,7 @@ from .. import ops
 from .._lib import PfstError
 from ..engine import LOSS_KEYS, PluginEngine, StepTotalFn
 from ..losses.pfgst_loss import PFGSTLoss
-from ..prototypes import PrototypeBank, proto_dist_loss
+from ..prototypes import PrototypeBank, masked_feat_dist as _masked_feat_dist, proto_dist_loss
 from ..registry import UDA, build_loss
 from ..utils.dacs_transforms import ClassMixPlan, draw_color_jitter, gaussian_blur_batch, get_mean_std
 from .log_ledger import StepRecord, ledger_for
@@ -86,9 +86,6 @@ class PFGST(UDADecorator):
         assert self.mix == 'class'
         if self.thre_type not in ('all', 'part'):
             raise ValueError(f"thre_type {self.thre_type!r}")
-        if self.enable_fdist:
-            raise PfstError("imnet_feature_dist_lambda > 0 (ImageNet feature distance) is not part of the "
-                            "B200 hot path; every shipped config sets it to 0 (_base_/uda/pfst.py:13)")
         # B200-path extras (absent keys = reference behaviour)
         self.pseudo_threshold_per_class = cfg.get('pseudo_threshold_per_class', None)   # north_star S2'
         # kornia's ColorJitter in strong_transform (dacs_transforms.py:56-85): 'builtin' (default) runs the
@@ -106,7 +103,9 @@ class PFGST(UDADecorator):
 
         self.class_probs = {}
         self.ema_model = build_model(cfg['model'])
-        self.imnet_model = None
+        # pfgst.py:84-87: with imnet_feature_dist_lambda > 0 the reference builds a third (ImageNet) copy of
+        # the segmentor — and never uses it: PFGST.forward_train has no feature-distance term
+        self.imnet_model = build_model(cfg['model']) if self.enable_fdist else None
 
         aux_losses = cfg.get('aux_losses', None)
         self.apply_aux = False
@@ -182,11 +181,8 @@ class PFGST(UDADecorator):
         return dict(log_vars=log_vars, num_samples=len(data_batch['img_metas']), states=vis_states)
 
     def masked_feat_dist(self, f1, f2, mask=None):
-        """pfgst.py:168-177 (plain torch; unreachable with fdist_lambda = 0)."""
-        pw = torch.norm(f1 - f2, dim=1, p=2)
-        if mask is not None:
-            pw = pw[mask.squeeze(1)]
-        return torch.mean(pw)
+        """pfgst.py:168-177 (no caller in the reference's PFGST either): one fused launch each way."""
+        return _masked_feat_dist(f1, f2, mask)
 
     def _threshold_args(self, dev):
         if self.pseudo_threshold_per_class is None:

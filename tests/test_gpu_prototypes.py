@@ -152,3 +152,44 @@ def test_peer_board_single_rank_equals_local_finalize(cuda):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,D,h,w", [(2, 512, 64, 64), (1, 19, 5, 7), (3, 64, 15, 15)])
+def test_masked_feat_dist_matches_the_reference_method(cuda, B, D, h, w):
+    """G1: PFGST.masked_feat_dist (pfgst.py:168-177; oracle pinned to the reference method in
+    tests/test_oracle_pins.py) — value and both gradients, with / without a mask, 1e-5."""
+    g = torch.Generator().manual_seed(B * 31 + D)
+    f1 = torch.randn((B, D, h, w), generator=g)
+    f2 = torch.randn((B, D, h, w), generator=g)
+    f2[0, :, 0, 0] = f1[0, :, 0, 0]                          # a zero distance: gradient 0 there, not NaN
+    mask = torch.rand((B, 1, h, w), generator=g) > 0.3
+    mask[0, 0, 0, 0] = True
+    for m in (None, mask):
+        a1, a2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+        ref = OP.masked_feat_dist(a1, a2, m)
+        (ref * 0.37).backward()
+        b1, b2 = f1.to(cuda).requires_grad_(True), f2.to(cuda).requires_grad_(True)
+        got = P.masked_feat_dist(b1, b2, None if m is None else m.to(cuda))
+        (got * 0.37).backward()
+        assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+        for x, y in ((b1.grad, a1.grad), (b2.grad, a2.grad)):
+            assert (x.cpu() - y).abs().max() <= 1e-5 * y.abs().max()
+        assert float(b1.grad[0, :, 0, 0].abs().max()) == 0.0
+    empty = torch.zeros((B, 1, h, w), dtype=torch.bool)
+    assert torch.isnan(P.masked_feat_dist(f1.to(cuda), f2.to(cuda), empty.to(cuda)))
+    assert torch.isnan(OP.masked_feat_dist(f1, f2, empty))
+
+
+def test_drop_in_accepts_the_imnet_feature_distance_keys(cuda):
+    """pfgst.py:84-87: imnet_feature_dist_lambda > 0 builds a third copy of the segmentor and nothing
+    else (the reference's forward_train has no feature-distance term); masked_feat_dist is callable."""
+    from pfst_b200.uda import PFGST
+    from tests.fake_segmentor import TinySegmentor
+    from tests.golden.make_golden import STEP_CFG
+    cfg = dict(STEP_CFG)
+    cfg.update(imnet_feature_dist_lambda=0.005, imnet_feature_dist_classes=[1, 2], imnet_feature_dist_scale_min_ratio=0.75)
+    cfg['model'] = lambda: TinySegmentor(6, 16, seed=0)
+    m = PFGST(**cfg).to(cuda)
+    assert m.enable_fdist and m.get_imnet_model() is not None and m.get_imnet_model() is not m.get_model()
+    f = torch.randn((2, 16, 8, 8), device=cuda)
+    assert float(m.masked_feat_dist(f, f + 1.0)) == pytest.approx(4.0, rel=1e-6)
