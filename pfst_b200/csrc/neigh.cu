@@ -25,8 +25,6 @@
 // fixed order (deterministic, no atomics).
 // Shapes TMA cannot describe (W % 4 != 0, e.g. SeasonNet's 15x15 maps) take a
 // plain coalesced kernel with the same outputs.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -208,125 +206,6 @@ neigh_dots_tma_kernel(const __grid_constant__ NeighMaps maps, int n_tensors, int
         }
         const int y = tl.y0 + r0 + k * DIL;
         if (y < h && x < w)   // w % 4 == 0: a strip is entirely inside or outside
-          *reinterpret_cast<float4*>(out + ((int64_t)m * h + y) * w + x) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-  }
-}
-
-// ---------------------------------------------------------------- forward (TMA), eight consumer warps
-// Same tiles, boxes and ring as neigh_dots_tma_kernel, but the 32x16 tile of a channel is shared by TWO
-// warps (rows 0-7 / 8-15): a lane owns a chain of two 1x4 strips (8 pixels, 40 accumulators instead of
-// 80), so a CTA has eight consumer warps at ~90 registers and two CTAs still fit an SM — 16 consumer
-// warps per SM instead of 8 to hide the shared-memory latency (ncu r1: 12 % warps active, issue slots
-// 0.3). Costs 8 instead of 7 LDS.128 per 8 pixels.
-constexpr int kNb8Consumers = 256;
-constexpr int kNb8Threads = kNb8Consumers + 32;
-
-template <int DIL>
-__global__ void __launch_bounds__(kNb8Threads, 2)
-neigh_dots_tma8_kernel(const __grid_constant__ NeighMaps maps, int n_tensors, int B, int D, int h, int w,
-                       int ksplit, int slot0, int n_slots, float* __restrict__ dots) {
-  using G = NbGeom<DIL>;
-  constexpr int kStageFloats = kNbCH * G::FWD_ROWS * G::RS;
-  extern __shared__ __align__(128) unsigned char nb_smem[];
-  float* stage_buf = reinterpret_cast<float*>(nb_smem);
-  __shared__ uint64_t full_bar[kNbStages], empty_bar[kNbStages];
-  const NbTile tl = nb_decode(n_tensors, B, h, w, D, ksplit);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kNbStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kNb8Consumers / 32);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == kNb8Consumers / 32) {
-    if (lane == 0)
-      nb_produce<G::FWD_ROWS, G::RS>(&maps.m[tl.t], stage_buf, full_bar, empty_bar, tl, tl.x0 - kNbHL, tl.y0);
-    return;
-  }
-  const int wq = warp & 3, half = warp >> 2;               // channel slot of the stage, upper / lower 8 rows
-  const int lx = (lane & 7) * 4, chain = lane >> 3;
-  const int r0 = half * 8 + (chain / DIL) * 2 * DIL + chain % DIL;     // rows r0, r0 + DIL
-  float acc[5][2][4];
-#pragma unroll
-  for (int m = 0; m < 5; ++m)
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[m][k][i] = 0.f;
-
-  int it = 0;
-  for (int c = tl.c_begin; c < tl.c_end; ++c, ++it) {
-    const int s = it % kNbStages;
-    mbar_wait(&full_bar[s], (uint32_t)(it / kNbStages) & 1u);
-    const float* buf = stage_buf + (size_t)s * kStageFloats + r0 * G::RS + lx;
-#pragma unroll
-    for (int cc = 0; cc < kNbCH / 4; ++cc) {
-      const int ch = wq + cc * 4;
-      const float* row = buf + ch * G::FWD_ROWS * G::RS;
-      float P[12], Q[12];
-#pragma unroll
-      for (int v = 1; v < 3; ++v) {
-        const float4 f = *reinterpret_cast<const float4*>(row + 4 * v);
-        P[4 * v] = f.x; P[4 * v + 1] = f.y; P[4 * v + 2] = f.z; P[4 * v + 3] = f.w;
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        row += DIL * G::RS;
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          const float4 f = *reinterpret_cast<const float4*>(row + 4 * v);
-          Q[4 * v] = f.x; Q[4 * v + 1] = f.y; Q[4 * v + 2] = f.z; Q[4 * v + 3] = f.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = P[4 + i];
-          acc[0][k][i] = fmaf(a, a, acc[0][k][i]);
-          acc[1][k][i] = fmaf(a, P[4 + i + DIL], acc[1][k][i]);      // ( 0, +d)
-          acc[2][k][i] = fmaf(a, Q[4 + i - DIL], acc[2][k][i]);      // (+d, -d)
-          acc[3][k][i] = fmaf(a, Q[4 + i], acc[3][k][i]);            // (+d,  0)
-          acc[4][k][i] = fmaf(a, Q[4 + i + DIL], acc[4][k][i]);      // (+d, +d)
-        }
-#pragma unroll
-        for (int j = 4; j < 12; ++j) P[j] = Q[j];
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
-  }
-  // merge the four channel-slot warps of each half in a fixed order (the ring is idle now)
-  asm volatile("bar.sync 1, %0;" ::"n"(kNb8Consumers) : "memory");
-  float* red = stage_buf;                                   // [half][3 warps][40 values][32 lanes]
-  if (wq > 0) {
-#pragma unroll
-    for (int m = 0; m < 5; ++m)
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          red[(((half * 3 + (wq - 1)) * 40) + (m * 8 + k * 4 + i)) * 32 + lane] = acc[m][k][i];
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(kNb8Consumers) : "memory");
-  if (wq == 0) {
-    const int x = tl.x0 + lx;
-    float* out = dots + ((((int64_t)tl.split * n_slots + slot0 + tl.t) * B + tl.b) * 5) * h * w;
-    const float* rh = red + (size_t)half * 3 * 40 * 32;
-#pragma unroll
-    for (int m = 0; m < 5; ++m)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = m * 8 + k * 4 + i;
-          o[i] = ((acc[m][k][i] + rh[e * 32 + lane]) + rh[(40 + e) * 32 + lane]) + rh[(80 + e) * 32 + lane];
-        }
-        const int y = tl.y0 + r0 + k * DIL;
-        if (y < h && x < w)
           *reinterpret_cast<float4*>(out + ((int64_t)m * h + y) * w + x) = make_float4(o[0], o[1], o[2], o[3]);
       }
   }
@@ -736,18 +615,10 @@ static int launch_dots_tma(const float* xa, const float* xb, int T, int B, int D
   if (!make_nchw_tensor_map(&maps.m[0], xa, B, D, h, w, G::RS, G::FWD_ROWS, kNbCH)) return PFST_ERR_CUDA;
   if (!make_nchw_tensor_map(&maps.m[1], xb ? xb : xa, B, D, h, w, G::RS, G::FWD_ROWS, kNbCH)) return PFST_ERR_CUDA;
   const size_t smem = (size_t)kNbStages * kNbCH * G::FWD_ROWS * G::RS * sizeof(float);
-  const int64_t tiles = (int64_t)((w + kNbTW - 1) / kNbTW) * ((h + kNbTH - 1) / kNbTH);
-  const int64_t grid = (int64_t)T * B * tiles * ks;
-  static const bool eight = getenv("PFST_DOTS_WARPS8") != nullptr;     // A/B switch: eight consumer warps per CTA
-  if (eight) {
-    auto k8 = neigh_dots_tma8_kernel<DIL>;
-    PFST_CUDA_TRY(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_neigh_dots/attr8");
-    k8<<<(unsigned)grid, kNb8Threads, smem, s>>>(maps, T, B, D, h, w, ks, slot0, n_slots, dots);
-    PFST_CHECK_LAUNCH("pfst_neigh_dots");
-    return PFST_OK;
-  }
   auto k = neigh_dots_tma_kernel<DIL>;
   PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_neigh_dots/attr");
+  const int64_t tiles = (int64_t)((w + kNbTW - 1) / kNbTW) * ((h + kNbTH - 1) / kNbTH);
+  const int64_t grid = (int64_t)T * B * tiles * ks;
   k<<<(unsigned)grid, kNbThreads, smem, s>>>(maps, T, B, D, h, w, ks, slot0, n_slots, dots);
   PFST_CHECK_LAUNCH("pfst_neigh_dots");
   return PFST_OK;
