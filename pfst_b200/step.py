@@ -63,11 +63,6 @@ class _Buffers:
         Bf, D, h, w = feat_shape
         self.ks = ops.neigh_dots_splits(Bf, D, h, w)
         self.dots = e((self.ks, 2, Bf, 5, h, w), f32)
-        # both feature tensors in ONE dots launch (the one-graph schedule): its own channel-split count
-        self.ks_pair = ops.neigh_dots_splits(Bf, D, h, w, n_tensors=2)
-        self.dots_pair = e((self.ks_pair, 2, Bf, 5, h, w), f32)
-        self.pair = False         # set by SelfTrainingStep: does the one-graph schedule use the pair launch
-        self.step_dots = self.dots
         ws_bytes = int(_lib.load().pfst_pfgst_loss_ws_bytes(geo.B, geo.C, geo.fh, geo.fw, geo.up))
         self.ws = e((ws_bytes,), torch.uint8)
         self.stats, self.losses = e((16,), torch.float64), e((6,), f32)
@@ -112,8 +107,6 @@ class SelfTrainingStep:
         # (csrc/peer.cu); PFST_PEER_REDUCE=0 falls back to ncclAllReduce between two kernels
         self.peer_reduce = os.environ.get("PFST_PEER_REDUCE", "1") != "0"
         self.split_bwd = os.environ.get("PFST_SPLIT_BWD", "0") == "1"    # loss backward as two launches (coef | grad_logits)
-        # one dots launch for x_ema and x_src ("auto": when a single tensor already fills the GPU — B * tiles >= 64)
-        self.dots_pair_mode = os.environ.get("PFST_DOTS_PAIR", "auto")
         self._bufs = {}           # shape key -> _Buffers
         self._graphs = {}         # pointer key -> (graph A, graph B)
         # fork/join plumbing: one side stream for the second branch of a segment, one for the EMA
@@ -231,19 +224,11 @@ class SelfTrainingStep:
         main = torch.cuda.current_stream()
         s = main.cuda_stream
         fork, dots_ema, dots_src, pl_done, proto_done, sort_done = (self._ev[i] for i in (0, 1, 2, 3, 4, 8))
-        pair = b.pair
-        dots_buf, dots_ks = (b.dots_pair, b.ks_pair) if pair else (b.dots, b.ks)
         fork.record(main)
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
-            if pair:      # x_ema and x_src in one launch: one fixed launch cost (~6.6 us) instead of two
-                _lib.call("pfst_neigh_dots", x_ema.data_ptr(), x_src.data_ptr(), Bf, D, h, w, geo.dilation // geo.up,
-                          dots_buf.data_ptr(), self._side.cuda_stream)
-                dots_ema.record(self._side)
-                dots_src.record(self._side)
-            else:
-                ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
-                dots_ema.record(self._side)
+            ops.neigh_dots_slot(x_ema, geo.dilation // geo.up, 0, b.dots)
+            dots_ema.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
         pl_done.record(main)
@@ -254,12 +239,11 @@ class SelfTrainingStep:
         with torch.cuda.stream(self._comm):
             bank.order(b.label, Bf, h, w)                             # label sort: 1 block / tile
             sort_done.record(self._comm)
-        if not pair:
-            if not unsafe:
-                self._side.wait_event(sort_done)
-            with torch.cuda.stream(self._side):
-                ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
-                dots_src.record(self._side)
+        if not unsafe:
+            self._side.wait_event(sort_done)
+        with torch.cuda.stream(self._side):
+            ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
+            dots_src.record(self._side)
         with torch.cuda.stream(self._comm):
             bank.accumulate_ordered(x_ema)                            # x_ema again: L2 hits
             if reduce and bank.peer is None:
@@ -276,7 +260,7 @@ class SelfTrainingStep:
                   b.mixed_img.data_ptr(), b.mixed_lbl.data_ptr(), b.weight.data_ptr(), b.mix_mask.data_ptr(), s)
         main.wait_event(dots_src)
         w6 = ops._w6(self.w6)
-        common = (dots_buf.data_ptr(), dots_ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C,
+        common = (b.dots.data_ptr(), b.ks, geo.B, geo.fh, geo.fw, geo.up, logits_trg.data_ptr(), geo.C,
                   geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), b.mix_mask.data_ptr(), geo.gt_h,
                   geo.gt_w, geo.dilation, int(self.top_k), w6, b.ws.data_ptr(), b.stats.data_ptr())
         _lib.call("pfst_pfgst_loss_fwd", *common, b.losses.data_ptr(), None, None, s)
@@ -413,8 +397,6 @@ class SelfTrainingStep:
         if ent is None:
             geo = ops.LossGeometry(logits_trg.shape, x_src.shape, gt.shape, self.downscale, self.dilation)
             ent = (_Buffers(self.device, B, self.C, H, W, img.shape, logits_trg.shape, x_src.shape, geo), geo)
-            tiles = ((x_src.shape[3] + 31) // 32) * ((x_src.shape[2] + 15) // 16)
-            ent[0].pair = self.dots_pair_mode == "1" or (self.dots_pair_mode == "auto" and x_src.shape[0] * tiles >= 64)
             self._bufs[skey] = ent
         b, geo = ent
         main = torch.cuda.current_stream()

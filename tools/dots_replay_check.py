@@ -24,12 +24,7 @@ for it in range(6):
     ref = torch.empty_like(b.dots)
     ops.neigh_dots_slot(inp["x_ema"], d, 0, ref); ops.neigh_dots_slot(inp["x_src"], d, 1, ref)
     torch.cuda.synchronize()
-    got = b.dots
-    if b.pair:
-        ref, _ = ops.neigh_dots(inp["x_ema"], inp["x_src"], d)
-        torch.cuda.synchronize()
-        got = b.dots_pair
-    diff = (got - ref).abs()
+    diff = (b.dots - ref).abs()
     per = diff.amax(dim=(2, 4, 5))    # (ks, slot, map)
     bad = (diff > 0).nonzero()
     if hasattr(step, "_scratch_dots"):
@@ -41,9 +36,9 @@ ws = step.bank._order_ws
 print("dots ptr", hex(b.dots.data_ptr()), "bytes", b.dots.numel() * 4, "end", hex(b.dots.data_ptr() + b.dots.numel() * 4))
 print("order ws ptr", hex(ws.data_ptr()), "bytes", ws.numel(), "end", hex(ws.data_ptr() + ws.numel()))
 print("packed", hex(step.bank.packed.data_ptr()), "label", hex(b.label.data_ptr()), b.label.numel() * 8)
-flat_bad = (got.flatten() != ref.flatten()).nonzero().flatten()
+flat_bad = (b.dots.flatten() != ref.flatten()).nonzero().flatten()
 print("first bad flat idx", flat_bad[:10].tolist(), "last", flat_bad[-5:].tolist())
-print("got", got.flatten()[flat_bad[:12]].tolist())
+print("got", b.dots.flatten()[flat_bad[:12]].tolist())
 print("ref", ref.flatten()[flat_bad[:12]].tolist())
 # runs of consecutive bad indices
 d = flat_bad[1:] - flat_bad[:-1]
