@@ -46,6 +46,10 @@ const char* pfst_error_string(int code);
 const char* pfst_last_cuda_error(void);
 /* PFST_OK iff the current device is compute capability 10.x (B200). */
 int pfst_device_check(void);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the two tiny transfers of M1 (36 B of
+ * class-presence bits to pinned host memory, 32 B per image of chosen-class masks back) on an explicit
+ * stream, without a host-side stream switch. Host buffers must be pinned for the copy to be async. */
+int pfst_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
 /* ---- E1/E2: EMA mean-teacher update ---------------------------------------
  * Replaces PFGST._init_ema_weights / PFGST._update_ema

@@ -32,6 +32,14 @@ const char* pfst_error_string(int code) {
 
 const char* pfst_last_cuda_error(void) { return pfst::g_last_error; }
 
+int pfst_copy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!dst || !src || bytes < 0) return PFST_ERR_INVALID_ARG;
+  if (bytes == 0) return PFST_OK;
+  PFST_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)),
+                "pfst_copy_async");
+  return PFST_OK;
+}
+
 int pfst_device_check(void) {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);

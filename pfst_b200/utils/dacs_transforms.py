@@ -40,14 +40,13 @@ def draw_class_choice(classes: np.ndarray, batch: int, rng=np.random) -> np.ndar
     matters because this draw sits on the step's only host round trip."""
     n = int(classes.shape[0])
     k = int((n + n % 2) / 2)
-    vals = classes.tolist()
-    words = []
-    for _ in range(batch):
-        mask = 0
-        for i in rng.permutation(n)[:k].tolist():
-            mask |= 1 << vals[i]
-        words.append([(mask >> (32 * w)) & 0xffffffff for w in range(8)])
-    return np.array(words, dtype=np.uint32).reshape(batch, 8)
+    lut = np.zeros((max(n, 1), 8), dtype=np.uint32)             # one-hot 256-bit word rows of the present classes
+    lut[np.arange(n), classes >> 5] = np.uint32(1) << (classes & 31).astype(np.uint32)
+    out = np.zeros((batch, 8), dtype=np.uint32)
+    for b in range(batch):
+        if k:
+            np.bitwise_or.reduce(lut[rng.permutation(n)[:k]], axis=0, out=out[b])
+    return out
 
 
 class ClassMixPlan:
@@ -87,8 +86,8 @@ class ClassMixPlan:
             stream = torch.cuda.current_stream()
         _lib.call("pfst_class_presence", ops._dev(gt, "gt", torch.int64), gt.numel(), self._presence.data_ptr(),
                   stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            self._presence_host[slot].copy_(self._presence, non_blocking=True)
+        _lib.call("pfst_copy_async", self._presence_host.data_ptr() + 36 * slot, self._presence.data_ptr(), 36,
+                  stream.cuda_stream)
         self._events[slot].record(stream)
 
     def drop_pending(self) -> int:
@@ -112,7 +111,8 @@ class ClassMixPlan:
             self._h2d_events[slot].synchronize()   # the upload issued SLOTS steps ago has read this slot
         self._chosen_np[slot, :batch] = chosen.view(np.int32)
         dst = self._chosen[:batch]
-        dst.copy_(self._chosen_host[slot, :batch], non_blocking=True)
+        _lib.call("pfst_copy_async", dst.data_ptr(), self._chosen_host.data_ptr() + slot * self._chosen_host.stride(0) * 4,
+                  32 * batch, ops._stream())
         self._h2d_events[slot].record()
         self._h2d_pending[slot] = True
         return dst
