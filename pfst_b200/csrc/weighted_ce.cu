@@ -18,6 +18,7 @@
 // HBM-bound in principle: (8 + 4 [+4]) B per high-res pixel.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -230,6 +231,164 @@ weighted_ce_kernel(const CeParams P) {
   }
 }
 
+
+// ---- v2 (round-2 candidate): one thread per HIGH-resolution pixel ---------------------------
+// The cell-per-thread kernel above walks 16 pixels per thread with stride-s label / weight loads
+// (25-50 % sector efficiency) and keeps only 131 k threads busy at cfg2. Here a warp owns a
+// 32-pixel-wide, 16-row strip of a 64x64 high-res tile: label and weight loads are coalesced
+// 256 B / 128 B rows, a thread walks DOWN its column, so consecutive pixels of a thread stay in the
+// same bilinear cell for s rows and their corner gradients are summed in registers; a cell change
+// flushes 4*C shared atomics into the block's low-res gradient tile (the s lanes that share a
+// cell column hit the same word: s-way serialisation on 1/s of the pixels).
+constexpr int kCe2Tile = 64;          // high-res tile edge
+constexpr int kCe2Rows = 16;          // rows per strip
+constexpr int kCe2Threads = 256;
+
+template <int CMAX>
+__global__ void __launch_bounds__(kCe2Threads)
+weighted_ce_px_kernel(const CeParams P, int LT) {
+  extern __shared__ __align__(16) float ce_smem[];
+  float* z_s = ce_smem;                               // [C][LT*LT] low-res logits under the tile
+  float* g_s = z_s + (size_t)P.C * LT * LT;           // same shape: gradient tile
+  __shared__ double red[3][kCe2Threads / 32];
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * kCe2Tile, X0 = blockIdx.x * kCe2Tile;
+  const float sch = (float)P.lh / (float)P.H, scw = (float)P.lw / (float)P.W;
+  int ly_org, lx_org;
+  {
+    int i1; float a0, a1;
+    ce_src(Y0, sch, P.lh, ly_org, i1, a0, a1);
+    ce_src(X0, scw, P.lw, lx_org, i1, a0, a1);
+  }
+  const int64_t lplane = (int64_t)P.lh * P.lw;
+  const float* zb = P.logits + (int64_t)b * P.C * lplane;
+  const int LT2 = LT * LT;
+  for (int i = threadIdx.x; i < P.C * LT2; i += kCe2Threads) {
+    const int c = i / LT2, r = i - c * LT2;
+    const int ly = ly_org + r / LT, lx = lx_org + r % LT;
+    z_s[i] = (ly < P.lh && lx < P.lw) ? zb[c * lplane + (int64_t)ly * P.lw + lx] : 0.f;
+    g_s[i] = 0.f;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float gscale = P.loss_weight / (float)((double)P.B * P.H * P.W);
+  double loss = 0.0, correct = 0.0, valid = 0.0;
+  constexpr int kStripsX = kCe2Tile / 32, kStripsY = kCe2Tile / kCe2Rows;
+  for (int strip = warp; strip < kStripsX * kStripsY; strip += kCe2Threads / 32) {
+    const int x = X0 + (strip % kStripsX) * 32 + lane;
+    const int ys = Y0 + (strip / kStripsX) * kCe2Rows;
+    if (x >= P.W) continue;
+    int x0, x1;
+    float wx0l, wx1l;
+    ce_src(x, scw, P.lw, x0, x1, wx0l, wx1l);
+    const int dx = x1 - x0, cx = x0 - lx_org;
+    float acc[CMAX][4];
+    int cell = -1, cdy = 0;                            // tile offset of the open cell, its row step
+    auto flush = [&]() {
+      if (cell < 0) return;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < P.C) {
+          float* gs = g_s + c * LT2 + cell;
+          atomicAdd(gs, acc[c][0]); atomicAdd(gs + dx, acc[c][1]);
+          atomicAdd(gs + cdy, acc[c][2]); atomicAdd(gs + cdy + dx, acc[c][3]);
+        }
+      }
+    };
+    for (int y = ys; y < ys + kCe2Rows && y < P.H; ++y) {
+      int y0, y1;
+      float hy0l, hy1l;
+      ce_src(y, sch, P.lh, y0, y1, hy0l, hy1l);
+      const int dy = (y1 - y0) * LT;
+      const int i00 = (y0 - ly_org) * LT + cx;
+      const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
+      const int64_t lab = P.labels[pix];
+      float vreg[CMAX];
+      float m = -INFINITY;
+      int arg = 0;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < P.C) {
+          const float* z = z_s + c * LT2 + i00;
+          vreg[c] = hy0l * (wx0l * z[0] + wx1l * z[dx]) + hy1l * (wx0l * z[dy] + wx1l * z[dy + dx]);
+        } else {
+          vreg[c] = -INFINITY;
+        }
+        if (vreg[c] > m) { m = vreg[c]; arg = c; }     // first maximum wins
+      }
+      const bool ign = lab == P.ignore_index || lab < 0 || lab >= P.C;
+      if (ign) continue;
+      valid += 1.0;
+      if (arg == (int)lab) correct += 1.0;
+      float sum = 0.f, vlab = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < P.C) {
+          if (c == (int)lab) vlab = vreg[c];
+          vreg[c] = expf(vreg[c] - m);
+          sum += vreg[c];
+        }
+      }
+      float wpx = P.weight ? P.weight[pix] : 1.f;
+      if (P.class_weight) wpx *= P.class_weight[lab];
+      loss += (double)(((m + logf(sum)) - vlab) * wpx);
+      if (P.grad) {
+        if (i00 != cell || dy != cdy) {
+          flush();
+          cell = i00; cdy = dy;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+        }
+        const float t00 = hy0l * wx0l, t01 = hy0l * wx1l, t10 = hy1l * wx0l, t11 = hy1l * wx1l;
+        const float inv = 1.f / sum, k = gscale * wpx;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < P.C) {
+            const float g = k * (vreg[c] * inv - (c == (int)lab ? 1.f : 0.f));
+            acc[c][0] += t00 * g; acc[c][1] += t01 * g; acc[c][2] += t10 * g; acc[c][3] += t11 * g;
+          }
+        }
+      }
+    }
+    if (P.grad) flush();
+  }
+
+  __syncthreads();
+  if (P.grad) {
+    float* gb = P.grad + (int64_t)b * P.C * lplane;
+    for (int i = threadIdx.x; i < P.C * LT2; i += kCe2Threads) {
+      const float v = g_s[i];
+      if (v == 0.f) continue;
+      const int c = i / LT2, r = i - c * LT2;
+      const int ly = ly_org + r / LT, lx = lx_org + r % LT;
+      if (ly < P.lh && lx < P.lw) atomicAdd(gb + c * lplane + (int64_t)ly * P.lw + lx, v);
+    }
+  }
+  loss = warp_sum(loss); correct = warp_sum(correct); valid = warp_sum(valid);
+  if (lane == 0) { red[0][warp] = loss; red[1][warp] = correct; red[2][warp] = valid; }
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x < 3) {
+    double v = 0.0;
+    for (int wv = 0; wv < kCe2Threads / 32; ++wv) v += red[threadIdx.x][wv];
+    if (v != 0.0) atomicAdd(&P.stats[threadIdx.x], v);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    is_last = atomicAdd(reinterpret_cast<unsigned*>(P.stats + 3), 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const double s = *((volatile double*)&P.stats[0]);
+    const double nc = *((volatile double*)&P.stats[1]), nv = *((volatile double*)&P.stats[2]);
+    P.out[0] = P.loss_weight * (float)(s / ((double)P.B * P.H * P.W));
+    const float eps = FLT_EPSILON;
+    P.out[1] = ((float)nc + eps) * (float)(100.0 / (nv + (double)eps));
+  }
+}
+
 }  // namespace pfst
 
 extern "C" {
@@ -250,6 +409,23 @@ int pfst_weighted_ce(const float* logits, const int64_t* labels, const float* we
   if (B == 0) return PFST_OK;
   pfst::CeParams P{logits, labels, weight, class_weight, (int)B, C, lh, lw, H, W, H / lh,
                    ignore_index, loss_weight, grad_logits, stats, out2};
+  // round-2 candidate: pixel-per-thread kernel for the common case (C <= 8, up-sampling factor >= 2);
+  // PFST_CE_V1=1 in the environment keeps the cell-per-thread kernel for A/B timing
+  static const bool force_v1 = getenv("PFST_CE_V1") != nullptr;
+  if (!force_v1 && C <= 8 && H / lh >= 2) {
+    const int LT = pfst::kCe2Tile / (H / lh) + 3;
+    const size_t smem2 = (size_t)2 * C * LT * LT * sizeof(float);
+    const dim3 grid2((unsigned)((W + pfst::kCe2Tile - 1) / pfst::kCe2Tile),
+                     (unsigned)((H + pfst::kCe2Tile - 1) / pfst::kCe2Tile), (unsigned)B);
+    if (grid2.y <= 65535 && smem2 <= 100 * 1024) {
+      auto k2 = pfst::weighted_ce_px_kernel<8>;
+      PFST_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
+                    "pfst_weighted_ce/attr2");
+      k2<<<grid2, pfst::kCe2Threads, smem2, s>>>(P, LT);
+      PFST_CHECK_LAUNCH("pfst_weighted_ce");
+      return PFST_OK;
+    }
+  }
   const dim3 grid((unsigned)((lw + pfst::kCeTile - 1) / pfst::kCeTile),
                   (unsigned)((lh + pfst::kCeTile - 1) / pfst::kCeTile), (unsigned)B);
   if (grid.y > 65535) return PFST_ERR_UNSUPPORTED;
