@@ -23,6 +23,8 @@
 // tiled (8 outputs per thread sliding over the taps: 2 shared loads per 8 FMAs) and bank
 // conflict free (lanes walk rows in the horizontal pass — odd pitch — and columns in the
 // vertical pass).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pfst {
@@ -78,7 +80,10 @@ __device__ __forceinline__ void blur_weights(float* w, int k, int r, float sigma
 // acc[j] = sum_t w[t] * p[(j + t) * stride], j < 8, four taps per iteration over a register window
 // of 8 + 4 values (taps4 is a multiple of four, the padding weights are zero; the window reads up
 // to four finite slack values behind the last real one).
-template <int STRIDE_IS_ONE>
+// NG > 0: the number of four-tap groups is a compile-time constant — the tap loop is fully unrolled,
+// the window shift becomes register renaming (round-2 candidate: the runtime loop spends a third of
+// its instructions on window moves and loop control). NG == 0: runtime group count.
+template <int STRIDE_IS_ONE, int NG>
 __device__ __forceinline__ void blur_slide(const float* __restrict__ p, int stride, const float* __restrict__ w,
                                            int taps4, float (&acc)[kBlOut]) {
   const int st = STRIDE_IS_ONE ? 1 : stride;
@@ -89,8 +94,7 @@ __device__ __forceinline__ void blur_slide(const float* __restrict__ p, int stri
     ext[j] = p[j * st];
   }
   const float* nxt = p + kBlOut * st;
-#pragma unroll 2
-  for (int t = 0; t < taps4; t += 4) {
+  auto group = [&](int t) {
     const float4 wt = *reinterpret_cast<const float4*>(w + t);
 #pragma unroll
     for (int k = 0; k < 4; ++k) ext[kBlOut + k] = nxt[k * st];
@@ -105,6 +109,25 @@ __device__ __forceinline__ void blur_slide(const float* __restrict__ p, int stri
     for (int j = 0; j < kBlOut; ++j) acc[j] = __fmaf_rn(wt.w, ext[j + 3], acc[j]);
 #pragma unroll
     for (int j = 0; j < kBlOut; ++j) ext[j] = ext[j + 4];
+  };
+  if (NG > 0) {
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) group(4 * gi);
+  } else {
+#pragma unroll 2
+    for (int t = 0; t < taps4; t += 4) group(t);
+  }
+}
+
+// one pass of a block: `tasks` (row or column, 8-output chunk) pairs, group count dispatched once
+template <int STRIDE_IS_ONE, typename F>
+__device__ __forceinline__ void blur_pass(int taps4, F&& body) {
+  switch (taps4 >> 2) {
+    case 1: body(std::integral_constant<int, 1>()); break;
+    case 2: body(std::integral_constant<int, 2>()); break;
+    case 3: body(std::integral_constant<int, 3>()); break;
+    case 4: body(std::integral_constant<int, 4>()); break;
+    default: body(std::integral_constant<int, 0>()); break;
   }
 }
 
@@ -193,32 +216,38 @@ gaussian_blur_kernel(const BlurParams q) {
   // horizontal pass: task = (row, 8-column chunk); lanes of a warp take consecutive rows
   {
     const int tasks = rows * (kBlTile / kBlOut);
-    for (int t = tid; t < tasks; t += kBlThreads) {
-      const int chunk = t / rows, r = t - chunk * rows;
-      float acc[kBlOut];
-      blur_slide<1>(A + r * PA + chunk * kBlOut + (rx - rxi), 1, wx, (2 * rxi + 4) & ~3, acc);
+    const int t4 = (2 * rxi + 4) & ~3;
+    blur_pass<1>(t4, [&](auto ng) {
+      for (int t = tid; t < tasks; t += kBlThreads) {
+        const int chunk = t / rows, r = t - chunk * rows;
+        float acc[kBlOut];
+        blur_slide<1, decltype(ng)::value>(A + r * PA + chunk * kBlOut + (rx - rxi), 1, wx, t4, acc);
 #pragma unroll
-      for (int j = 0; j < kBlOut; ++j) Bm[r * PB + chunk * kBlOut + j] = acc[j];
-    }
+        for (int j = 0; j < kBlOut; ++j) Bm[r * PB + chunk * kBlOut + j] = acc[j];
+      }
+    });
   }
   __syncthreads();
 
   // vertical pass: task = (column, 8-row chunk); lanes take consecutive columns
   {
     const int tasks = kBlTile * (kBlTile / kBlOut);
-    for (int t = tid; t < tasks; t += kBlThreads) {
-      const int chunk = t / kBlTile, cc = t - chunk * kBlTile;
-      float acc[kBlOut];
-      blur_slide<0>(Bm + (chunk * kBlOut + (ry - ryi)) * PB + cc, PB, wy, (2 * ryi + 4) & ~3, acc);
-      const int gx = x_org + cc;
-      if (gx < q.W) {
+    const int t4 = (2 * ryi + 4) & ~3;
+    blur_pass<0>(t4, [&](auto ng) {
+      for (int t = tid; t < tasks; t += kBlThreads) {
+        const int chunk = t / kBlTile, cc = t - chunk * kBlTile;
+        float acc[kBlOut];
+        blur_slide<0, decltype(ng)::value>(Bm + (chunk * kBlOut + (ry - ryi)) * PB + cc, PB, wy, t4, acc);
+        const int gx = x_org + cc;
+        if (gx < q.W) {
 #pragma unroll
-        for (int j = 0; j < kBlOut; ++j) {
-          const int gy = y_org + chunk * kBlOut + j;
-          if (gy < q.H) dst[(int64_t)gy * q.W + gx] = acc[j];
+          for (int j = 0; j < kBlOut; ++j) {
+            const int gy = y_org + chunk * kBlOut + j;
+            if (gy < q.H) dst[(int64_t)gy * q.W + gx] = acc[j];
+          }
         }
       }
-    }
+    });
   }
 }
 
