@@ -50,6 +50,19 @@ int pfst_device_check(void);
  * class-presence bits to pinned host memory, 32 B per image of chosen-class masks back) on an explicit
  * stream, without a host-side stream switch. Host buffers must be pinned for the copy to be async. */
 int pfst_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* M1, host side (no device work): the per-image class draw of get_class_masks
+ * (rsiseg/models/utils/dacs_transforms.py:110-126: `np.random.choice(n, int((n + n % 2) / 2), replace=False)`
+ * once per image, n = number of classes present in the batch) replayed from RAW 32-bit outputs of the same
+ * numpy MT19937 stream. numpy's legacy choice(replace=False) is permutation(n)[:k], and permutation is a
+ * Fisher-Yates shuffle whose index draws are masked rejection samples of successive 32-bit outputs
+ * (`RandomState.bytes` / the MT19937 bit generator's `random_raw` hand out exactly those words; one per
+ * uint64 element, low 32 bits, as `random_raw` returns them). Resumable: `state` (258 int32: image index,
+ * swap index, permutation) starts as zeros; each call consumes ALL `n_words` new words. If they run out,
+ * *words_missing is the least number of further words the batch still needs (the caller draws exactly that
+ * many and calls again with the same state: the stream is never over-consumed); when *words_missing = 0
+ * the batch is complete and masks (batch x 8 uint32, 256 class bits per image) holds the chosen classes. */
+int pfst_classmix_draw(const uint64_t* words, int64_t n_words, const int64_t* classes, int32_t n_classes,
+                       int32_t batch, uint32_t* masks, int32_t* state, int64_t* words_missing);
 
 /* ---- E1/E2: EMA mean-teacher update ---------------------------------------
  * Replaces PFGST._init_ema_weights / PFGST._update_ema

@@ -31,6 +31,7 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_last_cuda_error": (C.c_char_p, []),
     "pfst_device_check": (C.c_int, []),
     "pfst_copy_async": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pfst_classmix_draw": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),   # host-only (no device work)
     "pfst_ema_coeffs": (C.c_int, [_i64, _f64, C.POINTER(_f32), C.POINTER(_f32)]),
     "pfst_ema_update_multi": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _vp]),
     "pfst_ema_update_multi_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _i32, _vp]),

@@ -62,19 +62,28 @@ __host__ __device__ inline size_t ws_floats(int B, int C, int fh, int fw, int up
 // the rest resample labels / masks and take the softmax (one thread per loss-grid pixel).
 constexpr int kPrepThreads = 128;
 
+template <int CMAX>
 __global__ void __launch_bounds__(kPrepThreads)
 pfgst_loss_prep_kernel(const LossParams P, int blocks_a) {
-  const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
+  const int fplane = P.fh * P.fw, gplane = P.gh * P.gw;       // per-image planes: 32-bit offsets
   if (blockIdx.x == 0 && threadIdx.x < 16) P.raw[threadIdx.x] = 0;     // the statistics kernel starts from zero
   if ((int)blockIdx.x < blocks_a) {
     const int64_t n_a = (int64_t)2 * P.B * 5 * fplane;
     const int64_t i = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
     if (i >= n_a) return;
     // i = ((tensor*B + image)*5 + map)*fplane + pixel: the same offset in every split
-    const int64_t split_stride = n_a;
     const float* src = P.dots + i;
     float a = 0.f;
-    for (int sp = 0; sp < P.ksplit; ++sp) a += src[sp * split_stride];   // fixed order: deterministic
+    if (P.ksplit == 8) {                                      // all partial maps in flight, summed in fixed order
+      float v[8];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) v[sp] = src[sp * n_a];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) a += v[sp];
+    } else {
+#pragma unroll 4
+      for (int sp = 0; sp < P.ksplit; ++sp) a += src[sp * n_a];   // fixed order: deterministic
+    }
     P.dm[i] = a;
     const int64_t tbk = i / fplane;
     if (tbk % 5 == 0) P.invn[(tbk / 5) * fplane + (i - tbk * fplane)] = 1.f / fmaxf(sqrtf(a), 1e-8f);
@@ -89,17 +98,27 @@ pfgst_loss_prep_kernel(const LossParams P, int blocks_a) {
   const int64_t go = ((int64_t)b * P.gt_h + sy) * P.gt_w + sx;
   const int64_t g = P.gt[go];
   const int64_t mx = P.mix[go];
-  // softmax of the nearest-resampled logits (pfgst_loss.py:57, 145)
+  // softmax of the nearest-resampled logits (pfgst_loss.py:57, 145): every class plane of the pixel
+  // is requested before the first value is used (one memory round trip instead of three per class)
   const int ly = nearest_src(y, P.lscale_h, P.lh), lx = nearest_src(x, P.lscale_w, P.lw);
-  const float* z = P.logits + ((int64_t)b * P.C * P.lh + ly) * P.lw + lx;
-  const int64_t lplane = (int64_t)P.lh * P.lw;
-  float m = -INFINITY;
-  for (int c = 0; c < P.C; ++c) m = fmaxf(m, z[c * lplane]);
-  float s = 0.f;
-  for (int c = 0; c < P.C; ++c) s += expf(z[c * lplane] - m);
-  const float inv = 1.f / s;
+  const int lplane = P.lh * P.lw;
+  const float* z = P.logits + (int64_t)b * P.C * lplane + ly * P.lw + lx;
   float* po = P.prob + (int64_t)b * P.C * gplane + r;
-  for (int c = 0; c < P.C; ++c) po[c * gplane] = expf(z[c * lplane] - m) * inv;
+  float zr[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) zr[c] = c < P.C ? z[c * lplane] : -INFINITY;
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) m = fmaxf(m, zr[c]);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    if (c < P.C) { zr[c] = expf(zr[c] - m); s += zr[c]; }
+  }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c)
+    if (c < P.C) po[c * gplane] = zr[c] * inv;
   P.lab[i] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
   P.flags[i] = (uint8_t)((g != 255 ? 1 : 0) | (mx <= 0 ? 2 : 0));   // (1 - mix) > 0.5
 }
@@ -268,7 +287,32 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
         const float* pn = P.prob + (int64_t)c.b * P.C * plane + (int64_t)c.y * P.gw + c.x;
         const float* pm = P.prob + (int64_t)c.b * P.C * plane + t.gm;
         float cp = 0.f;
-        for (int cc = 0; cc < P.C; ++cc) cp = fmaf(pn[cc * plane], pm[cc * plane], cp);
+        {
+          const int pl = (int)plane;
+          int cc = 0;
+          for (; cc + 16 <= P.C; cc += 16) {               // sixteen class planes of both pixels in flight
+            float a[16], q[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { a[u] = pn[(cc + u) * pl]; q[u] = pm[(cc + u) * pl]; }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) cp = fmaf(a[u], q[u], cp);
+          }
+          for (; cc + 8 <= P.C; cc += 8) {
+            float a[8], q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a[u] = pn[(cc + u) * pl]; q[u] = pm[(cc + u) * pl]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cp = fmaf(a[u], q[u], cp);
+          }
+          float a[8], q[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const bool on = cc + u < P.C;
+            a[u] = on ? pn[(cc + u) * pl] : 0.f; q[u] = on ? pm[(cc + u) * pl] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cp = fmaf(a[u], q[u], cp);
+        }
         if (top) lp = t.s_ema * (-cp);
         if (bot) ln = (1.f - t.s_ema) * (-(1.f - cp));
       }
@@ -363,11 +407,9 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
     s_k[7] = any_ ? (float)((double)gout[5] * P.w_sim_neg / (mk * (double)P.top_k)) : 0.f;
     s_any = any_ ? 1 : 0;
   }
-  __syncthreads();
-  const float a_pos = s_k[0], c_pos = s_k[1], a_neg = s_k[2], c_neg = s_k[3];
-  const float fmean_pos = s_k[4], fmean_neg = s_k[5], g_pos = s_k[6], g_neg = s_k[7];
-  const bool any = s_any != 0;
-  const bool want_logits = grad_logits != nullptr && any;     // block-uniform
+  // (no barrier yet: the first pixel's map loads are issued while thread 0 does the fp64 arithmetic)
+  float a_pos = 0.f, c_pos = 0.f, a_neg = 0.f, c_neg = 0.f, fmean_pos = 0.f, fmean_neg = 0.f, g_pos = 0.f, g_neg = 0.f;
+  bool want_logits = false;     // block-uniform
 
   float cf = 0.f;
   for (int uy = 0; uy < P.up; ++uy)
@@ -378,8 +420,14 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
       float bs = 0.f;
       c.valid_src = false; c.inv_n_src = 0.f; c.b = b; c.y = y; c.x = x;
       t.in = false; t.s_ema = 0.f; t.trg = false; t.gm = 0;
+      if (live) load_tap(P, k, b, y, x, c, t);
+      if (uy == 0 && ux == 0) {
+        __syncthreads();
+        a_pos = s_k[0]; c_pos = s_k[1]; a_neg = s_k[2]; c_neg = s_k[3];
+        fmean_pos = s_k[4]; fmean_neg = s_k[5]; g_pos = s_k[6]; g_neg = s_k[7];
+        want_logits = grad_logits != nullptr && s_any != 0;
+      }
       if (live) {
-        load_tap(P, k, b, y, x, c, t);
         // --- x_src: gather-form coefficients ---
         if (k != 4 && t.in) {
           const float S = t.s_src;
@@ -427,14 +475,20 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
             const int cc = k + 9 * j;
             dp[j] = 0.f; pc[j] = 0.f;
             if (cc < P.C) {
+              // all nine neighbour probabilities requested at once (zero-weight taps read a valid
+              // address and are dropped by the select: 0 * NaN must not leak)
+              const float* pcl = pb + (int64_t)cc * gplane;
+              float q[9];
+#pragma unroll
+              for (int kk = 0; kk < 9; ++kk) q[kk] = pcl[s_gm[kk][p]];
+              pc[j] = pcl[y * P.gw + x];
               float d = 0.f;
 #pragma unroll
               for (int kk = 0; kk < 9; ++kk) {
                 const float w = s_dcp[kk][p];
-                if (w != 0.f) d = fmaf(w, pb[cc * gplane + s_gm[kk][p]], d);
+                d = w != 0.f ? fmaf(w, q[kk], d) : d;
               }
               dp[j] = d;
-              pc[j] = pb[cc * gplane + (int64_t)y * P.gw + x];
               part = fmaf(pc[j], d, part);
             }
           }
@@ -523,7 +577,9 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
     const int64_t blocks_a = (n_a + pfst::kPrepThreads - 1) / pfst::kPrepThreads;
     const int64_t blocks_b = (total + pfst::kPrepThreads - 1) / pfst::kPrepThreads;
     if (blocks_a + blocks_b > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
-    pfst::pfgst_loss_prep_kernel<<<(unsigned)(blocks_a + blocks_b), pfst::kPrepThreads, 0, s>>>(P, (int)blocks_a);
+    auto prep = C <= 8 ? pfst::pfgst_loss_prep_kernel<8>
+                       : (C <= 40 ? pfst::pfgst_loss_prep_kernel<40> : pfst::pfgst_loss_prep_kernel<pfst::kMaxC>);
+    prep<<<(unsigned)(blocks_a + blocks_b), pfst::kPrepThreads, 0, s>>>(P, (int)blocks_a);
     PFST_CHECK_LAUNCH("pfst_pfgst_loss_fwd/prep");
   }
   if (P.gh > 65535 || P.B > 65535) return PFST_ERR_UNSUPPORTED;

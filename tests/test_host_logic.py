@@ -34,6 +34,22 @@ def test_class_draw_equals_numpy_choice_on_the_same_stream(seed):
     assert a.randint(1 << 30) == b.randint(1 << 30)                      # stream left in the same state
 
 
+@pytest.mark.parametrize("n,batch", [(1, 3), (2, 64), (6, 8), (33, 64), (200, 5), (256, 2)])
+def test_class_draw_from_raw_words_leaves_the_global_stream_where_numpy_would(n, batch):
+    """The library replays numpy's shuffles from raw MT19937 words (pfst_classmix_draw): same picks as
+    `batch` calls of np.random.choice on the GLOBAL stream, and the stream ends in the same state."""
+    rs = np.random.RandomState(n * 1000 + batch)
+    classes = np.array(sorted(rs.choice(256, size=n, replace=False)), dtype=np.int64)
+    np.random.seed(7 + n)
+    got = draw_class_choice(classes, batch, np.random)
+    after_got = np.random.randint(1 << 30)
+    np.random.seed(7 + n)
+    for i in range(batch):
+        pick = np.random.choice(n, int((n + n % 2) / 2), replace=False)
+        assert np.array_equal(got[i], _presence_words(classes[pick].tolist())[:8])
+    assert after_got == np.random.randint(1 << 30)
+
+
 @pytest.mark.skipif(not R.available(), reason="reference checkout not present")
 def test_class_draw_reproduces_reference_get_class_masks():
     ref = R.dacs_transforms()
