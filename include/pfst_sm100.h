@@ -260,6 +260,39 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         const double* stats, const float* grad_losses, float* coef,
                         float* grad_logits, void* stream);
 
+/* The same two entry points with the PFGSTLoss options outside the shipped configuration
+ * (pfgst_loss.py:16-18). `options` is a bit set:
+ *   PFST_LOSS_SIM_GAUSSIAN   sim_type='gaussian' (:189-191): exp(-|x_n - x_m|^2 / sigma^2), formed from the
+ *                            same five dot maps as the cosine (|x_n|^2 + |x_m|^2 - 2 x_n.x_m); the zero
+ *                            padding of the unfold is the zero vector (similarity exp(-|x_n|^2 / sigma^2));
+ *   PFST_LOSS_CROSS_PROB_EMA cross_prob_type='ema' (:161-178): q = unfold(softmax(logits_ema)), logits_ema
+ *                            (B,C,fh*up,fw*up) on the loss grid as the reference requires;
+ *   PFST_LOSS_UNFOLD_GRAD    detach_unfold=False (:148-149 not taken): the logits gradient also flows through
+ *                            the unfolded factor (one more launch in the backward).
+ * 0 = the shipped configuration. The workspace is pfst_pfgst_loss_ws_bytes_ex(..., options) bytes.          */
+#define PFST_LOSS_SIM_GAUSSIAN 1
+#define PFST_LOSS_CROSS_PROB_EMA 2
+#define PFST_LOSS_UNFOLD_GRAD 4
+int64_t pfst_pfgst_loss_ws_bytes_ex(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up,
+                                    int32_t options);
+int pfst_pfgst_loss_fwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
+                           int32_t fw, int32_t up, const float* logits, int32_t C,
+                           int32_t lh, int32_t lw, float lscale_h, float lscale_w,
+                           const int64_t* gt, const int64_t* mix, int32_t gt_h,
+                           int32_t gt_w, int32_t dilation, int32_t top_k,
+                           const float* weights6_host, void* workspace, double* stats,
+                           float* losses, float* density, uint8_t* eroded, int32_t options,
+                           float sigma, const float* logits_ema, void* stream);
+int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
+                           int32_t fw, int32_t up, const float* logits, int32_t C,
+                           int32_t lh, int32_t lw, float lscale_h, float lscale_w,
+                           const int64_t* gt, const int64_t* mix, int32_t gt_h,
+                           int32_t gt_w, int32_t dilation, int32_t top_k,
+                           const float* weights6_host, const void* workspace,
+                           const double* stats, const float* grad_losses, float* coef,
+                           float* grad_logits, int32_t options, float sigma,
+                           const float* logits_ema, void* stream);
+
 /* ---- P1-P3: class prototypes (north_star extension; no reference code) ----------
  * Anchor: PFGST.masked_feat_dist, rsiseg/models/uda/pfgst.py:168-177. Labels are
  * nearest-resampled to the feature grid as pfgst_loss.py:62 does.                  */

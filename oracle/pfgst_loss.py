@@ -1,6 +1,8 @@
-"""PFGST auxiliary loss — restates rsiseg/models/losses/pfgst_loss.py:44-234 for the
-shipped configuration (sim_type='cosine', cross_prob_type='trg',
-src_loss_type='mean_std', feat_level=None, no proj_net, src_perc=None).
+"""PFGST auxiliary loss — restates rsiseg/models/losses/pfgst_loss.py:44-234 for
+src_loss_type='mean_std', feat_level=None, no proj_net, src_perc=None: the shipped
+configuration (sim_type='cosine', cross_prob_type='trg', detach_unfold=True) and the
+options sim_type='gaussian' (:189-191), cross_prob_type='ema' (:161-178) and
+detach_unfold=False. Test infrastructure: only tests/, smoke() and bench.py's CPU legs use it.
 
 Written as free functions over the same ATen operator sequence as the reference
 (nn.Unfold / F.interpolate / F.cosine_similarity / topk / boolean gathers) so that
@@ -24,6 +26,9 @@ class LossCfg:
                                                    "sim_neg": 0.1, "src_pos_std": 0.1, "src_neg_std": 0.1})
     detach_unfold: bool = True
     downscale: float | None = 0.5
+    sim_type: str = "cosine"
+    sigma: float = 30.0
+    cross_prob_type: str = "trg"
 
 
 def _unfold(x: torch.Tensor, cfg: LossCfg) -> torch.Tensor:
@@ -33,11 +38,17 @@ def _unfold(x: torch.Tensor, cfg: LossCfg) -> torch.Tensor:
 
 
 def neighbourhood_cosine(x: torch.Tensor, size, cfg: LossCfg):
-    """get_sim_feat, pfgst_loss.py:181-201 (cosine branch) -> (feats, sim (B,k*k,H,W))."""
+    """get_sim_feat, pfgst_loss.py:181-201 -> (feats, sim (B,k*k,H,W)); cosine (:193-196) or
+    gaussian (:189-191) by cfg.sim_type."""
     B, ch = x.shape[:2]
     k2 = cfg.kernel_size ** 2
     feats = F.interpolate(x, size=size, mode="nearest")
     unf = _unfold(feats, cfg).view(B, ch, k2, size[0], size[1]).permute(0, 1, 3, 4, 2)
+    if cfg.sim_type == "gaussian":
+        dis = ((unf - feats.unsqueeze(4)) ** 2).sum(dim=1)
+        return feats, torch.exp(-dis / cfg.sigma ** 2).permute(0, 3, 1, 2)
+    if cfg.sim_type != "cosine":
+        raise ValueError()
     sim = F.cosine_similarity(unf, feats.unsqueeze(4), dim=1)
     return feats, sim.permute(0, 3, 1, 2)
 
@@ -51,6 +62,15 @@ def cross_prob_diag(logits: torch.Tensor, cfg: LossCfg) -> torch.Tensor:
     if cfg.detach_unfold:
         q = q.detach()
     q = q.view(B, -1, k2, H, W).permute(0, 1, 3, 4, 2)
+    return p.unsqueeze(4).repeat(1, 1, 1, 1, k2) * q
+
+
+def cross_prob_diag_ema(logits_trg: torch.Tensor, logits_ema: torch.Tensor, cfg: LossCfg) -> torch.Tensor:
+    """get_cross_prob_map_diag_ema, pfgst_loss.py:161-178 -> (B,C,H,W,k*k): q from the teacher's logits."""
+    B, C, H, W = logits_trg.shape
+    k2 = cfg.kernel_size ** 2
+    p = F.softmax(logits_trg, dim=1)
+    q = _unfold(F.softmax(logits_ema, dim=1), cfg).view(B, -1, k2, H, W).permute(0, 1, 3, 4, 2)
     return p.unsqueeze(4).repeat(1, 1, 1, 1, k2) * q
 
 
@@ -88,7 +108,10 @@ def pfgst_loss(tensors: dict, cfg: LossCfg) -> dict:
     unf_trg = _unfold(trg.float(), cfg).view(-1, k2, H, W).long()
     trg_eroded = unf_trg.sum(dim=1).unsqueeze(1) == k2
 
-    cross = cross_prob_diag(logits_trg, cfg)
+    if cfg.cross_prob_type == "ema":
+        cross = cross_prob_diag_ema(logits_trg, tensors["logits_ema"], cfg)
+    else:
+        cross = cross_prob_diag(logits_trg, cfg)
     _, sim_ema = neighbourhood_cosine(x_ema, (H, W), cfg)
     _, sim_src = neighbourhood_cosine(x_src, (H, W), cfg)
 

@@ -55,6 +55,13 @@ SIGNATURES: dict[str, tuple] = {
                                       _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp, _vp]),
     "pfst_pfgst_loss_bwd": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
                                       _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pfst_pfgst_loss_ws_bytes_ex": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32]),
+    "pfst_pfgst_loss_fwd_ex": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
+                                         _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp,
+                                         _i32, _f32, _vp, _vp]),
+    "pfst_pfgst_loss_bwd_ex": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
+                                         _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp,
+                                         _i32, _f32, _vp, _vp]),
     "pfst_class_quantile_ws_bytes": (_i64, [_i64, _i32, _i32]),
     "pfst_class_quantile": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "pfst_weighted_ce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp]),

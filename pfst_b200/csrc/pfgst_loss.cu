@@ -44,6 +44,12 @@ struct LossParams {
   uint8_t* lab;               // (B, gh, gw)        resampled source label (0..255)
   uint8_t* flags;             // (B, gh, gw)        bit0 = gt != 255, bit1 = target pixel (mix mask == 0)
   long long* raw;             // [16] integer accumulators of the statistics kernel (see kFix) + block counter
+  // options beyond the shipped configuration (pfgst_loss.py:16-18)
+  int gauss;                  // sim_type: 0 = 'cosine', 1 = 'gaussian' exp(-|x_n - x_m|^2 / sigma^2) (:189-191)
+  float inv_sigma2;           // 1 / sigma^2
+  const float* logits_q;      // cross_prob_type='ema' (:161-178): teacher logits (B,C,gh,gw) or null
+  float* prob_q;              // (B,C,gh,gw) softmax of logits_q (workspace) or null: q = unfold(prob_q)
+  float* dcp;                 // detach_unfold=False (:148-149): (B,9,gh,gw) d loss / d cross-prob (workspace) or null
 };
 
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
@@ -121,6 +127,24 @@ pfgst_loss_prep_kernel(const LossParams P, int blocks_a) {
     if (c < P.C) po[c * gplane] = zr[c] * inv;
   P.lab[i] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
   P.flags[i] = (uint8_t)((g != 255 ? 1 : 0) | (mx <= 0 ? 2 : 0));   // (1 - mix) > 0.5
+  if (P.logits_q) {     // cross_prob_type='ema': q comes from the teacher's logits, already on the loss grid
+    const float* zq = P.logits_q + (int64_t)b * P.C * gplane + r;
+    float* pq = P.prob_q + (int64_t)b * P.C * gplane + r;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) zr[c] = c < P.C ? zq[c * gplane] : -INFINITY;
+    m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) m = fmaxf(m, zr[c]);
+    s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < P.C) { zr[c] = expf(zr[c] - m); s += zr[c]; }
+    }
+    const float invq = 1.f / s;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < P.C) pq[c * gplane] = zr[c] * invq;
+  }
 }
 
 // ---- one (tap, pixel) thread: warp = tap k (0..8), lane = pixel of the block's 32 ---------
@@ -175,14 +199,23 @@ __device__ __forceinline__ void load_tap(const LossParams& P, int k, int b, int 
     // forward taps (k > 4) are stored at n, backward taps at the neighbour (symmetry)
     else if (k > 4)  { de = dme[(k - 4) * fplane + fn]; ds = dms[(k - 4) * fplane + fn]; }
     else             { de = dme[(4 - k) * fplane + fm]; ds = dms[(4 - k) * fplane + fm]; }
-    t.inv_m_src = ins[fm];
-    t.s_ema = de * (ine[fn] * ine[fm]);
-    t.s_src = ds * (c.inv_n_src * t.inv_m_src);
+    if (P.gauss) {    // exp(-|x_n - x_m|^2 / sigma^2), |x_n - x_m|^2 = |x_n|^2 + |x_m|^2 - 2 x_n.x_m  (>= 0)
+      t.s_ema = expf(-fmaxf(dme[fn] + dme[fm] - 2.f * de, 0.f) * P.inv_sigma2);
+      t.s_src = expf(-fmaxf(dms[fn] + dms[fm] - 2.f * ds, 0.f) * P.inv_sigma2);
+    } else {
+      t.inv_m_src = ins[fm];
+      t.s_ema = de * (ine[fn] * ine[fm]);
+      t.s_src = ds * (c.inv_n_src * t.inv_m_src);
+    }
     t.gm = yy * P.gw + xx;
     gk = lab[t.gm];
     const unsigned f = flg[t.gm];
     t.nb_valid = (f & 1u) != 0;
     t.trg = (f & 2u) != 0;
+  }
+  else if (P.gauss) {   // zero padding of the unfold: the neighbour is the zero vector (cosine: similarity 0)
+    t.s_ema = expf(-dme[fn] * P.inv_sigma2);
+    t.s_src = expf(-dms[fn] * P.inv_sigma2);
   }
   t.pos_pair = gk == g0;
 }
@@ -285,7 +318,7 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
       const bool top = rd < P.top_k + 1, bot = ra < P.top_k;
       if (top || bot) {
         const float* pn = P.prob + (int64_t)c.b * P.C * plane + (int64_t)c.y * P.gw + c.x;
-        const float* pm = P.prob + (int64_t)c.b * P.C * plane + t.gm;
+        const float* pm = (P.prob_q ? P.prob_q : P.prob) + (int64_t)c.b * P.C * plane + t.gm;
         float cp = 0.f;
         {
           const int pl = (int)plane;
@@ -425,16 +458,19 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         __syncthreads();
         a_pos = s_k[0]; c_pos = s_k[1]; a_neg = s_k[2]; c_neg = s_k[3];
         fmean_pos = s_k[4]; fmean_neg = s_k[5]; g_pos = s_k[6]; g_neg = s_k[7];
-        want_logits = grad_logits != nullptr && s_any != 0;
+        // (detach_unfold=False: the d loss / d cross-prob maps are always written, zeros included)
+        want_logits = P.dcp ? true : (grad_logits != nullptr && s_any != 0);
       }
       if (live) {
         // --- x_src: gather-form coefficients ---
-        if (k != 4 && t.in) {
+        if (k != 4 && (t.in || P.gauss)) {
           const float S = t.s_src;
           const float g = t.pos_pair ? a_pos + c_pos * (S - fmean_pos) : a_neg + c_neg * (S - fmean_neg);
-          // the pair (n, m) is counted once from n (if n is valid) and once from m (if m is valid)
-          const float W = g * ((c.valid_src ? 1.f : 0.f) + (t.nb_valid ? 1.f : 0.f));
-          cf += W * c.inv_n_src * t.inv_m_src;
+          // the pair (n, m) is counted once from n (if n is valid) and once from m (if m is valid);
+          // a padded (zero-vector) neighbour only from n, and only the Gaussian similarity depends on x_n then
+          const float W = g * ((c.valid_src ? 1.f : 0.f) + ((t.in && t.nb_valid) ? 1.f : 0.f));
+          // cosine: dS/dx_n = x_m / (|n||m|) - S x_n / |n|^2;  gaussian: dS/dx_n = (2/sigma^2) S (x_m - x_n)
+          if (t.in) cf += P.gauss ? W * S * (2.f * P.inv_sigma2) : W * c.inv_n_src * t.inv_m_src;
           bs = W * S;
         }
       }
@@ -447,7 +483,7 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         float bsum = 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j) bsum += s_bs[j][p];
-        cf -= bsum * c.inv_n_src * c.inv_n_src;
+        cf -= P.gauss ? bsum * (2.f * P.inv_sigma2) : bsum * c.inv_n_src * c.inv_n_src;
       }
       if (want_logits) {
         // --- logits_trg: through p only (q detached) ---
@@ -464,12 +500,14 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
           dcp = (top ? -t.s_ema * g_pos : 0.f) + (bot ? (1.f - t.s_ema) * g_neg : 0.f);
         }
         s_dcp[k][p] = dcp;
+        if (P.dcp && live) P.dcp[((int64_t)b * 9 + k) * gplane + y * P.gw + x] = dcp;
         __syncthreads();
         // class-parallel: this thread owns classes k, k+9, ... of pixel p
         float dp[kLpMaxOwn], pc[kLpMaxOwn];
         float part = 0.f;
         const float* pb = P.prob + (int64_t)b * P.C * gplane;
-        if (in_mk) {
+        const float* pbq = (P.prob_q ? P.prob_q : P.prob) + (int64_t)b * P.C * gplane;   // q = neighbours' distribution
+        if (in_mk && !P.dcp) {
 #pragma unroll
           for (int j = 0; j < kLpMaxOwn; ++j) {
             const int cc = k + 9 * j;
@@ -477,11 +515,11 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
             if (cc < P.C) {
               // all nine neighbour probabilities requested at once (zero-weight taps read a valid
               // address and are dropped by the select: 0 * NaN must not leak)
-              const float* pcl = pb + (int64_t)cc * gplane;
+              const float* pcl = pbq + (int64_t)cc * gplane;
               float q[9];
 #pragma unroll
               for (int kk = 0; kk < 9; ++kk) q[kk] = pcl[s_gm[kk][p]];
-              pc[j] = pcl[y * P.gw + x];
+              pc[j] = pb[(int64_t)cc * gplane + y * P.gw + x];
               float d = 0.f;
 #pragma unroll
               for (int kk = 0; kk < 9; ++kk) {
@@ -495,7 +533,7 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         }
         s_dot[k][p] = part;
         __syncthreads();
-        if (in_mk) {
+        if (in_mk && !P.dcp) {
           float dot = 0.f;
 #pragma unroll
           for (int j = 0; j < 9; ++j) dot += s_dot[j][p];
@@ -519,6 +557,65 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
     }
   if (live && coef) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
 }
+
+// ---- detach_unfold=False (pfgst_loss.py:148-149 not taken): cross_prob = p * unfold(p) sends gradient
+// through BOTH factors. With D_k(n) = d loss / d cross_prob_k(n) (written by the kernel above),
+//   d loss / d p_m[c] = sum_k D_k(m) p_{m+delta_k}[c]  +  sum_k D_k(m-delta_k) p_{m-delta_k}[c]
+// (the second sum is the pixel's role as somebody's neighbour; padded neighbours carry no gradient),
+// followed by the soft-max backward. One thread per loss pixel; off the shipped path.
+template <int CMAX>
+__global__ void __launch_bounds__(128)
+pfgst_loss_unfold_grad_kernel(const LossParams P, float* __restrict__ grad_logits) {
+  const int gplane = P.gh * P.gw;
+  const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= (int64_t)P.B * gplane) return;
+  const int b = (int)(i / gplane), r = (int)(i - (int64_t)b * gplane);
+  const int y = r / P.gw, x = r - y * P.gw;
+  const float* pb = P.prob + (int64_t)b * P.C * gplane;
+  const float* db = P.dcp + (int64_t)b * 9 * gplane;
+  float dp[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) dp[c] = 0.f;
+  bool touched = false;
+  for (int k = 0; k < 9; ++k) {
+    const int oy = (k / 3 - 1) * P.dil, ox = (k % 3 - 1) * P.dil;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      // side 0: this pixel as the centre of its own tap k; side 1: as the neighbour of the pixel at -delta_k
+      const int sy = side == 0 ? y : y - oy, sx = side == 0 ? x : x - ox;   // pixel whose D_k is used
+      const int py = side == 0 ? y + oy : sy, px = side == 0 ? x + ox : sx; // pixel whose p multiplies it
+      if (sy < 0 || sy >= P.gh || sx < 0 || sx >= P.gw || py < 0 || py >= P.gh || px < 0 || px >= P.gw) continue;
+      const float w = db[k * gplane + sy * P.gw + sx];
+      if (w == 0.f) continue;
+      touched = true;
+      const float* pp = pb + py * P.gw + px;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < P.C) dp[c] = fmaf(w, pp[c * gplane], dp[c]);
+    }
+  }
+  if (!touched) return;      // grad_logits was zero-filled
+  float pc[CMAX], dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    pc[c] = c < P.C ? pb[c * gplane + r] : 0.f;
+    dot = fmaf(pc[c], dp[c], dot);
+  }
+  const int ly = nearest_src(y, P.lscale_h, P.lh), lx = nearest_src(x, P.lscale_w, P.lw);
+  const int lplane = P.lh * P.lw;
+  float* gz = grad_logits + (int64_t)b * P.C * lplane + ly * P.lw + lx;
+  const bool shared_src = P.lscale_h < 1.f || P.lscale_w < 1.f;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    if (c < P.C) {
+      const float v = pc[c] * (dp[c] - dot);
+      if (shared_src) atomicAdd(gz + c * lplane, v); else gz[c * lplane] = v;
+    }
+  }
+}
+
+// bits of the `options` argument of the *_ex entry points
+constexpr int kOptGauss = 1, kOptProbEma = 2, kOptUnfoldGrad = 4;
 
 static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, int fh, int fw, int up,
                        const float* logits, int C, int lh, int lw, float lsh, float lsw, const int64_t* gt,
@@ -544,6 +641,28 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
   P.lab = reinterpret_cast<uint8_t*>(P.prob + (size_t)B * C * gplane);
   P.flags = P.lab + (size_t)B * gplane;
   P.raw = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(P.flags + (size_t)B * gplane) + 15) & ~(uintptr_t)15);
+  P.gauss = 0; P.inv_sigma2 = 0.f; P.logits_q = nullptr; P.prob_q = nullptr; P.dcp = nullptr;
+  return PFST_OK;
+}
+
+// the optional regions follow the 16 accumulators: prob_q (B,C,gh,gw), then dcp (B,9,gh,gw)
+static int apply_options(LossParams& P, int options, float sigma, const float* logits_ema) {
+  if (options & ~(kOptGauss | kOptProbEma | kOptUnfoldGrad)) return PFST_ERR_INVALID_ARG;
+  float* extra = reinterpret_cast<float*>(P.raw + 16);
+  const size_t gplane = (size_t)P.gh * P.gw;
+  if (options & kOptGauss) {
+    if (!(sigma > 0.f)) return PFST_ERR_INVALID_ARG;
+    P.gauss = 1;
+    P.inv_sigma2 = 1.f / (sigma * sigma);
+  }
+  if (options & kOptProbEma) {
+    if (!logits_ema) return PFST_ERR_INVALID_ARG;
+    P.logits_q = logits_ema;
+    P.prob_q = extra;
+    extra += (size_t)P.B * P.C * gplane;
+  }
+  // q from the teacher carries no gradient: detach_unfold is irrelevant then (pfgst_loss.py:161-178)
+  if ((options & kOptUnfoldGrad) && !(options & kOptProbEma)) P.dcp = extra;
   return PFST_OK;
 }
 
@@ -551,21 +670,31 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
 
 extern "C" {
 
-int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up) {
+int64_t pfst_pfgst_loss_ws_bytes_ex(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up, int32_t options) {
   if (B < 0 || C < 1 || fh < 1 || fw < 1 || up < 1) return 0;
   const size_t gplane = (size_t)fh * fw * up * up;
+  size_t extra = 0;
+  if (options & pfst::kOptProbEma) extra += (size_t)B * C * gplane * sizeof(float);
+  else if (options & pfst::kOptUnfoldGrad) extra += (size_t)B * 9 * gplane * sizeof(float);
   return (int64_t)(pfst::ws_floats((int)B, C, fh, fw, up) * sizeof(float) + 2 * (size_t)B * gplane + 16 +
-                   16 * sizeof(long long) + 16);
+                   16 * sizeof(long long) + 16 + extra);
 }
 
-int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
-                        const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
-                        float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
-                        int32_t dilation, int32_t top_k, const float* weights6_host, void* workspace,
-                        double* stats, float* losses, float* density, uint8_t* eroded, void* stream) {
+int64_t pfst_pfgst_loss_ws_bytes(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up) {
+  return pfst_pfgst_loss_ws_bytes_ex(B, C, fh, fw, up, 0);
+}
+
+int pfst_pfgst_loss_fwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
+                           const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
+                           float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
+                           int32_t dilation, int32_t top_k, const float* weights6_host, void* workspace,
+                           double* stats, float* losses, float* density, uint8_t* eroded, int32_t options,
+                           float sigma, const float* logits_ema, void* stream) {
   pfst::LossParams P;
-  const int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
-                                   mix, gt_h, gt_w, dilation, top_k, weights6_host, workspace);
+  int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
+                             mix, gt_h, gt_w, dilation, top_k, weights6_host, workspace);
+  if (rc != PFST_OK) return rc;
+  rc = pfst::apply_options(P, options, sigma, logits_ema);
   if (rc != PFST_OK) return rc;
   if (!stats || !losses) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -590,16 +719,29 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
   return PFST_OK;
 }
 
-int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
+int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
                         const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
                         float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
-                        int32_t dilation, int32_t top_k, const float* weights6_host, const void* workspace,
-                        const double* stats, const float* grad_losses, float* coef, float* grad_logits,
-                        void* stream) {
+                        int32_t dilation, int32_t top_k, const float* weights6_host, void* workspace,
+                        double* stats, float* losses, float* density, uint8_t* eroded, void* stream) {
+  return pfst_pfgst_loss_fwd_ex(dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt, mix, gt_h,
+                                gt_w, dilation, top_k, weights6_host, workspace, stats, losses, density, eroded, 0,
+                                0.f, nullptr, stream);
+}
+
+int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
+                           const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
+                           float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
+                           int32_t dilation, int32_t top_k, const float* weights6_host, const void* workspace,
+                           const double* stats, const float* grad_losses, float* coef, float* grad_logits,
+                           int32_t options, float sigma, const float* logits_ema, void* stream) {
   pfst::LossParams P;
-  const int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
-                                   mix, gt_h, gt_w, dilation, top_k, weights6_host, const_cast<void*>(workspace));
+  int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
+                             mix, gt_h, gt_w, dilation, top_k, weights6_host, const_cast<void*>(workspace));
   if (rc != PFST_OK) return rc;
+  rc = pfst::apply_options(P, options, sigma, logits_ema);
+  if (rc != PFST_OK) return rc;
+  if (!grad_logits) P.dcp = nullptr;        // nothing consumes the d loss / d cross-prob maps then
   if (!stats || !grad_losses || (!coef && !grad_logits)) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (grad_logits)
@@ -611,7 +753,25 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
   const dim3 grid((unsigned)((fw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)fh, (unsigned)P.B);
   pfst::pfgst_loss_bwd_kernel<<<grid, pfst::kLpThreads, 0, s>>>(P, stats, grad_losses, coef, grad_logits);
   PFST_CHECK_LAUNCH("pfst_pfgst_loss_bwd");
+  if (P.dcp) {      // detach_unfold=False: the logits gradient needs every pixel's d loss / d cross-prob map
+    const int64_t n = (int64_t)P.B * P.gh * P.gw;
+    auto k2 = C <= 8 ? pfst::pfgst_loss_unfold_grad_kernel<8>
+                     : (C <= 40 ? pfst::pfgst_loss_unfold_grad_kernel<40> : pfst::pfgst_loss_unfold_grad_kernel<pfst::kMaxC>);
+    k2<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, grad_logits);
+    PFST_CHECK_LAUNCH("pfst_pfgst_loss_bwd/unfold_grad");
+  }
   return PFST_OK;
+}
+
+int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
+                        const float* logits, int32_t C, int32_t lh, int32_t lw, float lscale_h,
+                        float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
+                        int32_t dilation, int32_t top_k, const float* weights6_host, const void* workspace,
+                        const double* stats, const float* grad_losses, float* coef, float* grad_logits,
+                        void* stream) {
+  return pfst_pfgst_loss_bwd_ex(dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt, mix, gt_h,
+                                gt_w, dilation, top_k, weights6_host, workspace, stats, grad_losses, coef,
+                                grad_logits, 0, 0.f, nullptr, stream);
 }
 
 }  // extern "C"

@@ -3,9 +3,12 @@
 Same constructor arguments, same `forward(tensors) -> dict` contract (six
 autograd-connected 0-dim `loss_*` tensors + the 'vis|density_sim_feat' tuple),
 computed by four sm_100a kernels (csrc/neigh.cu, csrc/pfgst_loss.cu) instead of
-~60 ATen kernels, two 604 MB im2col buffers and 3+ host syncs. Only the branch the
-shipped configs use is implemented (configs/pfst/*.py:34-47); every other option
-raises instead of silently computing something else.
+~60 ATen kernels, two 604 MB im2col buffers and 3+ host syncs. Besides the branch the
+shipped configs use (configs/pfst/*.py:34-47: cosine, cross_prob_type='trg',
+detach_unfold=True) the kernels cover sim_type='gaussian' (:189-191),
+cross_prob_type='ema' (:161-178) and detach_unfold=False (:148-149); the remaining
+options (src_perc, proj_net_cfg, the margin losses, kernel_size != 3, top_k=None) raise
+instead of silently computing something else.
 """
 from __future__ import annotations
 
@@ -25,7 +28,7 @@ class _PFGSTLossFn(torch.autograd.Function):
     logits_trg (through p only, q detached) and x_src, exactly as in the reference."""
 
     @staticmethod
-    def forward(ctx, logits_trg, x_src, x_ema, gt_src, mix_masks, cfg):
+    def forward(ctx, logits_trg, x_src, x_ema, gt_src, mix_masks, cfg, logits_ema=None):
         logits_trg = logits_trg.contiguous()
         x_src = x_src.contiguous()
         x_ema = x_ema.contiguous()
@@ -35,8 +38,13 @@ class _PFGSTLossFn(torch.autograd.Function):
         if x_ema.shape != x_src.shape:
             raise PfstError("PFGSTLoss: x_ema / x_src shape mismatch")
         dots, ks = ops.neigh_dots(x_ema, x_src, geo.dilation // geo.up)
+        opts, sigma = cfg.get("options", 0), cfg.get("sigma", 30.0)
+        if logits_ema is not None:
+            logits_ema = logits_ema.detach().contiguous()
         losses, stats, density, eroded = ops.pfgst_loss_fwd(dots, ks, geo, logits_trg, gt_src, mix_masks,
-                                                            cfg["top_k"], cfg["w6"])
+                                                            cfg["top_k"], cfg["w6"], options=opts, sigma=sigma,
+                                                            logits_ema=logits_ema)
+        ctx.logits_ema = logits_ema
         ctx.save_for_backward(logits_trg, x_src, gt_src, mix_masks, dots, stats[0], stats[1])
         ctx.geo, ctx.ks, ctx.cfg = geo, ks, cfg
         ctx.mark_non_differentiable(density, eroded)
@@ -49,9 +57,11 @@ class _PFGSTLossFn(torch.autograd.Function):
         geo, cfg = ctx.geo, ctx.cfg
         need_logits, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         coef, glog = ops.pfgst_loss_bwd(dots, ctx.ks, geo, logits_trg, gt_src, mix_masks, cfg["top_k"], cfg["w6"],
-                                        stats, grad_losses.contiguous().float(), want_logits_grad=need_logits)
+                                        stats, grad_losses.contiguous().float(), want_logits_grad=need_logits,
+                                        options=cfg.get("options", 0), sigma=cfg.get("sigma", 30.0),
+                                        logits_ema=ctx.logits_ema)
         gx = ops.neigh_grad(x_src, coef, geo.dilation // geo.up) if need_x else None
-        return glog, gx, None, None, None, None
+        return glog, gx, None, None, None, None, None
 
 
 @LOSSES.register_module()
@@ -63,8 +73,10 @@ class PFGSTLoss(nn.Module):
                  detach_unfold=False, cross_prob_type='trg', downscale=None):
         super().__init__()
         unsupported = []
-        if sim_type != 'cosine':
-            unsupported.append(f"sim_type={sim_type!r} (only 'cosine')")
+        if sim_type not in ('cosine', 'gaussian'):
+            raise ValueError()                      # pfgst_loss.py:198-199
+        if sim_type == 'gaussian' and not float(sigma) > 0:
+            unsupported.append(f"sigma={sigma} (must be positive)")
         if kernel_size != 3:
             unsupported.append(f"kernel_size={kernel_size} (only 3)")
         if top_k is None or not (1 <= int(top_k) <= 4):
@@ -75,10 +87,8 @@ class PFGSTLoss(nn.Module):
             unsupported.append("proj_net_cfg")
         if src_loss_type != 'mean_std':
             unsupported.append(f"src_loss_type={src_loss_type!r} (only 'mean_std')")
-        if not detach_unfold:
-            unsupported.append("detach_unfold=False (the shipped configs set True)")
-        if cross_prob_type != 'trg':
-            unsupported.append(f"cross_prob_type={cross_prob_type!r} (only 'trg')")
+        if cross_prob_type not in ('trg', 'ema'):
+            unsupported.append(f"cross_prob_type={cross_prob_type!r} ('trg' or 'ema')")
         if unsupported:
             raise PfstError("PFGSTLoss (B200 path) does not implement: " + "; ".join(unsupported))
         if not isinstance(weights, dict):
@@ -88,22 +98,33 @@ class PFGSTLoss(nn.Module):
         self.kernel_size = kernel_size
         self.weights = weights
         self.sim_type = sim_type
+        self.sigma = sigma
         self.feat_level = feat_level
         self.detach_unfold = detach_unfold
         self.cross_prob_type = cross_prob_type
         self.downscale = downscale
         self.src_loss_type = src_loss_type
+        options = ((ops.LOSS_SIM_GAUSSIAN if sim_type == 'gaussian' else 0) |
+                   (ops.LOSS_CROSS_PROB_EMA if cross_prob_type == 'ema' else 0) |
+                   (0 if detach_unfold else ops.LOSS_UNFOLD_GRAD))
         self._cfg = dict(top_k=self.top_k, dilation=self.dilation, downscale=downscale,
                          w6=(weights['src_pos'], weights['src_neg'], weights['src_pos_std'],
-                             weights['src_neg_std'], weights['sim_pos'], weights['sim_neg']))
+                             weights['src_neg_std'], weights['sim_pos'], weights['sim_neg']),
+                         options=options, sigma=float(sigma))
+
+    @property
+    def shipped_branch(self) -> bool:
+        """True for the configuration the fused launch groups of PluginEngine / SelfTrainingStep are built for."""
+        return self._cfg["options"] == 0
 
     def forward(self, tensors):
         logits_trg = tensors['logits_trg']
         gt_src = tensors['gt_src']
         x_ema = tensors['x_ema'][self.feat_level] if self.feat_level is not None else tensors['x_ema']
         x_src = tensors['x_src'][self.feat_level] if self.feat_level is not None else tensors['x_src']
+        logits_ema = tensors['logits_ema'] if self.cross_prob_type == 'ema' else None
         losses, density, eroded = _PFGSTLossFn.apply(logits_trg, x_src, x_ema.detach(), gt_src,
-                                                     tensors['mix_masks'], self._cfg)
+                                                     tensors['mix_masks'], self._cfg, logits_ema)
         out = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
         out['vis|density_sim_feat'] = (tensors.get('img_trg'), density, eroded.bool())
         return out

@@ -485,37 +485,58 @@ def _w6(weights6):
     return arr
 
 
-def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, want_vis=True):
+LOSS_SIM_GAUSSIAN, LOSS_CROSS_PROB_EMA, LOSS_UNFOLD_GRAD = 1, 2, 4     # include/pfst_sm100.h PFST_LOSS_*
+
+
+def _loss_options(options: int, logits_ema, geo: LossGeometry):
+    if options & LOSS_CROSS_PROB_EMA:
+        if logits_ema is None:
+            raise PfstError("PFGSTLoss(cross_prob_type='ema') needs tensors['logits_ema']")
+        _dev(logits_ema, "logits_ema", torch.float32)
+        if tuple(logits_ema.shape) != (geo.B, geo.C, geo.gh, geo.gw):
+            # the reference multiplies p (B,C,H,W,k) with unfold(softmax(logits_ema)) element-wise
+            # (pfgst_loss.py:175): any other shape fails there too
+            raise PfstError(f"PFGSTLoss(cross_prob_type='ema'): logits_ema {tuple(logits_ema.shape)} must have the "
+                            f"loss-grid shape {(geo.B, geo.C, geo.gh, geo.gw)} (the reference broadcasts p * q)")
+        return logits_ema.data_ptr()
+    return None
+
+
+def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, want_vis=True,
+                   options: int = 0, sigma: float = 30.0, logits_ema=None):
     """-> (losses float32[6], (stats float64[16], workspace), density|None, eroded|None)."""
     dev = logits.device
     _dev(dots, "dots", torch.float32)
     _dev(logits, "logits", torch.float32)
     _dev(gt, "gt", torch.int64)
     _dev(mix, "mix", torch.int64)
+    q_ptr = _loss_options(options, logits_ema, geo)
     stats = torch.empty(16, dtype=torch.float64, device=dev)
-    ws_bytes = int(_lib.load().pfst_pfgst_loss_ws_bytes(geo.B, geo.C, geo.fh, geo.fw, geo.up))
+    ws_bytes = int(_lib.load().pfst_pfgst_loss_ws_bytes_ex(geo.B, geo.C, geo.fh, geo.fw, geo.up, int(options)))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     losses = torch.empty(6, dtype=torch.float32, device=dev)
     density = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.float32, device=dev) if want_vis else None
     eroded = torch.empty((geo.B, 1, geo.gh, geo.gw), dtype=torch.uint8, device=dev) if want_vis else None
-    _lib.call("pfst_pfgst_loss_fwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
+    _lib.call("pfst_pfgst_loss_fwd_ex", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
               geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), losses.data_ptr(),
               None if density is None else density.data_ptr(), None if eroded is None else eroded.data_ptr(),
-              _stream())
+              int(options), float(sigma), q_ptr, _stream())
     return losses, (stats, ws), density, eroded
 
 
 def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, stats, grad_losses,
-                   want_logits_grad=True):
+                   want_logits_grad=True, options: int = 0, sigma: float = 30.0, logits_ema=None):
     """-> (coef (B,9,fh,fw), grad_logits|None)."""
     dev = logits.device
     _dev(grad_losses, "grad_losses", torch.float32)
+    q_ptr = _loss_options(options, logits_ema, geo)
     stats, ws = stats
     coef = torch.empty((geo.B, 9, geo.fh, geo.fw), dtype=torch.float32, device=dev)
     glog = torch.empty_like(logits) if want_logits_grad else None
-    _lib.call("pfst_pfgst_loss_bwd", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
+    _lib.call("pfst_pfgst_loss_bwd_ex", dots.data_ptr(), ks, geo.B, geo.fh, geo.fw, geo.up, logits.data_ptr(),
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
               geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), grad_losses.data_ptr(),
-              coef.data_ptr(), None if glog is None else glog.data_ptr(), _stream())
+              coef.data_ptr(), None if glog is None else glog.data_ptr(), int(options), float(sigma), q_ptr,
+              _stream())
     return coef, glog

@@ -212,7 +212,7 @@ class PFGST(UDADecorator):
         if not self.fused or not self.apply_aux or len(self.aux_losses) != 1:
             return None
         mod = self.aux_losses[0]
-        return mod if type(mod) is PFGSTLoss and mod.feat_level is None else None
+        return mod if type(mod) is PFGSTLoss and mod.feat_level is None and mod.shipped_branch else None
 
     def _get_engine(self, dev, loss_module) -> PluginEngine:
         if self._engine is None or self._engine.device != dev:

@@ -165,6 +165,58 @@ def gen_pfgst_loss():
     np.savez_compressed(OUT / "pfgst_loss.npz", **out)
 
 
+LOSS_OPTION_CASES = {
+    # name: (geometry case, reference constructor options)
+    "gauss": (dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=11), dict(sim_type='gaussian', sigma=3.0,
+                                                                          detach_unfold=True)),
+    "gauss33": (dict(B=2, C=33, H=48, D=16, dil=2, down=None, seed=12), dict(sim_type='gaussian', sigma=2.0,
+                                                                            detach_unfold=True)),
+    "ema": (dict(B=2, C=6, H=64, D=16, dil=2, down=None, seed=13), dict(sim_type='cosine', cross_prob_type='ema',
+                                                                       detach_unfold=True)),
+    "unfold": (dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=14), dict(sim_type='cosine', detach_unfold=False)),
+    "unfold33": (dict(B=2, C=33, H=48, D=16, dil=2, down=None, seed=15), dict(sim_type='gaussian', sigma=2.5,
+                                                                             detach_unfold=False)),
+}
+
+
+def loss_option_inputs(c):
+    g = torch.Generator().manual_seed(c["seed"])
+    B, C, H = c["B"], c["C"], c["H"]
+    gt = blocky_labels(B, H, H, C, g, min_rect=4, max_rect=max(8, H // 2))
+    logits = 2.0 * torch.randn((B, C, H // 4, H // 4), generator=g)
+    x_src = torch.relu(torch.randn((B, c["D"], H // 8, H // 8), generator=g))
+    x_ema = torch.relu(torch.randn((B, c["D"], H // 8, H // 8), generator=g))
+    gh = int((H // 4) * c["down"]) if c["down"] is not None else H // 4
+    logits_ema = 2.0 * torch.randn((B, C, gh, gh), generator=g)      # already on the loss grid (pfgst_loss.py:175)
+    return gt, logits, x_src, x_ema, logits_ema
+
+
+def gen_pfgst_loss_options():
+    """PFGSTLoss options outside the shipped configuration (sim_type='gaussian', cross_prob_type='ema',
+    detach_unfold=False), written by the reference module."""
+    L = R.pfgst_loss()
+    D = R.dacs_transforms()
+    out = {}
+    for name, (c, opts) in LOSS_OPTION_CASES.items():
+        gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
+        np.random.seed(3)
+        mix = torch.cat(D.get_class_masks(gt), 0)
+        mod = L.PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None,
+                          downscale=c["down"], **opts)
+        lt = logits.clone().requires_grad_(True)
+        xs = x_src.clone().requires_grad_(True)
+        with R.cpu_cuda_identity():
+            res = mod(dict(logits_trg=lt, logits_ema=logits_ema, gt_src=gt, x_ema=x_ema, x_src=xs, img_trg=None,
+                           mix_masks=mix))
+        sum(res[k] for k in LOSS_KEYS).backward()
+        out.update({f"{name}_mix": mix.numpy().astype(np.uint8),
+                    f"{name}_losses": np.array([float(res[k]) for k in LOSS_KEYS], dtype=np.float32),
+                    f"{name}_grad_x_src": xs.grad.numpy(), f"{name}_grad_logits": lt.grad.numpy(),
+                    f"{name}_density": res['vis|density_sim_feat'][1].numpy(),
+                    f"{name}_eroded": res['vis|density_sim_feat'][2].numpy()})
+    np.savez_compressed(OUT / "pfgst_loss_options.npz", **out)
+
+
 STEP_CFG = dict(max_iters=100, alpha=0.999, pseudo_threshold=0.6, pseudo_weight_ignore_top=2,
                 pseudo_weight_ignore_bottom=3, imnet_feature_dist_lambda=0, imnet_feature_dist_classes=None,
                 imnet_feature_dist_scale_min_ratio=None, mix='class', blur=False, color_jitter_strength=0.2,
@@ -360,7 +412,7 @@ if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_loss_options, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
                gen_offline_labels):
         fn()
         print("wrote", fn.__name__)

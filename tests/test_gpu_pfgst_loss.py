@@ -149,10 +149,63 @@ def test_pfgst_loss_empty_target_region(cuda):
 
 
 def test_unsupported_options_raise():
-    for kw in (dict(sim_type='gaussian'), dict(detach_unfold=False), dict(cross_prob_type='ema'),
-               dict(src_loss_type='margin'), dict(kernel_size=5)):
+    for kw in (dict(src_loss_type='margin'), dict(kernel_size=5), dict(src_perc=0.5), dict(top_k=None),
+               dict(proj_net_cfg=dict(in_channels=4, out_channels=4)), dict(cross_prob_type='src')):
         args = dict(top_k=3, dilation=2, kernel_size=3, weights=W6, sim_type='cosine', feat_level=None,
                     detach_unfold=True, downscale=0.5)
         args.update(kw)
         with pytest.raises(ops.PfstError):
             PFGSTLoss(**args)
+
+
+@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33"])
+def test_pfgst_loss_options_match_reference_golden_and_oracle(cuda, name):
+    """The PFGSTLoss options outside the shipped configuration (pfgst_loss.py:16-18): sim_type='gaussian',
+    cross_prob_type='ema', detach_unfold=False — CUDA path vs the fixture the reference module wrote
+    (tests/golden/pfgst_loss_options.npz) and vs the oracle, 1e-5 of the gradient scale."""
+    from pathlib import Path
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs
+    z = np.load(Path(__file__).resolve().parent / "golden" / "pfgst_loss_options.npz")
+    c, opts = LOSS_OPTION_CASES[name]
+    gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
+    mix = torch.from_numpy(z[f"{name}_mix"]).long()
+    mod = PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"],
+                    **opts)
+    assert not mod.shipped_branch
+    t = dict(logits_trg=logits.clone().to(cuda).requires_grad_(True), logits_ema=logits_ema.to(cuda),
+             gt_src=gt.to(cuda), x_ema=x_ema.to(cuda), x_src=x_src.clone().to(cuda).requires_grad_(True),
+             img_trg=None, mix_masks=mix.to(cuda))
+    out = mod(t)
+    sum(out[k] for k in LOSS_KEYS).backward()
+    cfg = OL.LossCfg(dilation=c["dil"], downscale=c["down"], sim_type=opts.get("sim_type", "cosine"),
+                     sigma=opts.get("sigma", 30.0), cross_prob_type=opts.get("cross_prob_type", "trg"),
+                     detach_unfold=opts.get("detach_unfold", True))
+    to = dict(logits_trg=logits.clone().requires_grad_(True), logits_ema=logits_ema, gt_src=gt, x_ema=x_ema,
+              x_src=x_src.clone().requires_grad_(True), img_trg=None, mix_masks=mix)
+    oo = OL.pfgst_loss(to, cfg)
+    sum(oo[k] for k in LOSS_KEYS).backward()
+    for i, k in enumerate(LOSS_KEYS):
+        a = float(out[k])
+        for b in (float(z[f"{name}_losses"][i]), float(oo[k])):
+            assert abs(a - b) <= 1e-5 * abs(b) + 1e-9, (k, a, b)
+    assert np.array_equal(out['vis|density_sim_feat'][2].cpu().numpy(), z[f"{name}_eroded"])
+    assert np.allclose(out['vis|density_sim_feat'][1].cpu().numpy(), z[f"{name}_density"], rtol=0, atol=2e-6)
+    for key, ref, ora in (("x_src", z[f"{name}_grad_x_src"], to["x_src"].grad),
+                          ("logits_trg", z[f"{name}_grad_logits"], to["logits_trg"].grad)):
+        g = t[key].grad.cpu()
+        for want in (torch.from_numpy(ref), ora):
+            scale = want.abs().max()
+            assert (g - want).abs().max() <= 1e-5 * scale + 1e-12, (key, float((g - want).abs().max()), float(scale))
+
+
+def test_pfgst_loss_option_errors(cuda):
+    with pytest.raises(ValueError):
+        PFGSTLoss(top_k=3, dilation=2, kernel_size=3, weights=W6, sim_type='l2', detach_unfold=True)
+    mod = PFGSTLoss(top_k=3, dilation=2, kernel_size=3, weights=W6, sim_type='cosine', feat_level=None,
+                    cross_prob_type='ema', detach_unfold=True, downscale=0.5)
+    inp = step_inputs(WORKLOADS["tiny"])
+    t = dict(logits_trg=inp['logits_trg'].to(cuda), logits_ema=inp['logits_trg'].to(cuda), gt_src=inp['gt'].to(cuda),
+             x_ema=inp['x_ema'].to(cuda), x_src=inp['x_src'].to(cuda), img_trg=None,
+             mix_masks=torch.zeros_like(inp['gt']).to(cuda))
+    with pytest.raises(ops.PfstError):        # logits_ema is not on the (down-scaled) loss grid: the reference fails too
+        mod(t)

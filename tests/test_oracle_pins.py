@@ -92,7 +92,62 @@ def test_pfgst_loss_oracle_vs_golden(name):
     assert np.allclose(res['vis|density_sim_feat'][1].numpy(), z[f"{name}_density"], rtol=0, atol=1e-6)
 
 
+def _option_cfg(c, opts):
+    return OL.LossCfg(dilation=c["dil"], downscale=c["down"], sim_type=opts.get("sim_type", "cosine"),
+                      sigma=opts.get("sigma", 30.0), cross_prob_type=opts.get("cross_prob_type", "trg"),
+                      detach_unfold=opts.get("detach_unfold", True))
+
+
+@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33"])
+def test_pfgst_loss_option_oracle_vs_golden(name):
+    """sim_type='gaussian', cross_prob_type='ema', detach_unfold=False: the oracle against what the
+    reference module wrote (tests/golden/make_golden.py::gen_pfgst_loss_options)."""
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs
+    z = load("pfgst_loss_options.npz")
+    c, opts = LOSS_OPTION_CASES[name]
+    gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
+    lt, xs = logits.clone().requires_grad_(True), x_src.clone().requires_grad_(True)
+    res = OL.pfgst_loss(dict(logits_trg=lt, logits_ema=logits_ema, gt_src=gt, x_ema=x_ema, x_src=xs, img_trg=None,
+                             mix_masks=torch.from_numpy(z[f"{name}_mix"]).long()), _option_cfg(c, opts))
+    sum(res[k] for k in OL.LOSS_KEYS).backward()
+    got = np.array([float(res[k].detach()) for k in OL.LOSS_KEYS], dtype=np.float32)
+    assert np.allclose(got, z[f"{name}_losses"], rtol=2e-6, atol=1e-8)
+    assert np.allclose(xs.grad.numpy(), z[f"{name}_grad_x_src"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(lt.grad.numpy(), z[f"{name}_grad_logits"], rtol=1e-5, atol=1e-9)
+    assert np.array_equal(res['vis|density_sim_feat'][2].numpy(), z[f"{name}_eroded"])
+    assert np.allclose(res['vis|density_sim_feat'][1].numpy(), z[f"{name}_density"], rtol=0, atol=1e-6)
+
+
 # ------------------------------------------------------------------ live reference
+@needs_ref
+@pytest.mark.parametrize("name", ["gauss", "ema", "unfold33"])
+def test_pfgst_loss_option_oracle_equals_reference_live(name):
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs, W6
+    warnings.filterwarnings("ignore")
+    D, L = R.dacs_transforms(), R.pfgst_loss()
+    c, opts = LOSS_OPTION_CASES[name]
+    gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
+    np.random.seed(3)
+    mix = torch.cat(D.get_class_masks(gt), 0)
+    mod = L.PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"],
+                      **opts)
+
+    def t():
+        return dict(logits_trg=logits.clone().requires_grad_(True), logits_ema=logits_ema, gt_src=gt, x_ema=x_ema,
+                    x_src=x_src.clone().requires_grad_(True), img_trg=None, mix_masks=mix)
+
+    t1, t2 = t(), t()
+    with R.cpu_cuda_identity():
+        a = mod(t1)
+    b = OL.pfgst_loss(t2, _option_cfg(c, opts))
+    sum(a[k] for k in OL.LOSS_KEYS).backward()
+    sum(b[k] for k in OL.LOSS_KEYS).backward()
+    for k in OL.LOSS_KEYS:
+        assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
+    assert torch.equal(t1['x_src'].grad, t2['x_src'].grad)
+    assert torch.equal(t1['logits_trg'].grad, t2['logits_trg'].grad)
+
+
 @needs_ref
 def test_reference_golden_test_retargeted():
     """The reference's only golden test (tests/test_metrics.py:86-143): eval_metrics must equal

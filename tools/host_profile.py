@@ -22,7 +22,7 @@ if world > 1:
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
-wl = WORKLOADS["cfg2"]
+wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 g = torch.Generator().manual_seed(1234 + rank)
 np.random.seed(1234 + rank)
 inp = {k: v.to(dev) for k, v in step_inputs(wl, 1234 + rank).items()}
