@@ -478,6 +478,24 @@ int pfst_argmax_confusion(const float* logits, int64_t n_images, int32_t C, int6
                           int32_t reduce_zero_label, const uint8_t* lut, int64_t* conf,
                           int32_t per_image, void* pred_out, int32_t pred_dtype, void* stream);
 
+/* ---- V0: test-time sliding-window accumulation and flip ---------------------------
+ * The tensor arithmetic of EncoderDecoder.slide_inference / inference
+ * (rsiseg/models/segmentors/encoder_decoder.py:220-263, 312-324); the network pass on each crop
+ * stays with the caller.
+ *   pfst_slide_add       preds[:, :, y1:y1+ch, x1:x1+cw] += crop      (:245-249: `preds += F.pad(crop_seg_logit, ...)`,
+ *                        a full-size padded copy and a full-size add per window in the reference)
+ *   pfst_slide_finalize  out = flip(preds / count)                    (:255 `preds / count_mat`, :316-321 the flips;
+ *                        a flip commutes with the per-pixel soft-max of :311)
+ * The windows are a product of row and column intervals, so count_mat(y, x) = cnt_y[y] * cnt_x[x]
+ * (device float vectors of H and W entries built by the caller; both NULL = no division). preds / out:
+ * (B, C, H, W) fp32, crop: (B, C, ch, cw) fp32. out may equal preds when no flip is requested.
+ * Bit-exact with the reference: same additions in the same window order, IEEE division.              */
+int pfst_slide_add(float* preds, const float* crop, int64_t B, int32_t C, int32_t H, int32_t W,
+                   int32_t y1, int32_t x1, int32_t ch, int32_t cw, void* stream);
+int pfst_slide_finalize(const float* preds, const float* cnt_y, const float* cnt_x, int64_t B,
+                        int32_t C, int32_t H, int32_t W, int32_t flip_h, int32_t flip_v, float* out,
+                        void* stream);
+
 /* ---- strong augmentation: Gaussian blur of the mixed image -----
  * Replaces gaussian_blur, rsiseg/models/utils/dacs_transforms.py:88-107:
  *   kornia.filters.GaussianBlur2d(kernel_size=(ksize_y,ksize_x), sigma=(s,s))(data)

@@ -102,3 +102,64 @@ def pre_eval(seg_logits: torch.Tensor, gt_seg_maps, num_classes: int, ignore_ind
     preds = list(seg_argmax(seg_logits).cpu().numpy())
     return [areas(p, np.asarray(g), num_classes, ignore_index, label_map, reduce_zero_label)
             for p, g in zip(preds, gt_seg_maps)]
+
+
+def slide_inference(encode_decode, img: torch.Tensor, img_meta, rescale: bool, crop_size, stride, num_classes: int,
+                    align_corners: bool = False) -> torch.Tensor:
+    """EncoderDecoder.slide_inference, rsiseg/models/segmentors/encoder_decoder.py:220-263, statement for
+    statement (`encode_decode(img, img_meta) -> (seg_logit, states)` is the network pass)."""
+    F = torch.nn.functional
+    h_stride, w_stride = stride
+    h_crop, w_crop = crop_size
+    batch_size, _, h_img, w_img = img.size()
+    h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+    w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+    preds = img.new_zeros((batch_size, num_classes, h_img, w_img))
+    count_mat = img.new_zeros((batch_size, 1, h_img, w_img))
+    for h_idx in range(h_grids):
+        for w_idx in range(w_grids):
+            y1 = h_idx * h_stride
+            x1 = w_idx * w_stride
+            y2 = min(y1 + h_crop, h_img)
+            x2 = min(x1 + w_crop, w_img)
+            y1 = max(y2 - h_crop, 0)
+            x1 = max(x2 - w_crop, 0)
+            crop_seg_logit, _ = encode_decode(img[:, :, y1:y2, x1:x2], img_meta)
+            preds += F.pad(crop_seg_logit, (int(x1), int(preds.shape[3] - x2), int(y1), int(preds.shape[2] - y2)))
+            count_mat[:, :, y1:y2, x1:x2] += 1
+    assert (count_mat == 0).sum() == 0
+    preds = preds / count_mat
+    if rescale:
+        preds = F.interpolate(preds, size=tuple(img_meta[0]['ori_shape'][:2]), mode='bilinear',
+                              align_corners=align_corners)
+    return preds
+
+
+def inference(encode_decode, img, img_meta, rescale: bool, mode: str, crop_size=None, stride=None,
+              num_classes: int = 0, align_corners: bool = False):
+    """EncoderDecoder.inference (+ whole_inference), encoder_decoder.py:265-324 -> (soft-max output, states)."""
+    F = torch.nn.functional
+    assert mode in ['slide', 'whole']
+    ori_shape = img_meta[0]['ori_shape']
+    assert all(_['ori_shape'] == ori_shape for _ in img_meta)
+    if mode == 'slide':
+        seg_logit = slide_inference(encode_decode, img, img_meta, rescale, crop_size, stride, num_classes,
+                                    align_corners)
+        states = {}
+    else:
+        seg_logit, states = encode_decode(img, img_meta)
+        if rescale:
+            seg_logit = F.interpolate(seg_logit, size=tuple(ori_shape[:2]), mode='bilinear',
+                                      align_corners=align_corners)
+    output = F.softmax(seg_logit, dim=1)
+    if img_meta[0]['flip']:
+        flip_direction = img_meta[0]['flip_direction']
+        if type(flip_direction) != list:
+            flip_direction = [flip_direction]
+        for direction_ in flip_direction:
+            assert direction_ in ['horizontal', 'vertical']
+            if direction_ == 'horizontal':
+                output = output.flip(dims=(3, ))
+            elif direction_ == 'vertical':
+                output = output.flip(dims=(2, ))
+    return output, states

@@ -217,6 +217,50 @@ def gen_pfgst_loss_options():
     np.savez_compressed(OUT / "pfgst_loss_options.npz", **out)
 
 
+def slide_cases():
+    """(name, B, C, H, W, mode, crop, stride, flip, flip_direction, ori_shape, seed)"""
+    return [("slide", 2, 6, 24, 40, "slide", (16, 16), (8, 12), False, None, (24, 40), 0),
+            ("slide_flip", 2, 6, 24, 40, "slide", (16, 24), (8, 8), True, ["horizontal", "vertical"], (24, 40), 1),
+            ("slide_rescale", 1, 3, 20, 28, "slide", (12, 12), (8, 8), True, "horizontal", (31, 45), 2),
+            ("big_crop", 1, 33, 10, 14, "slide", (16, 12), (8, 8), False, None, (10, 14), 3),
+            ("whole_flip", 2, 6, 18, 22, "whole", None, None, True, "vertical", (27, 33), 4)]
+
+
+def synthetic_encode_decode(num_classes):
+    """A stand-in network pass whose output depends on the crop's content AND on the position inside the
+    crop (so overlapping windows disagree), built from single IEEE operations: bit-identical on CPU and GPU."""
+    def encode_decode(img, img_meta):
+        B, _, h, w = img.shape
+        ii = torch.arange(h, device=img.device, dtype=torch.float32).view(1, 1, h, 1)
+        jj = torch.arange(w, device=img.device, dtype=torch.float32).view(1, 1, 1, w)
+        chans = [img[:, c % 3:c % 3 + 1] * (0.5 + 0.25 * c) + torch.remainder(ii * 3 + jj * 5 + c, 7) * 0.125
+                 for c in range(num_classes)]
+        return torch.cat(chans, 1), {}
+    return encode_decode
+
+
+def slide_meta(flip, direction, ori_shape, B):
+    return [dict(ori_shape=tuple(ori_shape) + (3,), flip=flip, flip_direction=direction) for _ in range(B)]
+
+
+def gen_slide_inference():
+    """EncoderDecoder.slide_inference / inference / simple_test compiled from the reference source."""
+    out = {}
+    for name, B, C, H, W, mode, crop, stride, flip, direction, ori, seed in slide_cases():
+        g = torch.Generator().manual_seed(900 + seed)
+        img = torch.randn((B, 3, H, W), generator=g)
+        cfg = types.SimpleNamespace(mode=mode, crop_size=crop, stride=stride)
+        seg = R.reference_segmentor(synthetic_encode_decode(C), cfg, C)
+        meta = slide_meta(flip, direction, ori, B)
+        output, _ = seg.inference(img, meta, True)
+        seg_pred, _ = seg.simple_test(img, meta, True)
+        out[f"{name}_output"] = output.numpy()
+        out[f"{name}_pred"] = np.stack(seg_pred).astype(np.uint8)
+        if mode == "slide":
+            out[f"{name}_slide"] = seg.slide_inference(img, meta, False).numpy()
+    np.savez_compressed(OUT / "slide_inference.npz", **out)
+
+
 STEP_CFG = dict(max_iters=100, alpha=0.999, pseudo_threshold=0.6, pseudo_weight_ignore_top=2,
                 pseudo_weight_ignore_bottom=3, imnet_feature_dist_lambda=0, imnet_feature_dist_classes=None,
                 imnet_feature_dist_scale_min_ratio=None, mix='class', blur=False, color_jitter_strength=0.2,
@@ -412,7 +456,7 @@ if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_loss_options, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_loss_options, gen_slide_inference, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
                gen_offline_labels):
         fn()
         print("wrote", fn.__name__)

@@ -197,6 +197,41 @@ def simple_test_fns():
     return _cache["simple_test"]
 
 
+def inference_fns():
+    """-> dict of EncoderDecoder.{slide_inference, whole_inference, inference, simple_test} compiled
+    straight from the reference source (rsiseg/models/segmentors/encoder_decoder.py:220-353); `resize` is
+    the reference's own rsiseg/ops/wrappers.py function. Usable unbound on a duck-typed object that
+    supplies test_cfg, num_classes, align_corners and encode_decode."""
+    if "inference_fns" not in _cache:
+        import ast
+        import torch
+        import torch.nn.functional as F
+
+        class DataContainer:
+            pass
+
+        names = ("slide_inference", "whole_inference", "inference", "simple_test")
+        tree = ast.parse((REF_ROOT / "rsiseg/models/segmentors/encoder_decoder.py").read_text())
+        fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in names]
+        assert len(fns) == len(names)
+        ns = {"torch": torch, "F": F, "DataContainer": DataContainer, "resize": decode_head_loss_fns()[0]}
+        exec(compile(ast.Module(body=fns, type_ignores=[]), "ref:encoder_decoder.py", "exec"), ns)
+        _cache["inference_fns"] = {k: ns[k] for k in names}
+    return _cache["inference_fns"]
+
+
+def reference_segmentor(encode_decode, test_cfg, num_classes, align_corners=False):
+    """A duck-typed EncoderDecoder whose four inference methods are the reference's own code and whose
+    network pass is `encode_decode(img, img_meta) -> (seg_logit, states)`."""
+    import types
+    f = inference_fns()
+    obj = types.SimpleNamespace(test_cfg=test_cfg, num_classes=num_classes, align_corners=align_corners,
+                                encode_decode=encode_decode)
+    for k, fn in f.items():
+        setattr(obj, k, (lambda fn: lambda *a, **kw: fn(obj, *a, **kw))(fn))
+    return obj
+
+
 def simple_test_on_logits(seg_logits):
     """Run the reference's inference + simple_test on synthetic logits (whole mode, no flip)
     -> list of per-image int64 numpy arg-max maps, as simple_test returns them."""

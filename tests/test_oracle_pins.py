@@ -405,3 +405,41 @@ def test_strong_aug_oracle_equals_reference_class_live():
         ops_ = SA.draw_strong_aug(np.random, 20, (0.7, 1.3), (0.4, 1.6), 10)
         assert after == np.random.random()
         assert np.array_equal(SA.apply_strong_aug(img.copy(), ops_), ref), it
+
+
+# ------------------------------------------------------------------ test-time slide / flip inference
+def _slide_case_inputs(case):
+    from tests.golden.make_golden import slide_meta, synthetic_encode_decode
+    name, B, C, H, W, mode, crop, stride, flip, direction, ori, seed = case
+    g = torch.Generator().manual_seed(900 + seed)
+    return torch.randn((B, 3, H, W), generator=g), slide_meta(flip, direction, ori, B), synthetic_encode_decode(C)
+
+
+def test_slide_inference_oracle_vs_golden():
+    """oracle.metrics.slide_inference / inference against what the reference methods (compiled from
+    encoder_decoder.py:220-353) wrote: bit-exact."""
+    from tests.golden.make_golden import slide_cases
+    z = load("slide_inference.npz")
+    for case in slide_cases():
+        name, B, C, H, W, mode, crop, stride = case[:8]
+        img, meta, enc = _slide_case_inputs(case)
+        out, _ = om.inference(enc, img, meta, True, mode, crop, stride, C)
+        assert np.array_equal(out.numpy(), z[f"{name}_output"]), name
+        assert np.array_equal(out.argmax(dim=1).numpy().astype(np.uint8), z[f"{name}_pred"]), name
+        if mode == "slide":
+            raw = om.slide_inference(enc, img, meta, False, crop, stride, C)
+            assert np.array_equal(raw.numpy(), z[f"{name}_slide"]), name
+
+
+@needs_ref
+def test_slide_inference_oracle_equals_reference_live():
+    import types
+    from tests.golden.make_golden import slide_cases
+    for case in slide_cases():
+        name, B, C, H, W, mode, crop, stride = case[:8]
+        img, meta, enc = _slide_case_inputs(case)
+        img = img + 0.25                                   # not the fixture's input
+        seg = R.reference_segmentor(enc, types.SimpleNamespace(mode=mode, crop_size=crop, stride=stride), C)
+        want, _ = seg.inference(img, meta, True)
+        got, _ = om.inference(enc, img, meta, True, mode, crop, stride, C)
+        assert torch.equal(got, want), name
