@@ -14,6 +14,7 @@
 // Everything here works on maps of (B, few, g, g) floats — a few MB; the cost is
 // launch latency, not bandwidth. The heavy tensors are touched by neigh.cu only.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -404,20 +405,35 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
 // feature pixel (up = 1 unless the features are coarser than the loss grid).
 constexpr int kLpMaxOwn = (kMaxC + 8) / 9;     // classes a tap-thread owns in the logits gradient
 
-__global__ void __launch_bounds__(kLpThreads, 3)
+// UP2 = false: lane = feature pixel, the up x up loss pixels of a feature pixel in a serial loop (any up).
+// UP2 = true (up == 2, SeasonNet): lane = LOSS pixel of one row, the two loss rows of a feature row on two
+// groups of nine tap-warps, so the four loss pixels of a feature pixel run in parallel; their coefficient
+// contributions meet in shared memory and are summed in the serial loop's order (uy, ux).
+template <bool UP2>
+__global__ void __launch_bounds__(kLpThreads * (UP2 ? 2 : 1), UP2 ? 2 : 3)
 pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, const float* __restrict__ gout,
                       float* __restrict__ coef, float* __restrict__ grad_logits) {
-  __shared__ float s_se[9][kLpPix];
-  __shared__ uint8_t s_ok[9][kLpPix];
-  __shared__ float s_bs[9][kLpPix];           // W * S of every tap (centre-tap coefficient)
-  __shared__ float s_dcp[9][kLpPix];          // d loss / d cross-prob of every tap
-  __shared__ int s_gm[9][kLpPix];             // neighbour offsets (for the class-parallel pass)
-  __shared__ float s_dot[9][kLpPix];
-  const int k = threadIdx.x >> 5, p = threadIdx.x & 31;
+  constexpr int NR = UP2 ? 2 : 1;
+  __shared__ float s_se_[NR][9][kLpPix];
+  __shared__ uint8_t s_ok_[NR][9][kLpPix];
+  __shared__ float s_bs_[NR][9][kLpPix];           // W * S of every tap (centre-tap coefficient)
+  __shared__ float s_dcp_[NR][9][kLpPix];          // d loss / d cross-prob of every tap
+  __shared__ int s_gm_[NR][9][kLpPix];             // neighbour offsets (for the class-parallel pass)
+  __shared__ float s_dot_[NR][9][kLpPix];
+  const int wid = threadIdx.x >> 5, p = threadIdx.x & 31;
+  const int ry = UP2 ? wid / 9 : 0, k = UP2 ? wid % 9 : wid;
+  float (*s_se)[kLpPix] = s_se_[ry];
+  uint8_t (*s_ok)[kLpPix] = s_ok_[ry];
+  float (*s_bs)[kLpPix] = s_bs_[ry];
+  float (*s_dcp)[kLpPix] = s_dcp_[ry];
+  int (*s_gm)[kLpPix] = s_gm_[ry];
+  float (*s_dot)[kLpPix] = s_dot_[ry];
   const int64_t fplane = (int64_t)P.fh * P.fw, gplane = (int64_t)P.gh * P.gw;
-  // grid = (row segments of 32 feature pixels, feature rows, images)
-  const int b = blockIdx.z, fy = blockIdx.y, fx = blockIdx.x * kLpPix + p;
-  const bool live = fx < P.fw;
+  // grid = (row segments of 32 feature pixels [UP2: 32 loss pixels], feature rows, images)
+  const int b = blockIdx.z, fy = blockIdx.y;
+  const int xl = blockIdx.x * kLpPix + p;                     // UP2: loss-grid column; else feature column
+  const int fx = UP2 ? xl >> 1 : xl;
+  const bool live = UP2 ? xl < P.gw : fx < P.fw;
   const int r = fy * P.fw + fx;
 
   // the backward constants (fp64 divisions and square roots) once per block, not per thread
@@ -445,9 +461,10 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
   bool want_logits = false;     // block-uniform
 
   float cf = 0.f;
-  for (int uy = 0; uy < P.up; ++uy)
-    for (int ux = 0; ux < P.up; ++ux) {
-      const int y = fy * P.up + uy, x = fx * P.up + ux;
+  const int n_u = UP2 ? 1 : P.up;
+  for (int uy = 0; uy < n_u; ++uy)
+    for (int ux = 0; ux < n_u; ++ux) {
+      const int y = UP2 ? fy * 2 + ry : fy * P.up + uy, x = UP2 ? xl : fx * P.up + ux;
       Center c;
       Tap t;
       float bs = 0.f;
@@ -555,7 +572,16 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
       }
       __syncthreads();     // the shared arrays are rewritten by the next loss pixel
     }
-  if (live && coef) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
+  if (UP2) {
+    // the four loss pixels of a feature pixel: (uy, ux) order of the serial loop
+    s_dot_[ry][k][p] = cf;
+    __syncthreads();
+    if (ry == 0 && (p & 1) == 0 && live && coef)
+      coef[((int64_t)b * 9 + k) * fplane + r] =
+          ((s_dot_[0][k][p] + s_dot_[0][k][p + 1]) + s_dot_[1][k][p]) + s_dot_[1][k][p + 1];
+  } else {
+    if (live && coef) coef[((int64_t)b * 9 + k) * fplane + r] = cf;
+  }
 }
 
 // ---- detach_unfold=False (pfgst_loss.py:148-149 not taken): cross_prob = p * unfold(p) sends gradient
@@ -750,8 +776,14 @@ int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
   const int64_t total = (int64_t)P.B * fh * fw;
   if (total == 0) return PFST_OK;
   if (fh > 65535 || P.B > 65535) return PFST_ERR_UNSUPPORTED;
-  const dim3 grid((unsigned)((fw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)fh, (unsigned)P.B);
-  pfst::pfgst_loss_bwd_kernel<<<grid, pfst::kLpThreads, 0, s>>>(P, stats, grad_losses, coef, grad_logits);
+  static const bool no_up2 = getenv("PFST_LOSS_NO_UP2") != nullptr;       // A/B switch
+  if (up == 2 && !no_up2) {
+    const dim3 grid2((unsigned)((P.gw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)fh, (unsigned)P.B);
+    pfst::pfgst_loss_bwd_kernel<true><<<grid2, 2 * pfst::kLpThreads, 0, s>>>(P, stats, grad_losses, coef, grad_logits);
+  } else {
+    const dim3 grid((unsigned)((fw + pfst::kLpPix - 1) / pfst::kLpPix), (unsigned)fh, (unsigned)P.B);
+    pfst::pfgst_loss_bwd_kernel<false><<<grid, pfst::kLpThreads, 0, s>>>(P, stats, grad_losses, coef, grad_logits);
+  }
   PFST_CHECK_LAUNCH("pfst_pfgst_loss_bwd");
   if (P.dcp) {      // detach_unfold=False: the logits gradient needs every pixel's d loss / d cross-prob map
     const int64_t n = (int64_t)P.B * P.gh * P.gw;
