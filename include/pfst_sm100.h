@@ -297,6 +297,11 @@ int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
  * Anchor: PFGST.masked_feat_dist, rsiseg/models/uda/pfgst.py:168-177. Labels are
  * nearest-resampled to the feature grid as pfgst_loss.py:62 does.                  */
 
+/* 1 when pfst_proto_accum(feats with these shapes) runs as ONE masked-accumulation launch (few classes,
+ * no label sort: nothing to order against the TMA kernels) — schedulers then call
+ * pfst_proto_accum directly instead of pfst_proto_order + pfst_proto_accum_ordered. Host only.        */
+int pfst_proto_accum_is_masked(int32_t C, int32_t h, int32_t w);
+
 /* packed: float[C*D + C], ACCUMULATED INTO (caller zeroes it; it is the NCCL
  * all-reduce buffer): packed[c*D+d] += sum of feats[b,d,n] over pixels n with
  * label c (0 <= label < C, and conf >= conf_thr when conf != NULL);

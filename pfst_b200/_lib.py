@@ -67,6 +67,7 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_class_quantile_ws_bytes": (_i64, [_i64, _i32, _i32]),
     "pfst_class_quantile": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "pfst_weighted_ce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp]),
+    "pfst_proto_accum_is_masked": (C.c_int, [_i32, _i32, _i32]),
     "pfst_proto_accum": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _f32, _i32, _vp, _vp]),
     "pfst_proto_order_ws_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "pfst_proto_order": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _vp, _vp, _vp]),

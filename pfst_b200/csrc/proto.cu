@@ -305,6 +305,137 @@ proto_accum_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   }
 }
 
+// ---- few classes (C <= 8): masked accumulation, no sort ------------------------------------------
+// With a handful of classes the class test is cheaper than the sorted gather's list handling: a
+// block stages the label bytes of its (image, tile) once (16 gathers per thread, all in flight), then
+// every warp streams channel planes straight from global memory with 128-bit loads (eight in flight
+// per lane) and adds each value to the register accumulator of its class — 2 predicated instructions
+// per class and value, NC accumulators per lane, one warp reduction and one RED per (class, channel).
+// No sort kernel, no workspace, one launch; and the step no longer has a kernel that must be kept
+// away from the TMA kernels.
+constexpr int kPmThreads = 256;
+constexpr int kPmTile = 4096;
+
+template <int NC, bool FULL>
+__global__ void __launch_bounds__(kPmThreads, 2)
+proto_accum_masked_kernel(const float* __restrict__ feats, int D, int h, int w, const int64_t* __restrict__ labels,
+                          const float* __restrict__ conf, float conf_thr, int lab_h, int lab_w, int groups,
+                          float* __restrict__ packed, float* __restrict__ counts) {
+  __shared__ __align__(16) uint8_t lab_s[kPmTile];
+  const int hw = h * w;
+  const int n_tiles = (hw + kPmTile - 1) / kPmTile;
+  const int grp_id = blockIdx.x % groups;
+  const int tile_id = (blockIdx.x / groups) % n_tiles;
+  const int b = blockIdx.x / (groups * n_tiles);
+  const int p0 = tile_id * kPmTile;
+  const int np = min(kPmTile, hw - p0);                 // multiple of 4 (host checks hw % 4 == 0)
+  const int ch0 = (int)((int64_t)grp_id * D / groups), ch1 = (int)((int64_t)(grp_id + 1) * D / groups);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // A warp owns the channel planes ch0 + warp + 8 i and accumulates them TWO at a time: the class tests
+  // of a pixel (the bulk of the instructions) are shared by both planes. Work = chunks of 4 float4 per
+  // lane and plane; two chunks are in flight: the first is requested BEFORE the label staging below (it
+  // does not need the labels), then chunk t+1 is requested while chunk t is accumulated.
+  // FULL: the tile is a whole number of 128-float4 chunks (no bounds tests in the loop).
+  const int nvec = np / 4;                              // float4 groups of the tile
+  const int cpp = (nvec + 127) / 128;                   // chunks per plane pair
+  const int n_planes = ch1 - ch0 > warp ? (ch1 - ch0 - warp + 7) / 8 : 0;
+  const int n_pairs = (n_planes + 1) / 2;
+  const int total = n_pairs * cpp;
+  const float* base = feats + ((int64_t)b * D) * hw + p0;
+  struct Buf { float4 a[4], b[4]; };
+  auto issue = [&](int pair_i, int chunk_i, Buf& q) {
+    const int ch = ch0 + warp + 16 * pair_i;
+    const bool has_b = ch + 8 < ch1;
+    const float4* pa = reinterpret_cast<const float4*>(base + (int64_t)ch * hw) + lane + 128 * chunk_i;
+    const float4* pb = reinterpret_cast<const float4*>(base + (int64_t)(ch + (has_b ? 8 : 0)) * hw) + lane + 128 * chunk_i;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = FULL || lane + 128 * chunk_i + 32 * u < nvec;
+      q.a[u] = ok ? __ldcs(pa + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q.b[u] = (ok && has_b) ? __ldcs(pb + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  Buf va, vb;
+  if (total > 0) issue(0, 0, va);
+  {
+    const float sh = (float)lab_h / (float)h, sw = (float)lab_w / (float)w;
+    constexpr int kPer = kPmTile / kPmThreads;          // 16 label gathers per thread, issued back to back
+    uint8_t l[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int e = threadIdx.x + u * kPmThreads;
+      l[u] = e < np ? pr_label(labels, conf, conf_thr, b, p0 + e, w, lab_h, lab_w, sh, sw, NC) : (uint8_t)255;
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) lab_s[threadIdx.x + u * kPmThreads] = l[u];
+  }
+  __syncthreads();
+  if (grp_id == 0 && counts) {                          // pixel counts: once per (image, tile)
+    unsigned cnt[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) cnt[c] = 0;
+    for (int e = threadIdx.x; e < np; e += kPmThreads) {
+      const unsigned lv = lab_s[e];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cnt[c] += lv == (unsigned)c ? 1u : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const unsigned t = warp_sum(cnt[c]);
+      if (lane == 0 && t) atomicAdd(&counts[c], (float)t);
+    }
+  }
+  const uint32_t* lab_w4 = reinterpret_cast<const uint32_t*>(lab_s) + lane;
+  float acc_a[NC], acc_b[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc_a[c] = acc_b[c] = 0.f;
+  int pair_i = 0, chunk_i = 0;                          // position of the chunk being accumulated
+  auto process = [&](const Buf& q) {
+    const uint32_t* lp = lab_w4 + 128 * chunk_i;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t lw = (FULL || lane + 128 * chunk_i + 32 * u < nvec) ? lp[32 * u] : 0xffffffffu;
+      const unsigned l0 = __byte_perm(lw, 0, 0x4440), l1 = __byte_perm(lw, 0, 0x4441),
+                     l2 = __byte_perm(lw, 0, 0x4442), l3 = __byte_perm(lw, 0, 0x4443);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (l0 == (unsigned)c) { acc_a[c] += q.a[u].x; acc_b[c] += q.b[u].x; }
+        if (l1 == (unsigned)c) { acc_a[c] += q.a[u].y; acc_b[c] += q.b[u].y; }
+        if (l2 == (unsigned)c) { acc_a[c] += q.a[u].z; acc_b[c] += q.b[u].z; }
+        if (l3 == (unsigned)c) { acc_a[c] += q.a[u].w; acc_b[c] += q.b[u].w; }
+      }
+    }
+    if (++chunk_i == cpp) {                             // the plane pair is complete: one RED per class and plane
+      const int ch = ch0 + warp + 16 * pair_i;
+      const bool has_b = ch + 8 < ch1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float ta = warp_sum(acc_a[c]), tb = warp_sum(acc_b[c]);
+        if (lane == 0 && ta != 0.f) atomicAdd(packed + (int64_t)c * D + ch, ta);
+        if (lane == 0 && has_b && tb != 0.f) atomicAdd(packed + (int64_t)c * D + ch + 8, tb);
+        acc_a[c] = acc_b[c] = 0.f;
+      }
+      chunk_i = 0;
+      ++pair_i;
+    }
+  };
+  // request position: one chunk ahead of the accumulate position
+  int rp = 0, rc = 1;
+  if (rc == cpp) { rc = 0; rp = 1; }
+  for (int t = 0; t < total; t += 2) {
+    if (t + 1 < total) {
+      issue(rp, rc, vb);
+      if (++rc == cpp) { rc = 0; ++rp; }
+    }
+    process(va);
+    if (t + 2 < total) {
+      issue(rp, rc, va);
+      if (++rc == cpp) { rc = 0; ++rp; }
+    }
+    if (t + 1 < total) process(vb);
+  }
+}
+
 // ---- small planes (h*w <= kPsMaxHw, e.g. SeasonNet's 15x15): one block per (image, 32-channel chunk) --
 // The tile machinery above is built for 4096-pixel tiles: with 225 pixels and 33 classes every class
 // segment is padded to a 32-lane row (a 5x longer walk) and every (class, channel) costs a warp reduction
@@ -662,6 +793,11 @@ int pa_launch(const PaPlan& P, const float* feats, int64_t B, int32_t D, int32_t
 
 extern "C" {
 
+int pfst_proto_accum_is_masked(int32_t C, int32_t h, int32_t w) {
+  static const bool off = getenv("PFST_ACCUM_NO_MASKED") != nullptr;     // A/B switch
+  return (!off && C >= 1 && C <= 8 && ((int64_t)h * w) % 4 == 0 && (int64_t)h * w > pfst::kPsMaxHw) ? 1 : 0;
+}
+
 int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_t w,
                      const int64_t* labels, int32_t lab_h, int32_t lab_w, const float* conf,
                      float conf_thr, int32_t C, float* packed, void* stream) {
@@ -669,6 +805,36 @@ int pfst_proto_accum(const float* feats, int64_t B, int32_t D, int32_t h, int32_
     return PFST_ERR_INVALID_ARG;
   if (C > pfst::kPrMaxC) return PFST_ERR_UNSUPPORTED;
   if (B == 0) return PFST_OK;
+  const int64_t hw = (int64_t)h * w;
+  if (pfst_proto_accum_is_masked(C, h, w) && pfst::aligned16(feats)) {
+    // few classes: masked accumulation straight from global memory, no sort (see proto_accum_masked_kernel)
+    const int64_t n_tiles = (hw + pfst::kPmTile - 1) / pfst::kPmTile;
+    int64_t groups = ((int64_t)pfst::kNumSMs * 2) / (B * n_tiles);
+    const int64_t max_groups = (D + 15) / 16;                     // >= 2 planes per warp
+    if (groups > max_groups) groups = max_groups;
+    if (groups < 1) groups = 1;
+    const int64_t grid = B * n_tiles * groups;
+    if (grid > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+    void (*k)(const float*, int, int, int, const int64_t*, const float*, float, int, int, int, float*, float*);
+    // whole 128-float4 chunks in every tile: no bounds tests in the streaming loop
+    const bool full = hw % 512 == 0;
+#define PFST_PM_PICK(N) (full ? pfst::proto_accum_masked_kernel<N, true> : pfst::proto_accum_masked_kernel<N, false>)
+    switch (C) {
+      case 1: k = PFST_PM_PICK(1); break;
+      case 2: k = PFST_PM_PICK(2); break;
+      case 3: k = PFST_PM_PICK(3); break;
+      case 4: k = PFST_PM_PICK(4); break;
+      case 5: k = PFST_PM_PICK(5); break;
+      case 6: k = PFST_PM_PICK(6); break;
+      case 7: k = PFST_PM_PICK(7); break;
+      default: k = PFST_PM_PICK(8); break;
+    }
+#undef PFST_PM_PICK
+    k<<<(unsigned)grid, pfst::kPmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        feats, D, h, w, labels, conf, conf_thr, lab_h, lab_w, (int)groups, packed, packed + (int64_t)C * D);
+    PFST_CHECK_LAUNCH("pfst_proto_accum/masked");
+    return PFST_OK;
+  }
   PaPlan P;
   const int rc = pa_plan(P, feats, B, D, h, w, C, true);
   if (rc != PFST_OK) return rc;

@@ -171,14 +171,21 @@ class PluginEngine:
                       None if thr_vec is None else thr_vec.data_ptr(), 0, -1, b["label"].data_ptr(),
                       b["conf"].data_ptr(), None if b["wpart"] is None else b["wpart"].data_ptr(),
                       b["count"].data_ptr(), main.cuda_stream)
-            if dots_here:
+            masked = bank is not None and bank.masked(x_ema.shape[2], x_ema.shape[3])
+            if dots_here and not masked:
                 main.wait_event(self._ev[3])             # the label sort never runs next to a TMA dots kernel (step.py)
             if bank is not None:
                 Bf, D, h, w = x_ema.shape
-                bank.order(b["label"], Bf, h, w, b["conf"] if conf_thr is not None else None,
-                           conf_thr if conf_thr is not None else 0.0)
-                bank.accumulate_ordered(x_ema)           # x_ema again: L2 hits
+                cf = b["conf"] if conf_thr is not None else None
+                ct = conf_thr if conf_thr is not None else 0.0
+                if masked:                               # few classes: one masked launch, runs next to dots(x_ema)
+                    bank.accumulate(x_ema, b["label"], cf, ct)
+                else:
+                    bank.order(b["label"], Bf, h, w, cf, ct)
+                    bank.accumulate_ordered(x_ema)       # x_ema again: L2 hits
                 bank.finalize_captured(main.cuda_stream)
+            if dots_here and masked:
+                main.wait_event(self._ev[3])             # join the dots branch
 
         key = skey + (ema_logits.data_ptr(), None if not use_x else x_ema.data_ptr(), float(thr),
                       None if thr_vec is None else thr_vec.data_ptr())

@@ -101,12 +101,21 @@ class PrototypeBank:
     # P1
     def accumulate(self, feats: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None,
                    conf_thr: float = 0.0) -> None:
-        """packed += [class sums | class counts] of `feats` over `labels` — two launches: the label
-        sort (once per image tile) and the streaming segment-reduce (`order` / `accumulate_ordered`
-        can also be issued separately, e.g. the sort next to another kernel)."""
+        """packed += [class sums | class counts] of `feats` over `labels`. Few classes (`masked`): one
+        launch. Otherwise two: the label sort (once per image tile) and the streaming segment-reduce
+        (`order` / `accumulate_ordered` can also be issued separately)."""
         B, D, h, w = feats.shape
+        if self.masked(h, w):               # few classes: one masked-accumulation launch, no sort
+            self.accumulate_single_launch(feats, labels, conf, conf_thr)
+            return
         self.order(labels, B, h, w, conf, conf_thr)
         self.accumulate_ordered(feats)
+
+    def masked(self, h: int, w: int) -> bool:
+        """True when `accumulate` for (h, w) feature maps is the single masked-accumulation launch
+        (C <= 8, h*w % 4 == 0, not a small plane): no label-sort kernel exists then, so a scheduler has
+        nothing to keep away from the TMA neighbourhood kernels."""
+        return bool(_lib.load().pfst_proto_accum_is_masked(self.C, int(h), int(w)))
 
     def order(self, labels: torch.Tensor, B: int, h: int, w: int, conf: Optional[torch.Tensor] = None,
               conf_thr: float = 0.0) -> None:

@@ -132,6 +132,10 @@ class SelfTrainingStep:
             join.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), ops._stream())
+        if self.bank.masked(x_ema.shape[2], x_ema.shape[3]):
+            self.bank.accumulate(x_ema, b.label)                  # one masked launch next to dots(x_ema)
+            main.wait_event(join)
+            return
         main.wait_event(join)                                     # the sort never runs next to a TMA dots kernel
         self.bank.order(b.label, x_ema.shape[0], x_ema.shape[2], x_ema.shape[3])   # label sort: 1 block / tile
         self.bank.accumulate_ordered(x_ema)                       # x_ema again: L2 hits
@@ -233,19 +237,24 @@ class SelfTrainingStep:
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
         pl_done.record(main)
         unsafe = os.environ.get("PFST_DAG_UNSAFE") == "1"           # reproduces DESIGN.md 3.2 (tools/dots_replay_check.py)
+        masked = bank.masked(h, w)        # few classes: no sort kernel -> nothing to keep away from the TMA kernels
         self._comm.wait_event(pl_done)
-        if not unsafe:
-            self._comm.wait_event(dots_ema)
-        with torch.cuda.stream(self._comm):
-            bank.order(b.label, Bf, h, w)                             # label sort: 1 block / tile
-            sort_done.record(self._comm)
-        if not unsafe:
-            self._side.wait_event(sort_done)
+        if not masked:
+            if not unsafe:
+                self._comm.wait_event(dots_ema)
+            with torch.cuda.stream(self._comm):
+                bank.order(b.label, Bf, h, w)                         # label sort: 1 block / tile
+                sort_done.record(self._comm)
+            if not unsafe:
+                self._side.wait_event(sort_done)
         with torch.cuda.stream(self._side):
             ops.neigh_dots_slot(x_src, geo.dilation // geo.up, 1, b.dots)
             dots_src.record(self._side)
         with torch.cuda.stream(self._comm):
-            bank.accumulate_ordered(x_ema)                            # x_ema again: L2 hits
+            if masked:
+                bank.accumulate(x_ema, b.label)                       # one masked launch (x_ema: L2 hits after dots)
+            else:
+                bank.accumulate_ordered(x_ema)                        # x_ema again: L2 hits
             if reduce and bank.peer is None:
                 import torch.distributed as dist
                 dist.all_reduce(bank.packed, op=dist.ReduceOp.SUM, group=bank.group)
