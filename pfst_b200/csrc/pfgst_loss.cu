@@ -51,6 +51,8 @@ struct LossParams {
   const float* logits_q;      // cross_prob_type='ema' (:161-178): teacher logits (B,C,gh,gw) or null
   float* prob_q;              // (B,C,gh,gw) softmax of logits_q (workspace) or null: q = unfold(prob_q)
   float* dcp;                 // detach_unfold=False (:148-149): (B,9,gh,gw) d loss / d cross-prob (workspace) or null
+  int zfill;                  // backward: L > 0 = the logits are exactly L x the loss grid; every loss pixel then writes
+                              // its whole L x L cell of grad_logits (value at the sampled logit, zeros elsewhere): no memset
 };
 
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
@@ -476,7 +478,7 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         a_pos = s_k[0]; c_pos = s_k[1]; a_neg = s_k[2]; c_neg = s_k[3];
         fmean_pos = s_k[4]; fmean_neg = s_k[5]; g_pos = s_k[6]; g_neg = s_k[7];
         // (detach_unfold=False: the d loss / d cross-prob maps are always written, zeros included)
-        want_logits = P.dcp ? true : (grad_logits != nullptr && s_any != 0);
+        want_logits = P.dcp ? true : (grad_logits != nullptr && (s_any != 0 || P.zfill));
       }
       if (live) {
         // --- x_src: gather-form coefficients ---
@@ -550,7 +552,24 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         }
         s_dot[k][p] = part;
         __syncthreads();
-        if (in_mk && !P.dcp) {
+        if (P.zfill && live) {
+          // the whole L x L logit cell of this loss pixel (nearest sampling reads its first element)
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) dot += s_dot[j][p];
+          const int L = P.zfill;
+          float* gz = grad_logits + ((int64_t)b * P.C * P.lh + L * y) * P.lw + L * x;
+          const int lplane = P.lh * P.lw;
+#pragma unroll
+          for (int j = 0; j < kLpMaxOwn; ++j) {
+            const int cc = k + 9 * j;
+            if (cc < P.C) {
+              const float v = in_mk ? pc[j] * (dp[j] - dot) : 0.f;
+              for (int dy = 0; dy < L; ++dy)
+                for (int dx = 0; dx < L; ++dx) gz[cc * lplane + dy * P.lw + dx] = (dy | dx) == 0 ? v : 0.f;
+            }
+          }
+        } else if (in_mk && !P.dcp) {
           float dot = 0.f;
 #pragma unroll
           for (int j = 0; j < 9; ++j) dot += s_dot[j][p];
@@ -667,7 +686,7 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
   P.lab = reinterpret_cast<uint8_t*>(P.prob + (size_t)B * C * gplane);
   P.flags = P.lab + (size_t)B * gplane;
   P.raw = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(P.flags + (size_t)B * gplane) + 15) & ~(uintptr_t)15);
-  P.gauss = 0; P.inv_sigma2 = 0.f; P.logits_q = nullptr; P.prob_q = nullptr; P.dcp = nullptr;
+  P.gauss = 0; P.inv_sigma2 = 0.f; P.logits_q = nullptr; P.prob_q = nullptr; P.dcp = nullptr; P.zfill = 0;
   return PFST_OK;
 }
 
@@ -768,9 +787,17 @@ int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
   rc = pfst::apply_options(P, options, sigma, logits_ema);
   if (rc != PFST_OK) return rc;
   if (!grad_logits) P.dcp = nullptr;        // nothing consumes the d loss / d cross-prob maps then
+  {
+    // logits exactly L x the loss grid (the shipped configs: L = 2, or 1 without downscale): the kernel covers
+    // every element of grad_logits itself and the memset node in front of it is dropped
+    const int L = (int)lscale_h;
+    if (grad_logits && !P.dcp && L >= 1 && L <= 4 && (float)L == lscale_h && lscale_w == lscale_h &&
+        lh == L * P.gh && lw == L * P.gw)
+      P.zfill = L;
+  }
   if (!stats || !grad_losses || (!coef && !grad_logits)) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (grad_logits)
+  if (grad_logits && !P.zfill)
     PFST_CUDA_TRY(cudaMemsetAsync(grad_logits, 0, sizeof(float) * (size_t)P.B * C * lh * lw, s),
                   "pfst_pfgst_loss_bwd/memset");
   const int64_t total = (int64_t)P.B * fh * fw;
