@@ -703,6 +703,70 @@ proto_dist_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
   }
 }
 
+// ---- forward distance for planes a float4 cannot address (h*w % 4 != 0, e.g. SeasonNet's 15x15) --------
+// The kernel above then falls back to four guarded scalar loads per lane and, with 128-pixel tiles, to two
+// blocks per 225-pixel image (128 blocks on 148 SMs), each staging all C*D prototypes (67 KB at C = 33).
+// Here a block owns 32 consecutive pixels of one image (one per lane: a plane row of a warp is one
+// coalesced 128-byte request) and its eight warps split the channels, sixteen planes in flight per lane;
+// the prototype value of a pixel's class comes through L1 (the table is <= 67 KB and shared by every block
+// of the SM). The eight channel partials of a pixel are summed in warp order: deterministic like the kernel above.
+constexpr int kPdsUnroll = 16;
+
+__global__ void __launch_bounds__(kPrThreads)
+proto_dist_small_kernel(const float* __restrict__ feats, int D, int h, int w, const int64_t* __restrict__ labels,
+                        int lab_h, int lab_w, const float* __restrict__ mu, const uint8_t* __restrict__ seen, int C,
+                        float* __restrict__ dist, double* __restrict__ acc, float* __restrict__ loss,
+                        unsigned* __restrict__ done_counter) {
+  __shared__ float part[kPrWarps][32];
+  const int hw = h * w;
+  const int tiles = (hw + 31) / 32;
+  const int b = blockIdx.x / tiles, p0 = (blockIdx.x - b * tiles) * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = p0 + lane;
+  const bool in = p < hw;
+  uint8_t l = 255;
+  if (in) l = pr_label(labels, nullptr, 0.f, b, p, w, lab_h, lab_w, (float)lab_h / (float)h, (float)lab_w / (float)w, C);
+  if (l != 255 && seen && !seen[l]) l = 255;
+  const bool ok = l != 255;
+  const float* src = feats + (int64_t)b * D * hw + p;
+  const float* mrow = mu + (int64_t)(ok ? l : 0) * D;
+  float ss = 0.f;
+  if (in)
+    for (int d0 = warp; d0 < D; d0 += kPrWarps * kPdsUnroll) {
+      float v[kPdsUnroll], m[kPdsUnroll];
+#pragma unroll
+      for (int u = 0; u < kPdsUnroll; ++u) {
+        const int d = d0 + u * kPrWarps;
+        v[u] = d < D ? __ldg(src + (int64_t)d * hw) : 0.f;
+        m[u] = d < D ? __ldg(mrow + d) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kPdsUnroll; ++u) {
+        const float df = v[u] - m[u];
+        ss = fmaf(df, df, ss);
+      }
+    }
+  part[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kPrWarps; ++wv) t += part[wv][lane];
+    const float dn = ok ? sqrtf(t) : 0.f;
+    if (in) dist[(int64_t)b * hw + p] = dn;
+    const double bsum = warp_sum(ok ? (double)dn : 0.0), bcnt = warp_sum(ok ? 1.0 : 0.0);
+    if (lane == 0) {
+      if (bcnt != 0.0) { atomicAdd(&acc[0], bsum); atomicAdd(&acc[1], bcnt); }
+      __threadfence();
+      if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+        __threadfence();
+        const double sd = *((volatile double*)&acc[0]), n = *((volatile double*)&acc[1]);
+        loss[0] = (float)(sd / n);   // mean of an empty selection is NaN, as torch.mean
+      }
+    }
+  }
+}
+
 // all-class distances: out[b,c,n] = ||f_n - mu_c||_2
 __global__ void __launch_bounds__(kPrThreads)
 proto_dist_all_kernel(const float* __restrict__ feats, int B, int D, int h, int w,
@@ -927,6 +991,15 @@ static int proto_dist_common(bool bwd, const float* feats, int64_t B, int32_t D,
   if (!bwd) {
     if (!loss) return PFST_ERR_INVALID_ARG;
     PFST_CUDA_TRY(cudaMemsetAsync(acc, 0, 4 * sizeof(double), s), "pfst_proto_dist_fwd/memset");
+    static const bool no_small = getenv("PFST_DIST_NO_SMALL") != nullptr;       // A/B switch
+    if (hw % 4 != 0 && !no_small) {
+      const int64_t grid_s = B * ((hw + 31) / 32);
+      if (grid_s > 0x7fffffffll) return PFST_ERR_UNSUPPORTED;
+      pfst::proto_dist_small_kernel<<<(unsigned)grid_s, pfst::kPrThreads, 0, s>>>(
+          feats, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist, acc, loss, reinterpret_cast<unsigned*>(acc + 3));
+      PFST_CHECK_LAUNCH("pfst_proto_dist_fwd/small");
+      return PFST_OK;
+    }
     auto k = pfst::proto_dist_kernel<false>;
     PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "pfst_proto_dist_fwd/attr");
     k<<<(unsigned)grid, pfst::kPrThreads, smem, s>>>(feats, (int)B, D, h, w, labels, lab_h, lab_w, mu, seen, C, dist,
