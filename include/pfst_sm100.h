@@ -501,6 +501,17 @@ int pfst_slide_finalize(const float* preds, const float* cnt_y, const float* cnt
                         int32_t C, int32_t H, int32_t W, int32_t flip_h, int32_t flip_v, float* out,
                         void* stream);
 
+/* aug_test (encoder_decoder.py:355-373): `seg_logit = inference(imgs[0]); seg_logit += inference(imgs[i])...;
+ * seg_logit /= len(imgs); seg_pred = seg_logit.argmax(dim=1)` where `inference` returns the soft-max.
+ *   pfst_softmax_accum  acc (+)= softmax(logits) per pixel, torch CUDA's arithmetic (max, sum of expf in class
+ *                       order, IEEE division); first != 0 overwrites acc. logits / acc: (n_images, C, pixels) fp32.
+ *   pfst_div_argmax     pred = argmax_c (acc / divisor): first maximum wins, NaN counts as maximum (torch.argmax).
+ * The soft-max tensors of the augmentations never exist.                                                      */
+int pfst_softmax_accum(const float* logits, float* acc, int64_t n_images, int32_t C, int64_t pixels,
+                       int32_t first, void* stream);
+int pfst_div_argmax(const float* acc, int64_t n_images, int32_t C, int64_t pixels, float divisor,
+                    int64_t* pred, void* stream);
+
 /* ---- strong augmentation: Gaussian blur of the mixed image -----
  * Replaces gaussian_blur, rsiseg/models/utils/dacs_transforms.py:88-107:
  *   kornia.filters.GaussianBlur2d(kernel_size=(ksize_y,ksize_x), sigma=(s,s))(data)

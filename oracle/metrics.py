@@ -163,3 +163,18 @@ def inference(encode_decode, img, img_meta, rescale: bool, mode: str, crop_size=
             elif direction_ == 'vertical':
                 output = output.flip(dims=(2, ))
     return output, states
+
+
+def aug_test(encode_decode, imgs, img_metas, rescale: bool, mode: str, crop_size=None, stride=None,
+             num_classes: int = 0, align_corners: bool = False):
+    """EncoderDecoder.aug_test, encoder_decoder.py:355-373 -> (list of int64 numpy maps, {})."""
+    assert rescale
+    seg_logit, _ = inference(encode_decode, imgs[0], img_metas[0], rescale, mode, crop_size, stride, num_classes,
+                             align_corners)
+    for i in range(1, len(imgs)):
+        cur_seg_logit, _ = inference(encode_decode, imgs[i], img_metas[i], rescale, mode, crop_size, stride,
+                                     num_classes, align_corners)
+        seg_logit += cur_seg_logit
+    seg_logit /= len(imgs)
+    seg_pred = seg_logit.argmax(dim=1)
+    return list(seg_pred.cpu().numpy()), {}

@@ -64,6 +64,8 @@ SIGNATURES: dict[str, tuple] = {
                                          _i32, _f32, _vp, _vp]),
     "pfst_slide_add": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "pfst_slide_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pfst_softmax_accum": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp]),
+    "pfst_div_argmax": (C.c_int, [_vp, _i64, _i32, _i64, _f32, _vp, _vp]),
     "pfst_class_quantile_ws_bytes": (_i64, [_i64, _i32, _i32]),
     "pfst_class_quantile": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "pfst_weighted_ce": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp, _vp]),

@@ -10,7 +10,10 @@
 // flips are one pass (pfst_slide_finalize). Bit-exact with the reference: the same fp32 additions in the
 // same window order (x + 0 outside a window is x), an IEEE division by an exactly representable count,
 // and a flip commutes with the per-pixel soft-max that follows.
+#include <math.h>
+
 #include "common.cuh"
+#include "exp_exact.cuh"
 
 namespace pfst {
 
@@ -58,9 +61,81 @@ slide_finalize_kernel(const float* __restrict__ preds, const float* __restrict__
   }
 }
 
+// ---- aug_test (encoder_decoder.py:355-373): seg_logit = sum_i softmax(logits_i); seg_logit /= n; argmax ----
+// acc[b, c, p] (+)= softmax over c of logits[b, :, p], as torch's CUDA soft-max computes it along a
+// non-innermost dim (max, sum of expf(x - max) in class order, expf(x - max) / sum with an IEEE division);
+// first != 0 overwrites acc instead of adding (the reference starts from the first augmentation's output).
+__global__ void __launch_bounds__(kSlThreads)
+softmax_accum_kernel(const float* __restrict__ logits, float* __restrict__ acc, int64_t n_img, int C, int64_t pixels,
+                     int first) {
+  const int64_t total = n_img * pixels;
+  for (int64_t i = (int64_t)blockIdx.x * kSlThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kSlThreads) {
+    const int64_t b = i / pixels, p = i - b * pixels;
+    const float* x = logits + b * C * pixels + p;
+    float* a = acc + b * C * pixels + p;
+    float m = x[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, x[c * pixels]);
+    if (x[0] != x[0]) m = x[0];
+    bool nan = false;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = x[c * pixels];
+      nan |= v != v;
+      const ExpParts e = exp_split(v - m);
+      s = __fmaf_rn(e.scale, e.mant, s);
+    }
+    for (int c = 0; c < C; ++c) {
+      float q = __fdiv_rn(exp_exact(x[c * pixels] - m), s);
+      if (nan) q = __int_as_float(0x7fc00000);
+      a[c * pixels] = first ? q : __fadd_rn(a[c * pixels], q);
+    }
+  }
+}
+
+// pred[b, p] = argmax_c (acc[b, c, p] / n): first maximum wins, a NaN counts as the maximum (torch.argmax)
+__global__ void __launch_bounds__(kSlThreads)
+div_argmax_kernel(const float* __restrict__ acc, int64_t n_img, int C, int64_t pixels, float n, int64_t* __restrict__ pred) {
+  const int64_t total = n_img * pixels;
+  for (int64_t i = (int64_t)blockIdx.x * kSlThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kSlThreads) {
+    const int64_t b = i / pixels, p = i - b * pixels;
+    const float* a = acc + b * C * pixels + p;
+    float m = __fdiv_rn(a[0], n);
+    int am = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = __fdiv_rn(a[c * pixels], n);
+      if (m == m && (v > m || v != v)) { m = v; am = c; }
+    }
+    pred[i] = am;
+  }
+}
+
 }  // namespace pfst
 
 extern "C" {
+
+int pfst_softmax_accum(const float* logits, float* acc, int64_t n_images, int32_t C, int64_t pixels, int32_t first,
+                       void* stream) {
+  if (!logits || !acc || n_images < 0 || C < 1 || pixels < 1) return PFST_ERR_INVALID_ARG;
+  if (n_images == 0) return PFST_OK;
+  int64_t blocks = (n_images * pixels + pfst::kSlThreads - 1) / pfst::kSlThreads;
+  if (blocks > (int64_t)pfst::kNumSMs * 16) blocks = (int64_t)pfst::kNumSMs * 16;
+  pfst::softmax_accum_kernel<<<(unsigned)blocks, pfst::kSlThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, acc, n_images, C, pixels, first);
+  PFST_CHECK_LAUNCH("pfst_softmax_accum");
+  return PFST_OK;
+}
+
+int pfst_div_argmax(const float* acc, int64_t n_images, int32_t C, int64_t pixels, float divisor, int64_t* pred,
+                    void* stream) {
+  if (!acc || !pred || n_images < 0 || C < 1 || pixels < 1) return PFST_ERR_INVALID_ARG;
+  if (n_images == 0) return PFST_OK;
+  int64_t blocks = (n_images * pixels + pfst::kSlThreads - 1) / pfst::kSlThreads;
+  if (blocks > (int64_t)pfst::kNumSMs * 16) blocks = (int64_t)pfst::kNumSMs * 16;
+  pfst::div_argmax_kernel<<<(unsigned)blocks, pfst::kSlThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, n_images, C, pixels, divisor, pred);
+  PFST_CHECK_LAUNCH("pfst_div_argmax");
+  return PFST_OK;
+}
 
 int pfst_slide_add(float* preds, const float* crop, int64_t B, int32_t C, int32_t H, int32_t W, int32_t y1,
                    int32_t x1, int32_t ch, int32_t cw, void* stream) {

@@ -168,5 +168,28 @@ def simple_test(encode_decode: Callable, img, img_meta, rescale: bool = True, *,
     return seg_pred, state_list
 
 
+def aug_test(encode_decode: Callable, imgs, img_metas, rescale: bool = True, *, test_cfg, num_classes: int,
+             align_corners: bool = False):
+    """EncoderDecoder.aug_test (encoder_decoder.py:355-373): the soft-max outputs of the augmented
+    inferences are summed, divided by their number and arg-maxed. Here every augmentation's logits go
+    through `pfst_softmax_accum` (soft-max and accumulation in one pass: the per-augmentation soft-max
+    tensors never exist) and `pfst_div_argmax`. -> (list of int64 numpy maps, {})."""
+    assert rescale
+    acc = None
+    for i in range(len(imgs)):
+        logits, _ = inference_logits(encode_decode, imgs[i], img_metas[i], rescale, test_cfg, num_classes,
+                                     align_corners)
+        if acc is None:
+            acc = torch.empty_like(logits)
+        elif acc.shape != logits.shape:
+            raise PfstError(f"aug_test: augmentation {i} gives {tuple(logits.shape)}, the first {tuple(acc.shape)}")
+        B, Cn, H, W = logits.shape
+        _lib.call("pfst_softmax_accum", logits.data_ptr(), acc.data_ptr(), B, Cn, H * W, int(i == 0), ops._stream())
+    B, Cn, H, W = acc.shape
+    pred = torch.empty((B, H, W), dtype=torch.int64, device=acc.device)
+    _lib.call("pfst_div_argmax", acc.data_ptr(), B, Cn, H * W, float(len(imgs)), pred.data_ptr(), ops._stream())
+    return list(pred.cpu().numpy()), {}
+
+
 def make_test_cfg(mode='whole', crop_size=None, stride=None):
     return SimpleNamespace(mode=mode, crop_size=crop_size, stride=stride)

@@ -261,6 +261,40 @@ def gen_slide_inference():
     np.savez_compressed(OUT / "slide_inference.npz", **out)
 
 
+def aug_cases():
+    """(name, B, C, ori_shape, mode, crop, stride, [(H, W, flip, direction), ...], seed)"""
+    return [("whole3", 2, 6, (24, 40), "whole", None, None,
+             [(24, 40, False, None), (18, 30, True, "horizontal"), (30, 50, True, "vertical")], 0),
+            ("slide2", 1, 33, (20, 28), "slide", (12, 12), (8, 8),
+             [(20, 28, False, None), (26, 36, True, ["horizontal", "vertical"])], 1)]
+
+
+def aug_inputs(case):
+    name, B, C, ori, mode, crop, stride, augs, seed = case
+    g = torch.Generator().manual_seed(950 + seed)
+    imgs = [torch.randn((B, 3, H, W), generator=g) for (H, W, _, _) in augs]
+    metas = [slide_meta(flip, direction, ori, B) for (_, _, flip, direction) in augs]
+    return imgs, metas
+
+
+def gen_aug_test():
+    """EncoderDecoder.aug_test compiled from the reference source (encoder_decoder.py:355-373)."""
+    out = {}
+    for case in aug_cases():
+        name, B, C, ori, mode, crop, stride, augs, seed = case
+        imgs, metas = aug_inputs(case)
+        seg = R.reference_segmentor(synthetic_encode_decode(C), types.SimpleNamespace(mode=mode, crop_size=crop,
+                                                                                       stride=stride), C)
+        pred, _ = seg.aug_test(imgs, metas, True)
+        out[f"{name}_pred"] = np.stack(pred).astype(np.uint8)
+        acc = None                                   # the averaged soft-max, for the near-tie mask of the tests
+        for im, me in zip(imgs, metas):
+            o, _ = seg.inference(im, me, True)
+            acc = o if acc is None else acc + o
+        out[f"{name}_avg"] = (acc / len(imgs)).numpy()
+    np.savez_compressed(OUT / "aug_test.npz", **out)
+
+
 STEP_CFG = dict(max_iters=100, alpha=0.999, pseudo_threshold=0.6, pseudo_weight_ignore_top=2,
                 pseudo_weight_ignore_bottom=3, imnet_feature_dist_lambda=0, imnet_feature_dist_classes=None,
                 imnet_feature_dist_scale_min_ratio=None, mix='class', blur=False, color_jitter_strength=0.2,
@@ -456,7 +490,7 @@ if __name__ == "__main__":
     warnings.filterwarnings("ignore")
     assert R.available(), "reference checkout not found"
     torch.set_num_threads(1)      # bit-stable reductions
-    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_loss_options, gen_slide_inference, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
+    for fn in (gen_metrics, gen_ema, gen_pseudo_mix, gen_pfgst_loss, gen_pfgst_loss_options, gen_slide_inference, gen_aug_test, gen_pfgst_step, gen_weighted_ce, gen_eval_logits, gen_strong_aug,
                gen_offline_labels):
         fn()
         print("wrote", fn.__name__)

@@ -198,8 +198,8 @@ def simple_test_fns():
 
 
 def inference_fns():
-    """-> dict of EncoderDecoder.{slide_inference, whole_inference, inference, simple_test} compiled
-    straight from the reference source (rsiseg/models/segmentors/encoder_decoder.py:220-353); `resize` is
+    """-> dict of EncoderDecoder.{slide_inference, whole_inference, inference, simple_test, aug_test} compiled
+    straight from the reference source (rsiseg/models/segmentors/encoder_decoder.py:220-373); `resize` is
     the reference's own rsiseg/ops/wrappers.py function. Usable unbound on a duck-typed object that
     supplies test_cfg, num_classes, align_corners and encode_decode."""
     if "inference_fns" not in _cache:
@@ -210,7 +210,7 @@ def inference_fns():
         class DataContainer:
             pass
 
-        names = ("slide_inference", "whole_inference", "inference", "simple_test")
+        names = ("slide_inference", "whole_inference", "inference", "simple_test", "aug_test")
         tree = ast.parse((REF_ROOT / "rsiseg/models/segmentors/encoder_decoder.py").read_text())
         fns = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in names]
         assert len(fns) == len(names)

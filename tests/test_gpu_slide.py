@@ -91,3 +91,37 @@ def test_cpu_tensors_are_rejected():
     enc = synthetic_encode_decode(3)
     with pytest.raises(PfstError):
         E.slide_logits(enc, torch.zeros(1, 3, 8, 8), slide_meta(False, None, (8, 8), 1), (4, 4), (4, 4), 3)
+
+
+def test_aug_test_matches_reference_golden(cuda):
+    """aug_test (encoder_decoder.py:355-373): soft-max accumulation over augmentations + arg-max, against the
+    fixture the reference method wrote; labels equal wherever the two largest averaged probabilities are more
+    than 1e-6 apart (CPU vs CUDA soft-max differ in the last bit)."""
+    from tests.golden.make_golden import aug_cases, aug_inputs
+    z = np.load(G / "aug_test.npz")
+    for case in aug_cases():
+        name, B, C, ori, mode, crop, stride, augs, seed = case
+        imgs, metas = aug_inputs(case)
+        enc = synthetic_encode_decode(C)
+        pred, st = E.aug_test(enc, [im.to(cuda) for im in imgs], metas, True,
+                              test_cfg=E.make_test_cfg(mode, crop, stride), num_classes=C)
+        assert st == {} and len(pred) == B and pred[0].dtype == np.int64
+        assert _same_labels(np.stack(pred), z[f"{name}_pred"].astype(np.int64), z[f"{name}_avg"]), name
+        assert (np.stack(pred) == z[f"{name}_pred"]).mean() > 0.999
+
+
+def test_softmax_accum_equals_torch_cuda_softmax(cuda):
+    """pfst_softmax_accum restates torch's CUDA soft-max along dim 1: bit-identical sums on the device."""
+    from pfst_b200 import _lib, ops
+    g = torch.Generator().manual_seed(5)
+    xs = [(3.0 * torch.randn((2, 7, 33, 21), generator=g)).to(cuda) for _ in range(3)]
+    acc = torch.empty_like(xs[0])
+    want = None
+    for i, x in enumerate(xs):
+        _lib.call("pfst_softmax_accum", x.data_ptr(), acc.data_ptr(), 2, 7, 33 * 21, int(i == 0), ops._stream())
+        sm = torch.softmax(x, dim=1)
+        want = sm if want is None else want + sm
+    assert torch.equal(acc, want)
+    pred = torch.empty((2, 33, 21), dtype=torch.int64, device=cuda)
+    _lib.call("pfst_div_argmax", acc.data_ptr(), 2, 7, 33 * 21, 3.0, pred.data_ptr(), ops._stream())
+    assert torch.equal(pred, (want / 3).argmax(dim=1))

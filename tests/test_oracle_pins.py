@@ -443,3 +443,23 @@ def test_slide_inference_oracle_equals_reference_live():
         want, _ = seg.inference(img, meta, True)
         got, _ = om.inference(enc, img, meta, True, mode, crop, stride, C)
         assert torch.equal(got, want), name
+
+
+def test_aug_test_oracle_vs_golden_and_reference():
+    """oracle.metrics.aug_test against the fixture the reference method wrote and, when the reference is
+    mounted, against the method itself on other inputs."""
+    import types
+    from tests.golden.make_golden import aug_cases, aug_inputs, synthetic_encode_decode
+    z = load("aug_test.npz")
+    for case in aug_cases():
+        name, B, C, ori, mode, crop, stride, augs, seed = case
+        imgs, metas = aug_inputs(case)
+        enc = synthetic_encode_decode(C)
+        pred, _ = om.aug_test(enc, imgs, metas, True, mode, crop, stride, C)
+        assert np.array_equal(np.stack(pred).astype(np.uint8), z[f"{name}_pred"]), name
+        if R.available():
+            imgs2 = [im * 0.5 + 0.1 for im in imgs]
+            seg = R.reference_segmentor(enc, types.SimpleNamespace(mode=mode, crop_size=crop, stride=stride), C)
+            want, _ = seg.aug_test(imgs2, metas, True)
+            got, _ = om.aug_test(enc, imgs2, metas, True, mode, crop, stride, C)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), name
