@@ -269,10 +269,18 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
  *                            (B,C,fh*up,fw*up) on the loss grid as the reference requires;
  *   PFST_LOSS_UNFOLD_GRAD    detach_unfold=False (:148-149 not taken): the logits gradient also flows through
  *                            the unfolded factor (one more launch in the backward).
+ *   PFST_LOSS_SRC_MARGIN / PFST_LOSS_SRC_MARGIN2  src_loss_type='margin' / 'margin2' (:117-133): the source
+ *                            statistics are hinge terms relu(margin[0] - S) over positive pairs and
+ *                            relu(S - margin[1]) over negative pairs (margin2: squared); margin_host = HOST
+ *                            float[2], |margin| <= 1. losses[0], losses[1] = loss_src_pos, loss_src_neg;
+ *                            losses[2], losses[3] = 0.
+ * top_k = 0 stands for the reference's top_k=None (:218-220): every tap enters both consistency terms.
  * 0 = the shipped configuration. The workspace is pfst_pfgst_loss_ws_bytes_ex(..., options) bytes.          */
 #define PFST_LOSS_SIM_GAUSSIAN 1
 #define PFST_LOSS_CROSS_PROB_EMA 2
 #define PFST_LOSS_UNFOLD_GRAD 4
+#define PFST_LOSS_SRC_MARGIN 8
+#define PFST_LOSS_SRC_MARGIN2 16
 int64_t pfst_pfgst_loss_ws_bytes_ex(int64_t B, int32_t C, int32_t fh, int32_t fw, int32_t up,
                                     int32_t options);
 int pfst_pfgst_loss_fwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
@@ -282,7 +290,8 @@ int pfst_pfgst_loss_fwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
                            int32_t gt_w, int32_t dilation, int32_t top_k,
                            const float* weights6_host, void* workspace, double* stats,
                            float* losses, float* density, uint8_t* eroded, int32_t options,
-                           float sigma, const float* logits_ema, void* stream);
+                           float sigma, const float* logits_ema, const float* margin_host,
+                           void* stream);
 int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh,
                            int32_t fw, int32_t up, const float* logits, int32_t C,
                            int32_t lh, int32_t lw, float lscale_h, float lscale_w,
@@ -291,7 +300,7 @@ int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
                            const float* weights6_host, const void* workspace,
                            const double* stats, const float* grad_losses, float* coef,
                            float* grad_logits, int32_t options, float sigma,
-                           const float* logits_ema, void* stream);
+                           const float* logits_ema, const float* margin_host, void* stream);
 
 /* ---- P1-P3: class prototypes (north_star extension; no reference code) ----------
  * Anchor: PFGST.masked_feat_dist, rsiseg/models/uda/pfgst.py:168-177. Labels are

@@ -1,8 +1,8 @@
 """PFGST auxiliary loss — restates rsiseg/models/losses/pfgst_loss.py:44-234 for
 src_loss_type='mean_std', feat_level=None, no proj_net, src_perc=None: the shipped
 configuration (sim_type='cosine', cross_prob_type='trg', detach_unfold=True) and the
-options sim_type='gaussian' (:189-191), cross_prob_type='ema' (:161-178) and
-detach_unfold=False. Test infrastructure: only tests/, smoke() and bench.py's CPU legs use it.
+options sim_type='gaussian' (:189-191), cross_prob_type='ema' (:161-178),
+detach_unfold=False, src_loss_type='margin'/'margin2' (:117-133) and top_k=None (:218-220). Test infrastructure: only tests/, smoke() and bench.py's CPU legs use it.
 
 Written as free functions over the same ATen operator sequence as the reference
 (nn.Unfold / F.interpolate / F.cosine_similarity / topk / boolean gathers) so that
@@ -19,7 +19,7 @@ import torch.nn.functional as F
 
 @dataclass
 class LossCfg:
-    top_k: int = 3
+    top_k: int | None = 3
     dilation: int = 2
     kernel_size: int = 3
     weights: dict = field(default_factory=lambda: {"src_pos": 0.1, "src_neg": 0.1, "sim_pos": 0.1,
@@ -29,6 +29,8 @@ class LossCfg:
     sim_type: str = "cosine"
     sigma: float = 30.0
     cross_prob_type: str = "trg"
+    src_loss_type: str = "mean_std"
+    margin: tuple = (0.5, 0.5)
 
 
 def _unfold(x: torch.Tensor, cfg: LossCfg) -> torch.Tensor:
@@ -78,10 +80,14 @@ def consistency_losses(sim: torch.Tensor, cross: torch.Tensor, mask: torch.Tenso
     """get_sim_losses, pfgst_loss.py:203-234 (top_k branch, ignore_mask given)."""
     cp = cross.sum(dim=1).permute(0, 3, 1, 2)
     cn = 1 - cp
-    _, imax = torch.topk(sim, cfg.top_k + 1, dim=1)
-    _, imin = torch.topk(sim, cfg.top_k, dim=1, largest=False)
-    loc_pos = torch.gather(sim, 1, imax) * (-torch.gather(cp, 1, imax))
-    loc_neg = (1 - torch.gather(sim, 1, imin)) * (-torch.gather(cn, 1, imin))
+    if cfg.top_k is not None:
+        _, imax = torch.topk(sim, cfg.top_k + 1, dim=1)
+        _, imin = torch.topk(sim, cfg.top_k, dim=1, largest=False)
+        loc_pos = torch.gather(sim, 1, imax) * (-torch.gather(cp, 1, imax))
+        loc_neg = (1 - torch.gather(sim, 1, imin)) * (-torch.gather(cn, 1, imin))
+    else:                                    # pfgst_loss.py:218-220
+        loc_pos = sim * (-cp)
+        loc_neg = (1 - sim) * (-cn)
     l_pos = torch.zeros(1, device=sim.device)
     l_neg = torch.zeros(1, device=sim.device)
     if mask.sum() > 1:
@@ -125,6 +131,18 @@ def pfgst_loss(tensors: dict, cfg: LossCfg) -> dict:
 
     l_pos, l_neg = consistency_losses(sim_ema, cross, valid_src & trg_eroded, cfg)
     w = cfg.weights
+    if cfg.src_loss_type in ("margin", "margin2"):           # pfgst_loss.py:117-133
+        hp, hn = F.relu(cfg.margin[0] - pos), F.relu(neg - cfg.margin[1])
+        if cfg.src_loss_type == "margin2":
+            hp, hn = hp ** 2, hn ** 2
+        return {
+            "loss_src_pos": hp.mean() * w["src_pos"],
+            "loss_src_neg": hn.mean() * w["src_neg"],
+            "loss_sim_pos": l_pos * w["sim_pos"],
+            "loss_sim_neg": l_neg * w["sim_neg"],
+            "vis|density_sim_feat": (tensors.get("img_trg"), 1 - sim_ema.mean(dim=1).detach().unsqueeze(1),
+                                     trg_eroded),
+        }
     return {
         "loss_src_pos_mean": -pos.mean() * w["src_pos"],
         "loss_src_neg_mean": neg.mean() * w["src_neg"],

@@ -58,10 +58,10 @@ SIGNATURES: dict[str, tuple] = {
     "pfst_pfgst_loss_ws_bytes_ex": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "pfst_pfgst_loss_fwd_ex": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
                                          _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp,
-                                         _i32, _f32, _vp, _vp]),
+                                         _i32, _f32, _vp, C.POINTER(_f32), _vp]),
     "pfst_pfgst_loss_bwd_ex": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _f32, _f32,
                                          _vp, _vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), _vp, _vp, _vp, _vp, _vp,
-                                         _i32, _f32, _vp, _vp]),
+                                         _i32, _f32, _vp, C.POINTER(_f32), _vp]),
     "pfst_slide_add": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "pfst_slide_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "pfst_softmax_accum": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp]),

@@ -51,6 +51,9 @@ struct LossParams {
   const float* logits_q;      // cross_prob_type='ema' (:161-178): teacher logits (B,C,gh,gw) or null
   float* prob_q;              // (B,C,gh,gw) softmax of logits_q (workspace) or null: q = unfold(prob_q)
   float* dcp;                 // detach_unfold=False (:148-149): (B,9,gh,gw) d loss / d cross-prob (workspace) or null
+  int n_top, n_bot;           // taps kept by the two top-k selections: top_k + 1 / top_k, or 9 / 9 for top_k=None (:215-217)
+  int src_mode;               // src_loss_type (:110-135): 0 'mean_std', 1 'margin', 2 'margin2'
+  float margin_pos, margin_neg;
   int zfill;                  // backward: L > 0 = the logits are exactly L x the loss grid; every loss pixel then writes
                               // its whole L x L cell of grad_logits (value at the sampled logit, zeros elsewhere): no memset
 };
@@ -248,13 +251,20 @@ __device__ __forceinline__ void finalize_losses(const LossParams& P, const doubl
   const double mean_pos = st[1] / n_pos, mean_neg = st[4] / n_neg;
   const double var_pos = (st[2] - n_pos * mean_pos * mean_pos) / (n_pos - 1.0);
   const double var_neg = (st[5] - n_neg * mean_neg * mean_neg) / (n_neg - 1.0);
-  losses[0] = (float)(-mean_pos) * P.w_src_pos;
-  losses[1] = (float)(mean_neg) * P.w_src_neg;
-  losses[2] = (float)sqrt(var_pos > 0.0 || var_pos != var_pos ? var_pos : 0.0) * P.w_src_pos_std;
-  losses[3] = (float)sqrt(var_neg > 0.0 || var_neg != var_neg ? var_neg : 0.0) * P.w_src_neg_std;
+  if (P.src_mode == 0) {
+    losses[0] = (float)(-mean_pos) * P.w_src_pos;
+    losses[1] = (float)(mean_neg) * P.w_src_neg;
+    losses[2] = (float)sqrt(var_pos > 0.0 || var_pos != var_pos ? var_pos : 0.0) * P.w_src_pos_std;
+    losses[3] = (float)sqrt(var_neg > 0.0 || var_neg != var_neg ? var_neg : 0.0) * P.w_src_neg_std;
+  } else {      // margin / margin2 (:117-133): st[1], st[4] hold the sums of the hinge terms; two losses only
+    losses[0] = (float)mean_pos * P.w_src_pos;
+    losses[1] = (float)mean_neg * P.w_src_neg;
+    losses[2] = 0.f;
+    losses[3] = 0.f;
+  }
   const bool any = mk > 1.0;   // pfgst_loss.py:227  `if ignore_mask.sum() > 1`
-  losses[4] = any ? (float)(st[7] / (mk * (double)(P.top_k + 1))) * P.w_sim_pos : 0.f;
-  losses[5] = any ? (float)(st[8] / (mk * (double)P.top_k)) * P.w_sim_neg : 0.f;
+  losses[4] = any ? (float)(st[7] / (mk * (double)P.n_top)) * P.w_sim_pos : 0.f;
+  losses[5] = any ? (float)(st[8] / (mk * (double)P.n_bot)) * P.w_sim_neg : 0.f;
 }
 
 // The nine statistics are accumulated as INTEGERS: counts exactly, sums in fixed point with
@@ -318,7 +328,7 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
     if (er && c.valid_src) {
       int rd, ra;
       tap_rank(s_se, p, k, rd, ra);
-      const bool top = rd < P.top_k + 1, bot = ra < P.top_k;
+      const bool top = rd < P.n_top, bot = ra < P.n_bot;
       if (top || bot) {
         const float* pn = P.prob + (int64_t)c.b * P.C * plane + (int64_t)c.y * P.gw + c.x;
         const float* pm = (P.prob_q ? P.prob_q : P.prob) + (int64_t)c.b * P.C * plane + t.gm;
@@ -358,7 +368,13 @@ pfgst_loss_fwd_kernel(const LossParams P, double* __restrict__ stats, float* __r
 
   // warp reductions: three ballots and six integer REDUX
   const unsigned full = 0xffffffffu;
-  const int f_s = to_fix(s_val, bad), f_s2 = to_fix(s_val * s_val, bad);
+  float v1 = s_val, v2 = s_val * s_val;
+  if (P.src_mode) {        // hinge terms instead of the similarity itself (margin: linear, margin2: squared)
+    const float h = is_pos ? fmaxf(P.margin_pos - s_val, 0.f) : (is_neg ? fmaxf(s_val - P.margin_neg, 0.f) : 0.f);
+    v1 = P.src_mode == 2 ? h * h : h;
+    v2 = 0.f;
+  }
+  const int f_s = to_fix(v1, bad), f_s2 = to_fix(v2, bad);
   long long w[kNumStats + 1];
   w[0] = __popc(__ballot_sync(full, is_pos));
   w[1] = __reduce_add_sync(full, is_pos ? f_s : 0);
@@ -454,8 +470,13 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
     s_k[3] = (float)((double)gout[3] * P.w_src_neg_std / ((n_neg - 1.0) * std_neg));
     s_k[4] = (float)mean_pos;
     s_k[5] = (float)mean_neg;
-    s_k[6] = any_ ? (float)((double)gout[4] * P.w_sim_pos / (mk * (double)(P.top_k + 1))) : 0.f;
-    s_k[7] = any_ ? (float)((double)gout[5] * P.w_sim_neg / (mk * (double)P.top_k)) : 0.f;
+    if (P.src_mode) {       // hinge losses: d loss / d S = -/+ a [* 2 relu] (applied per pair below)
+      s_k[0] = (float)((double)gout[0] * P.w_src_pos / n_pos);
+      s_k[2] = (float)((double)gout[1] * P.w_src_neg / n_neg);
+      s_k[1] = s_k[3] = 0.f;
+    }
+    s_k[6] = any_ ? (float)((double)gout[4] * P.w_sim_pos / (mk * (double)P.n_top)) : 0.f;
+    s_k[7] = any_ ? (float)((double)gout[5] * P.w_sim_neg / (mk * (double)P.n_bot)) : 0.f;
     s_any = any_ ? 1 : 0;
   }
   // (no barrier yet: the first pixel's map loads are issued while thread 0 does the fp64 arithmetic)
@@ -484,7 +505,14 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         // --- x_src: gather-form coefficients ---
         if (k != 4 && (t.in || P.gauss)) {
           const float S = t.s_src;
-          const float g = t.pos_pair ? a_pos + c_pos * (S - fmean_pos) : a_neg + c_neg * (S - fmean_neg);
+          float g;
+          if (P.src_mode == 0) {
+            g = t.pos_pair ? a_pos + c_pos * (S - fmean_pos) : a_neg + c_neg * (S - fmean_neg);
+          } else {          // relu'(0) = 0 as torch
+            const float h = t.pos_pair ? P.margin_pos - S : S - P.margin_neg;
+            const float d = h > 0.f ? (P.src_mode == 2 ? 2.f * h : 1.f) : 0.f;
+            g = t.pos_pair ? -a_pos * d : a_neg * d;
+          }
           // the pair (n, m) is counted once from n (if n is valid) and once from m (if m is valid);
           // a padded (zero-vector) neighbour only from n, and only the Gaussian similarity depends on x_n then
           const float W = g * ((c.valid_src ? 1.f : 0.f) + ((t.in && t.nb_valid) ? 1.f : 0.f));
@@ -514,7 +542,7 @@ pfgst_loss_bwd_kernel(const LossParams P, const double* __restrict__ stats, cons
         if (in_mk) {
           int rd, ra;
           tap_rank(s_se, p, k, rd, ra);
-          const bool top = rd < P.top_k + 1, bot = ra < P.top_k;
+          const bool top = rd < P.n_top, bot = ra < P.n_bot;
           // d/dcp of  -S*cp  and of  -(1-S)*(1-cp)
           dcp = (top ? -t.s_ema * g_pos : 0.f) + (bot ? (1.f - t.s_ema) * g_neg : 0.f);
         }
@@ -660,7 +688,7 @@ pfgst_loss_unfold_grad_kernel(const LossParams P, float* __restrict__ grad_logit
 }
 
 // bits of the `options` argument of the *_ex entry points
-constexpr int kOptGauss = 1, kOptProbEma = 2, kOptUnfoldGrad = 4;
+constexpr int kOptGauss = 1, kOptProbEma = 2, kOptUnfoldGrad = 4, kOptMargin = 8, kOptMargin2 = 16;
 
 static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, int fh, int fw, int up,
                        const float* logits, int C, int lh, int lw, float lsh, float lsw, const int64_t* gt,
@@ -669,7 +697,7 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
   if (B < 0 || B > 0x7fffffff || fh < 1 || fw < 1 || up < 1 || C < 1 || lh < 1 || lw < 1 || gt_h < 1 || gt_w < 1)
     return PFST_ERR_INVALID_ARG;
   if (C > kMaxC) return PFST_ERR_UNSUPPORTED;
-  if (dil < 1 || dil % up != 0 || top_k < 1 || top_k > 4 || ksplit < 1) return PFST_ERR_INVALID_ARG;
+  if (dil < 1 || dil % up != 0 || top_k < 0 || top_k > 4 || ksplit < 1) return PFST_ERR_INVALID_ARG;   // top_k 0 = None
   P.dots = dots; P.ksplit = ksplit; P.B = (int)B; P.fh = fh; P.fw = fw; P.up = up;
   P.logits = logits; P.C = C; P.lh = lh; P.lw = lw; P.lscale_h = lsh; P.lscale_w = lsw;
   P.gt = gt; P.mix = mix; P.gt_h = gt_h; P.gt_w = gt_w;
@@ -687,12 +715,22 @@ static int fill_params(LossParams& P, const float* dots, int ksplit, int64_t B, 
   P.flags = P.lab + (size_t)B * gplane;
   P.raw = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(P.flags + (size_t)B * gplane) + 15) & ~(uintptr_t)15);
   P.gauss = 0; P.inv_sigma2 = 0.f; P.logits_q = nullptr; P.prob_q = nullptr; P.dcp = nullptr; P.zfill = 0;
+  P.n_top = top_k ? top_k + 1 : 9; P.n_bot = top_k ? top_k : 9;
+  P.src_mode = 0; P.margin_pos = 0.f; P.margin_neg = 0.f;
   return PFST_OK;
 }
 
 // the optional regions follow the 16 accumulators: prob_q (B,C,gh,gw), then dcp (B,9,gh,gw)
-static int apply_options(LossParams& P, int options, float sigma, const float* logits_ema) {
-  if (options & ~(kOptGauss | kOptProbEma | kOptUnfoldGrad)) return PFST_ERR_INVALID_ARG;
+static int apply_options(LossParams& P, int options, float sigma, const float* logits_ema, const float* margin) {
+  if (options & ~(kOptGauss | kOptProbEma | kOptUnfoldGrad | kOptMargin | kOptMargin2)) return PFST_ERR_INVALID_ARG;
+  if (options & (kOptMargin | kOptMargin2)) {
+    if (!margin || ((options & kOptMargin) && (options & kOptMargin2))) return PFST_ERR_INVALID_ARG;
+    // the hinge terms are summed in 2^-24 fixed point with |value| <= 4: similarities lie in [-1, 1]
+    if (!(fabsf(margin[0]) <= 1.f) || !(fabsf(margin[1]) <= 1.f)) return PFST_ERR_UNSUPPORTED;
+    P.src_mode = (options & kOptMargin2) ? 2 : 1;
+    P.margin_pos = margin[0];
+    P.margin_neg = margin[1];
+  }
   float* extra = reinterpret_cast<float*>(P.raw + 16);
   const size_t gplane = (size_t)P.gh * P.gw;
   if (options & kOptGauss) {
@@ -734,12 +772,12 @@ int pfst_pfgst_loss_fwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
                            float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
                            int32_t dilation, int32_t top_k, const float* weights6_host, void* workspace,
                            double* stats, float* losses, float* density, uint8_t* eroded, int32_t options,
-                           float sigma, const float* logits_ema, void* stream) {
+                           float sigma, const float* logits_ema, const float* margin_host, void* stream) {
   pfst::LossParams P;
   int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
                              mix, gt_h, gt_w, dilation, top_k, weights6_host, workspace);
   if (rc != PFST_OK) return rc;
-  rc = pfst::apply_options(P, options, sigma, logits_ema);
+  rc = pfst::apply_options(P, options, sigma, logits_ema, margin_host);
   if (rc != PFST_OK) return rc;
   if (!stats || !losses) return PFST_ERR_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -771,7 +809,7 @@ int pfst_pfgst_loss_fwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         double* stats, float* losses, float* density, uint8_t* eroded, void* stream) {
   return pfst_pfgst_loss_fwd_ex(dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt, mix, gt_h,
                                 gt_w, dilation, top_k, weights6_host, workspace, stats, losses, density, eroded, 0,
-                                0.f, nullptr, stream);
+                                0.f, nullptr, nullptr, stream);
 }
 
 int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t fh, int32_t fw, int32_t up,
@@ -779,12 +817,13 @@ int pfst_pfgst_loss_bwd_ex(const float* dots, int32_t ksplit, int64_t B, int32_t
                            float lscale_w, const int64_t* gt, const int64_t* mix, int32_t gt_h, int32_t gt_w,
                            int32_t dilation, int32_t top_k, const float* weights6_host, const void* workspace,
                            const double* stats, const float* grad_losses, float* coef, float* grad_logits,
-                           int32_t options, float sigma, const float* logits_ema, void* stream) {
+                           int32_t options, float sigma, const float* logits_ema, const float* margin_host,
+                           void* stream) {
   pfst::LossParams P;
   int rc = pfst::fill_params(P, dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt,
                              mix, gt_h, gt_w, dilation, top_k, weights6_host, const_cast<void*>(workspace));
   if (rc != PFST_OK) return rc;
-  rc = pfst::apply_options(P, options, sigma, logits_ema);
+  rc = pfst::apply_options(P, options, sigma, logits_ema, margin_host);
   if (rc != PFST_OK) return rc;
   if (!grad_logits) P.dcp = nullptr;        // nothing consumes the d loss / d cross-prob maps then
   {
@@ -830,7 +869,7 @@ int pfst_pfgst_loss_bwd(const float* dots, int32_t ksplit, int64_t B, int32_t fh
                         void* stream) {
   return pfst_pfgst_loss_bwd_ex(dots, ksplit, B, fh, fw, up, logits, C, lh, lw, lscale_h, lscale_w, gt, mix, gt_h,
                                 gt_w, dilation, top_k, weights6_host, workspace, stats, grad_losses, coef,
-                                grad_logits, 0, 0.f, nullptr, stream);
+                                grad_logits, 0, 0.f, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -6,9 +6,9 @@ computed by four sm_100a kernels (csrc/neigh.cu, csrc/pfgst_loss.cu) instead of
 ~60 ATen kernels, two 604 MB im2col buffers and 3+ host syncs. Besides the branch the
 shipped configs use (configs/pfst/*.py:34-47: cosine, cross_prob_type='trg',
 detach_unfold=True) the kernels cover sim_type='gaussian' (:189-191),
-cross_prob_type='ema' (:161-178) and detach_unfold=False (:148-149); the remaining
-options (src_perc, proj_net_cfg, the margin losses, kernel_size != 3, top_k=None) raise
-instead of silently computing something else.
+cross_prob_type='ema' (:161-178), detach_unfold=False (:148-149), src_loss_type='margin' /
+'margin2' (:117-133) and top_k=None (:218-220); the remaining options (src_perc, proj_net_cfg,
+kernel_size != 3) raise instead of silently computing something else.
 """
 from __future__ import annotations
 
@@ -43,7 +43,7 @@ class _PFGSTLossFn(torch.autograd.Function):
             logits_ema = logits_ema.detach().contiguous()
         losses, stats, density, eroded = ops.pfgst_loss_fwd(dots, ks, geo, logits_trg, gt_src, mix_masks,
                                                             cfg["top_k"], cfg["w6"], options=opts, sigma=sigma,
-                                                            logits_ema=logits_ema)
+                                                            logits_ema=logits_ema, margin=cfg.get("margin"))
         ctx.logits_ema = logits_ema
         ctx.save_for_backward(logits_trg, x_src, gt_src, mix_masks, dots, stats[0], stats[1])
         ctx.geo, ctx.ks, ctx.cfg = geo, ks, cfg
@@ -59,7 +59,7 @@ class _PFGSTLossFn(torch.autograd.Function):
         coef, glog = ops.pfgst_loss_bwd(dots, ctx.ks, geo, logits_trg, gt_src, mix_masks, cfg["top_k"], cfg["w6"],
                                         stats, grad_losses.contiguous().float(), want_logits_grad=need_logits,
                                         options=cfg.get("options", 0), sigma=cfg.get("sigma", 30.0),
-                                        logits_ema=ctx.logits_ema)
+                                        logits_ema=ctx.logits_ema, margin=cfg.get("margin"))
         gx = ops.neigh_grad(x_src, coef, geo.dilation // geo.up) if need_x else None
         return glog, gx, None, None, None, None, None
 
@@ -79,21 +79,24 @@ class PFGSTLoss(nn.Module):
             unsupported.append(f"sigma={sigma} (must be positive)")
         if kernel_size != 3:
             unsupported.append(f"kernel_size={kernel_size} (only 3)")
-        if top_k is None or not (1 <= int(top_k) <= 4):
-            unsupported.append(f"top_k={top_k} (1..4)")
+        if top_k is not None and not (1 <= int(top_k) <= 4):
+            unsupported.append(f"top_k={top_k} (1..4 or None)")
         if src_perc is not None:
             unsupported.append("src_perc")
         if proj_net_cfg is not None:
             unsupported.append("proj_net_cfg")
-        if src_loss_type != 'mean_std':
-            unsupported.append(f"src_loss_type={src_loss_type!r} (only 'mean_std')")
+        if src_loss_type not in ('mean_std', 'margin', 'margin2'):
+            unsupported.append(f"src_loss_type={src_loss_type!r} ('mean_std', 'margin', 'margin2')")
+        elif src_loss_type != 'mean_std' and not all(abs(float(m)) <= 1.0 for m in margin):
+            unsupported.append(f"margin={margin} (|margin| <= 1: similarities lie in [-1, 1])")
         if cross_prob_type not in ('trg', 'ema'):
             unsupported.append(f"cross_prob_type={cross_prob_type!r} ('trg' or 'ema')")
         if unsupported:
             raise PfstError("PFGSTLoss (B200 path) does not implement: " + "; ".join(unsupported))
         if not isinstance(weights, dict):
             raise PfstError("PFGSTLoss: `weights` must be the dict form used by configs/pfst/*.py")
-        self.top_k = int(top_k)
+        self.top_k = None if top_k is None else int(top_k)
+        self.margin = margin
         self.dilation = int(dilation)
         self.kernel_size = kernel_size
         self.weights = weights
@@ -106,16 +109,19 @@ class PFGSTLoss(nn.Module):
         self.src_loss_type = src_loss_type
         options = ((ops.LOSS_SIM_GAUSSIAN if sim_type == 'gaussian' else 0) |
                    (ops.LOSS_CROSS_PROB_EMA if cross_prob_type == 'ema' else 0) |
-                   (0 if detach_unfold else ops.LOSS_UNFOLD_GRAD))
-        self._cfg = dict(top_k=self.top_k, dilation=self.dilation, downscale=downscale,
-                         w6=(weights['src_pos'], weights['src_neg'], weights['src_pos_std'],
-                             weights['src_neg_std'], weights['sim_pos'], weights['sim_neg']),
-                         options=options, sigma=float(sigma))
+                   (0 if detach_unfold else ops.LOSS_UNFOLD_GRAD) |
+                   {'mean_std': 0, 'margin': ops.LOSS_SRC_MARGIN, 'margin2': ops.LOSS_SRC_MARGIN2}[src_loss_type])
+        # top_k=None (pfgst_loss.py:218-220) travels as 0; the margin losses read no *_std weights (:117-133)
+        self._cfg = dict(top_k=self.top_k or 0, dilation=self.dilation, downscale=downscale,
+                         w6=(weights['src_pos'], weights['src_neg'], weights.get('src_pos_std', 0.0),
+                             weights.get('src_neg_std', 0.0), weights['sim_pos'], weights['sim_neg']),
+                         options=options, sigma=float(sigma),
+                         margin=None if src_loss_type == 'mean_std' else (float(margin[0]), float(margin[1])))
 
     @property
     def shipped_branch(self) -> bool:
         """True for the configuration the fused launch groups of PluginEngine / SelfTrainingStep are built for."""
-        return self._cfg["options"] == 0
+        return self._cfg["options"] == 0 and self.top_k is not None
 
     def forward(self, tensors):
         logits_trg = tensors['logits_trg']
@@ -125,6 +131,10 @@ class PFGSTLoss(nn.Module):
         logits_ema = tensors['logits_ema'] if self.cross_prob_type == 'ema' else None
         losses, density, eroded = _PFGSTLossFn.apply(logits_trg, x_src, x_ema.detach(), gt_src,
                                                      tensors['mix_masks'], self._cfg, logits_ema)
-        out = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+        if self.src_loss_type == 'mean_std':
+            out = {k: losses[i] for i, k in enumerate(LOSS_KEYS)}
+        else:                                   # pfgst_loss.py:117-133: two source losses, no std terms
+            out = {'loss_src_pos': losses[0], 'loss_src_neg': losses[1], 'loss_sim_pos': losses[4],
+                   'loss_sim_neg': losses[5]}
         out['vis|density_sim_feat'] = (tensors.get('img_trg'), density, eroded.bool())
         return out

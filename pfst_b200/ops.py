@@ -485,7 +485,7 @@ def _w6(weights6):
     return arr
 
 
-LOSS_SIM_GAUSSIAN, LOSS_CROSS_PROB_EMA, LOSS_UNFOLD_GRAD = 1, 2, 4     # include/pfst_sm100.h PFST_LOSS_*
+LOSS_SIM_GAUSSIAN, LOSS_CROSS_PROB_EMA, LOSS_UNFOLD_GRAD, LOSS_SRC_MARGIN, LOSS_SRC_MARGIN2 = 1, 2, 4, 8, 16   # PFST_LOSS_*
 
 
 def _loss_options(options: int, logits_ema, geo: LossGeometry):
@@ -502,8 +502,12 @@ def _loss_options(options: int, logits_ema, geo: LossGeometry):
     return None
 
 
+def _margin(margin):
+    return None if margin is None else (C.c_float * 2)(float(margin[0]), float(margin[1]))
+
+
 def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, want_vis=True,
-                   options: int = 0, sigma: float = 30.0, logits_ema=None):
+                   options: int = 0, sigma: float = 30.0, logits_ema=None, margin=None):
     """-> (losses float32[6], (stats float64[16], workspace), density|None, eroded|None)."""
     dev = logits.device
     _dev(dots, "dots", torch.float32)
@@ -521,12 +525,12 @@ def pfgst_loss_fwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
               geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), losses.data_ptr(),
               None if density is None else density.data_ptr(), None if eroded is None else eroded.data_ptr(),
-              int(options), float(sigma), q_ptr, _stream())
+              int(options), float(sigma), q_ptr, _margin(margin), _stream())
     return losses, (stats, ws), density, eroded
 
 
 def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6, stats, grad_losses,
-                   want_logits_grad=True, options: int = 0, sigma: float = 30.0, logits_ema=None):
+                   want_logits_grad=True, options: int = 0, sigma: float = 30.0, logits_ema=None, margin=None):
     """-> (coef (B,9,fh,fw), grad_logits|None)."""
     dev = logits.device
     _dev(grad_losses, "grad_losses", torch.float32)
@@ -538,5 +542,5 @@ def pfgst_loss_bwd(dots, ks, geo: LossGeometry, logits, gt, mix, top_k, weights6
               geo.C, geo.lh, geo.lw, geo.lscale, geo.lscale, gt.data_ptr(), mix.data_ptr(), geo.gt_h, geo.gt_w,
               geo.dilation, int(top_k), _w6(weights6), ws.data_ptr(), stats.data_ptr(), grad_losses.data_ptr(),
               coef.data_ptr(), None if glog is None else glog.data_ptr(), int(options), float(sigma), q_ptr,
-              _stream())
+              _margin(margin), _stream())
     return coef, glog

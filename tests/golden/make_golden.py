@@ -176,7 +176,20 @@ LOSS_OPTION_CASES = {
     "unfold": (dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=14), dict(sim_type='cosine', detach_unfold=False)),
     "unfold33": (dict(B=2, C=33, H=48, D=16, dil=2, down=None, seed=15), dict(sim_type='gaussian', sigma=2.5,
                                                                              detach_unfold=False)),
+    "margin": (dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=16), dict(sim_type='cosine', detach_unfold=True,
+                                                                          src_loss_type='margin', margin=[0.6, 0.2])),
+    "margin2": (dict(B=2, C=33, H=48, D=16, dil=2, down=None, seed=17), dict(sim_type='cosine', detach_unfold=True,
+                                                                            src_loss_type='margin2',
+                                                                            margin=[0.8, 0.1])),
+    "topk_none": (dict(B=2, C=6, H=128, D=32, dil=2, down=0.5, seed=18), dict(sim_type='cosine', detach_unfold=True,
+                                                                             top_k=None)),
 }
+
+
+def loss_option_keys(opts):
+    if opts.get("src_loss_type", "mean_std") != "mean_std":
+        return ("loss_src_pos", "loss_src_neg", "loss_sim_pos", "loss_sim_neg")
+    return LOSS_KEYS
 
 
 def loss_option_inputs(c):
@@ -201,16 +214,19 @@ def gen_pfgst_loss_options():
         gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
         np.random.seed(3)
         mix = torch.cat(D.get_class_masks(gt), 0)
-        mod = L.PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None,
-                          downscale=c["down"], **opts)
+        kw = dict(top_k=3)
+        kw.update(opts)
+        mod = L.PFGSTLoss(dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None,
+                          downscale=c["down"], **kw)
         lt = logits.clone().requires_grad_(True)
         xs = x_src.clone().requires_grad_(True)
         with R.cpu_cuda_identity():
             res = mod(dict(logits_trg=lt, logits_ema=logits_ema, gt_src=gt, x_ema=x_ema, x_src=xs, img_trg=None,
                            mix_masks=mix))
-        sum(res[k] for k in LOSS_KEYS).backward()
+        keys = loss_option_keys(opts)
+        sum(res[k] for k in keys).backward()
         out.update({f"{name}_mix": mix.numpy().astype(np.uint8),
-                    f"{name}_losses": np.array([float(res[k]) for k in LOSS_KEYS], dtype=np.float32),
+                    f"{name}_losses": np.array([float(res[k]) for k in keys], dtype=np.float32),
                     f"{name}_grad_x_src": xs.grad.numpy(), f"{name}_grad_logits": lt.grad.numpy(),
                     f"{name}_density": res['vis|density_sim_feat'][1].numpy(),
                     f"{name}_eroded": res['vis|density_sim_feat'][2].numpy()})

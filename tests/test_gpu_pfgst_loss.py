@@ -149,7 +149,8 @@ def test_pfgst_loss_empty_target_region(cuda):
 
 
 def test_unsupported_options_raise():
-    for kw in (dict(src_loss_type='margin'), dict(kernel_size=5), dict(src_perc=0.5), dict(top_k=None),
+    for kw in (dict(src_loss_type='hinge'), dict(kernel_size=5), dict(src_perc=0.5), dict(top_k=7),
+               dict(src_loss_type='margin', margin=[1.5, 0.5]),
                dict(proj_net_cfg=dict(in_channels=4, out_channels=4)), dict(cross_prob_type='src')):
         args = dict(top_k=3, dilation=2, kernel_size=3, weights=W6, sim_type='cosine', feat_level=None,
                     detach_unfold=True, downscale=0.5)
@@ -158,33 +159,38 @@ def test_unsupported_options_raise():
             PFGSTLoss(**args)
 
 
-@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33"])
+@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33", "margin", "margin2", "topk_none"])
 def test_pfgst_loss_options_match_reference_golden_and_oracle(cuda, name):
     """The PFGSTLoss options outside the shipped configuration (pfgst_loss.py:16-18): sim_type='gaussian',
     cross_prob_type='ema', detach_unfold=False — CUDA path vs the fixture the reference module wrote
     (tests/golden/pfgst_loss_options.npz) and vs the oracle, 1e-5 of the gradient scale."""
     from pathlib import Path
-    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs, loss_option_keys
     z = np.load(Path(__file__).resolve().parent / "golden" / "pfgst_loss_options.npz")
     c, opts = LOSS_OPTION_CASES[name]
+    KEYS = loss_option_keys(opts)
     gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
     mix = torch.from_numpy(z[f"{name}_mix"]).long()
-    mod = PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"],
-                    **opts)
+    kw = dict(top_k=3)
+    kw.update(opts)
+    mod = PFGSTLoss(dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"], **kw)
     assert not mod.shipped_branch
     t = dict(logits_trg=logits.clone().to(cuda).requires_grad_(True), logits_ema=logits_ema.to(cuda),
              gt_src=gt.to(cuda), x_ema=x_ema.to(cuda), x_src=x_src.clone().to(cuda).requires_grad_(True),
              img_trg=None, mix_masks=mix.to(cuda))
     out = mod(t)
-    sum(out[k] for k in LOSS_KEYS).backward()
+    assert set(k for k in out if k.startswith("loss_")) == set(KEYS)
+    sum(out[k] for k in KEYS).backward()
     cfg = OL.LossCfg(dilation=c["dil"], downscale=c["down"], sim_type=opts.get("sim_type", "cosine"),
                      sigma=opts.get("sigma", 30.0), cross_prob_type=opts.get("cross_prob_type", "trg"),
-                     detach_unfold=opts.get("detach_unfold", True))
+                     detach_unfold=opts.get("detach_unfold", True), top_k=opts.get("top_k", 3),
+                     src_loss_type=opts.get("src_loss_type", "mean_std"),
+                     margin=tuple(opts.get("margin", (0.5, 0.5))))
     to = dict(logits_trg=logits.clone().requires_grad_(True), logits_ema=logits_ema, gt_src=gt, x_ema=x_ema,
               x_src=x_src.clone().requires_grad_(True), img_trg=None, mix_masks=mix)
     oo = OL.pfgst_loss(to, cfg)
-    sum(oo[k] for k in LOSS_KEYS).backward()
-    for i, k in enumerate(LOSS_KEYS):
+    sum(oo[k] for k in KEYS).backward()
+    for i, k in enumerate(KEYS):
         a = float(out[k])
         for b in (float(z[f"{name}_losses"][i]), float(oo[k])):
             assert abs(a - b) <= 1e-5 * abs(b) + 1e-9, (k, a, b)

@@ -95,22 +95,24 @@ def test_pfgst_loss_oracle_vs_golden(name):
 def _option_cfg(c, opts):
     return OL.LossCfg(dilation=c["dil"], downscale=c["down"], sim_type=opts.get("sim_type", "cosine"),
                       sigma=opts.get("sigma", 30.0), cross_prob_type=opts.get("cross_prob_type", "trg"),
-                      detach_unfold=opts.get("detach_unfold", True))
+                      detach_unfold=opts.get("detach_unfold", True), top_k=opts.get("top_k", 3),
+                      src_loss_type=opts.get("src_loss_type", "mean_std"), margin=tuple(opts.get("margin", (0.5, 0.5))))
 
 
-@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33"])
+@pytest.mark.parametrize("name", ["gauss", "gauss33", "ema", "unfold", "unfold33", "margin", "margin2", "topk_none"])
 def test_pfgst_loss_option_oracle_vs_golden(name):
     """sim_type='gaussian', cross_prob_type='ema', detach_unfold=False: the oracle against what the
     reference module wrote (tests/golden/make_golden.py::gen_pfgst_loss_options)."""
-    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs, loss_option_keys
     z = load("pfgst_loss_options.npz")
     c, opts = LOSS_OPTION_CASES[name]
+    keys = loss_option_keys(opts)
     gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
     lt, xs = logits.clone().requires_grad_(True), x_src.clone().requires_grad_(True)
     res = OL.pfgst_loss(dict(logits_trg=lt, logits_ema=logits_ema, gt_src=gt, x_ema=x_ema, x_src=xs, img_trg=None,
                              mix_masks=torch.from_numpy(z[f"{name}_mix"]).long()), _option_cfg(c, opts))
-    sum(res[k] for k in OL.LOSS_KEYS).backward()
-    got = np.array([float(res[k].detach()) for k in OL.LOSS_KEYS], dtype=np.float32)
+    sum(res[k] for k in keys).backward()
+    got = np.array([float(res[k].detach()) for k in keys], dtype=np.float32)
     assert np.allclose(got, z[f"{name}_losses"], rtol=2e-6, atol=1e-8)
     assert np.allclose(xs.grad.numpy(), z[f"{name}_grad_x_src"], rtol=1e-5, atol=1e-9)
     assert np.allclose(lt.grad.numpy(), z[f"{name}_grad_logits"], rtol=1e-5, atol=1e-9)
@@ -120,17 +122,19 @@ def test_pfgst_loss_option_oracle_vs_golden(name):
 
 # ------------------------------------------------------------------ live reference
 @needs_ref
-@pytest.mark.parametrize("name", ["gauss", "ema", "unfold33"])
+@pytest.mark.parametrize("name", ["gauss", "ema", "unfold33", "margin2", "topk_none"])
 def test_pfgst_loss_option_oracle_equals_reference_live(name):
-    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs, W6
+    from tests.golden.make_golden import LOSS_OPTION_CASES, loss_option_inputs, loss_option_keys, W6
     warnings.filterwarnings("ignore")
     D, L = R.dacs_transforms(), R.pfgst_loss()
     c, opts = LOSS_OPTION_CASES[name]
     gt, logits, x_src, x_ema, logits_ema = loss_option_inputs(c)
     np.random.seed(3)
     mix = torch.cat(D.get_class_masks(gt), 0)
-    mod = L.PFGSTLoss(top_k=3, dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"],
-                      **opts)
+    kw = dict(top_k=3)
+    kw.update(opts)
+    mod = L.PFGSTLoss(dilation=c["dil"], kernel_size=3, weights=W6, feat_level=None, downscale=c["down"], **kw)
+    keys = loss_option_keys(opts)
 
     def t():
         return dict(logits_trg=logits.clone().requires_grad_(True), logits_ema=logits_ema, gt_src=gt, x_ema=x_ema,
@@ -140,9 +144,9 @@ def test_pfgst_loss_option_oracle_equals_reference_live(name):
     with R.cpu_cuda_identity():
         a = mod(t1)
     b = OL.pfgst_loss(t2, _option_cfg(c, opts))
-    sum(a[k] for k in OL.LOSS_KEYS).backward()
-    sum(b[k] for k in OL.LOSS_KEYS).backward()
-    for k in OL.LOSS_KEYS:
+    sum(a[k] for k in keys).backward()
+    sum(b[k] for k in keys).backward()
+    for k in keys:
         assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
     assert torch.equal(t1['x_src'].grad, t2['x_src'].grad)
     assert torch.equal(t1['logits_trg'].grad, t2['logits_trg'].grad)
