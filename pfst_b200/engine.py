@@ -171,7 +171,7 @@ class PluginEngine:
                       None if thr_vec is None else thr_vec.data_ptr(), 0, -1, b["label"].data_ptr(),
                       b["conf"].data_ptr(), None if b["wpart"] is None else b["wpart"].data_ptr(),
                       b["count"].data_ptr(), main.cuda_stream)
-            masked = bank is not None and bank.masked(x_ema.shape[2], x_ema.shape[3])
+            masked = bank is not None and bank.masked(x_ema.shape[2], x_ema.shape[3], x_ema)
             if dots_here and not masked:
                 main.wait_event(self._ev[3])             # the label sort never runs next to a TMA dots kernel (step.py)
             if bank is not None:

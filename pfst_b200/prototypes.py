@@ -105,16 +105,18 @@ class PrototypeBank:
         launch. Otherwise two: the label sort (once per image tile) and the streaming segment-reduce
         (`order` / `accumulate_ordered` can also be issued separately)."""
         B, D, h, w = feats.shape
-        if self.masked(h, w):               # few classes: one masked-accumulation launch, no sort
+        if self.masked(h, w, feats):        # few classes: one masked-accumulation launch, no sort
             self.accumulate_single_launch(feats, labels, conf, conf_thr)
             return
         self.order(labels, B, h, w, conf, conf_thr)
         self.accumulate_ordered(feats)
 
-    def masked(self, h: int, w: int) -> bool:
+    def masked(self, h: int, w: int, feats: Optional[torch.Tensor] = None) -> bool:
         """True when `accumulate` for (h, w) feature maps is the single masked-accumulation launch
         (C <= 8, h*w % 4 == 0, not a small plane): no label-sort kernel exists then, so a scheduler has
         nothing to keep away from the TMA neighbourhood kernels."""
+        if feats is not None and feats.data_ptr() % 16:
+            return False          # the library then takes the self-contained sort + stream kernel
         return bool(_lib.load().pfst_proto_accum_is_masked(self.C, int(h), int(w)))
 
     def order(self, labels: torch.Tensor, B: int, h: int, w: int, conf: Optional[torch.Tensor] = None,

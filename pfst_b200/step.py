@@ -132,7 +132,7 @@ class SelfTrainingStep:
             join.record(self._side)
         _lib.call("pfst_pseudo_label", ema_logits.data_ptr(), B, C, H * W, float(self.thr), None, 0, -1,
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), ops._stream())
-        if self.bank.masked(x_ema.shape[2], x_ema.shape[3]):
+        if self.bank.masked(x_ema.shape[2], x_ema.shape[3], x_ema):
             self.bank.accumulate(x_ema, b.label)                  # one masked launch next to dots(x_ema)
             main.wait_event(join)
             return
@@ -237,7 +237,7 @@ class SelfTrainingStep:
                   b.label.data_ptr(), b.conf.data_ptr(), None, b.count.data_ptr(), s)
         pl_done.record(main)
         unsafe = os.environ.get("PFST_DAG_UNSAFE") == "1"           # reproduces DESIGN.md 3.2 (tools/dots_replay_check.py)
-        masked = bank.masked(h, w)        # few classes: no sort kernel -> nothing to keep away from the TMA kernels
+        masked = bank.masked(h, w, x_ema)      # few classes: no sort kernel -> nothing to keep away from the TMA kernels
         self._comm.wait_event(pl_done)
         if not masked:
             if not unsafe:
