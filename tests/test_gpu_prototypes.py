@@ -54,6 +54,32 @@ def test_confidence_mask_and_chained_batches(cuda):
     assert (packed[:C * D].view(C, D).double() - (s1 + s2)).abs().max() <= 1e-5 * (s1 + s2).abs().max()
 
 
+@pytest.mark.parametrize("B,D,h,w,C,H,W,use_conf", [
+    (2, 37, 36, 36, 6, 288, 288, True),      # 1296 px: one partial tile (no whole 128-float4 chunk), odd channel count
+    (1, 24, 72, 72, 3, 144, 144, False),     # 5184 px: a full 4096-px tile + a 1088-px tail, labels 2x up-sampled
+    (3, 9, 32, 32, 8, 256, 256, True),       # fewer channels than warps, the largest class count of the kernel
+    (2, 16, 40, 28, 1, 320, 224, False),     # a single class, non-square
+    (4, 130, 64, 64, 2, 512, 512, True)])
+def test_masked_accumulation_path(cuda, B, D, h, w, C, H, W, use_conf):
+    """C <= 8, h*w % 4 == 0, h*w > 576: `accumulate` is the single masked-accumulation launch
+    (proto_accum_masked_kernel). Counts exact, sums within 1e-5 of the fp64 oracle, with and without
+    the confidence mask, chained over two calls."""
+    feats, labels = _case(B, D, h, w, C, H, W, seed=21)
+    labels[:, :, : H // 5] = 255                       # an ignored band
+    bank = P.PrototypeBank(C, D, cuda)
+    assert bank.masked(h, w, feats.to(cuda))
+    conf = torch.rand((B, H, W), generator=torch.Generator().manual_seed(5)) if use_conf else None
+    s1, c1 = OP.proto_accumulate(feats, labels[:, 0], C, conf, 0.4 if use_conf else 0.0)
+    feats2, labels2 = _case(B, D, h, w, C, H, W, seed=22)
+    s2, c2 = OP.proto_accumulate(feats2, labels2[:, 0], C)
+    bank.accumulate(feats.to(cuda), labels.to(cuda), None if conf is None else conf.to(cuda), 0.4 if use_conf else 0.0)
+    bank.accumulate(feats2.to(cuda), labels2.to(cuda))
+    packed = bank.packed.cpu()
+    assert torch.equal(packed[C * D:].long(), c1 + c2)
+    want = s1 + s2
+    assert (packed[:C * D].view(C, D).double() - want).abs().max() <= 1e-5 * want.abs().max()
+
+
 def test_prototype_ema_over_iterations(cuda):
     B, D, h, w, C, H, W = 2, 16, 8, 8, 5, 64, 64
     bank = P.PrototypeBank(C, D, cuda, alpha=0.999)
