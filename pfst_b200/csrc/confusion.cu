@@ -26,6 +26,8 @@
 // Blocks own a contiguous span of the pixel stream (persistent grid, one resident
 // wave), prefetch the next tile while counting the current one, and flush their
 // histogram once per image they touch, so global atomics are O(grid * bins).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pfst {
@@ -240,9 +242,11 @@ static int launch_cf_strat(CfParams q, size_t smem, cudaStream_t s) {
   if (smem > 0) {
     PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "pfst_confusion_accum/attr");
-    PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared),
-                  "pfst_confusion_accum/carveout");
+    static const bool max_carve = getenv("PFST_CONF_MAX_CARVEOUT") != nullptr;   // A/B switch (round-1 setting)
+    if (max_carve)
+      PFST_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared),
+                    "pfst_confusion_accum/carveout");
   }
   int occ = 0;
   PFST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kCfThreads, smem),
