@@ -101,7 +101,7 @@ class SelfTrainingStep:
         self.ema_events = None    # optional (start, end) CUDA events around the EMA launch
         self.graphs = bool(graphs)
         self.split_for_allreduce = split_for_allreduce   # None: split segment B only when world_size > 1
-        self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "3"))
+        self.ema_blocks_per_sm = int(os.environ.get("PFST_EMA_BLOCKS_PER_SM", "2"))
         self.nccl_in_graph = os.environ.get("PFST_NCCL_IN_GRAPH", "1") != "0"
         # multi-rank P2: one-shot all-reduce over NVLink peer memory inside the finalise kernel
         # (csrc/peer.cu); PFST_PEER_REDUCE=0 falls back to ncclAllReduce between two kernels
