@@ -463,7 +463,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "ema_multi_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": ab["ema"], "us_per_launch": ema_ms * 1e3,
-                         "timed": "20 launches alone after the timed steps (same grid: %d blocks/SM)" % step.ema_blocks_per_sm,
+                         "timed": "20 launches alone after the timed steps (same grid as in the step: %s)" % (
+                             "%d blocks/SM" % step.ema_blocks_per_sm if step.ema_blocks_per_sm else "one block per 4096-float chunk"),
                          "us_per_launch_overlapped_in_step": None if ema_overlapped_ms is None else ema_overlapped_ms * 1e3}}
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
