@@ -9,6 +9,8 @@ kernel's atomics write straight into it — no pack/copy step).
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -111,12 +113,21 @@ class PrototypeBank:
         self.order(labels, B, h, w, conf, conf_thr)
         self.accumulate_ordered(feats)
 
+    MASKED_MAX_PIXELS = int(os.environ.get("PFST_MASKED_MAX_PIXELS", "16384"))
+
     def masked(self, h: int, w: int, feats: Optional[torch.Tensor] = None) -> bool:
         """True when `accumulate` for (h, w) feature maps is the single masked-accumulation launch
         (C <= 8, h*w % 4 == 0, not a small plane): no label-sort kernel exists then, so a scheduler has
         nothing to keep away from the TMA neighbourhood kernels."""
-        if feats is not None and feats.data_ptr() % 16:
-            return False          # the library then takes the self-contained sort + stream kernel
+        if feats is not None:
+            if feats.data_ptr() % 16:
+                return False      # the library then takes the self-contained sort + stream kernel
+            # Measured inside the step (background EMA, DESIGN.md 4): the masked launch wins while the batch is
+            # too small to fill the GPU with streaming blocks (cfg1, 2 x 4096 px: 131 vs 137 us per step, the
+            # sort runs on two blocks); from 32 k feature pixels on the sort + bulk-copy stream kernel
+            # interferes less with the kernels next to it (cfg2 228 vs 240 us, cfg3 343 vs 349 us)
+            if feats.shape[0] * int(h) * int(w) > self.MASKED_MAX_PIXELS:
+                return False
         return bool(_lib.load().pfst_proto_accum_is_masked(self.C, int(h), int(w)))
 
     def order(self, labels: torch.Tensor, B: int, h: int, w: int, conf: Optional[torch.Tensor] = None,
