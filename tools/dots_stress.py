@@ -41,7 +41,7 @@ for name in names:
             ops.neigh_dots_slot(inp["x_src"], d, 1, ref)
             torch.cuda.synchronize()
         bad += int((b.dots != ref).any())
-    masked = step.bank.masked(inp["x_ema"].shape[2], inp["x_ema"].shape[3])
+    masked = step.bank.masked(inp["x_ema"].shape[2], inp["x_ema"].shape[3], inp["x_ema"])
     print(f"{name}: {n_rep} replays, masked accumulation={masked}, replays with a wrong dot map: {bad}", flush=True)
     bad_total += bad
     step.close() if hasattr(step, "close") else None
