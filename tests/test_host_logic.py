@@ -220,3 +220,46 @@ def test_softmax_space_argmax_shortcut_holds_on_the_cpu_softmax():
         shortcut = torch.where(nan_row, torch.zeros_like(first), first)
         assert torch.equal(shortcut[~near], ref[~near]), C
         assert int(near.sum()) > 0 and int(nan_row.sum()) >= 32
+
+
+def test_classmix_draw_is_resumable_word_by_word_and_validates_its_arguments():
+    """pfst_classmix_draw fed ONE raw word per call (the worst case for its resumable state) gives the same
+    masks as a single call with all words, consumes exactly as many words as numpy's shuffles, and rejects
+    inconsistent arguments instead of reading out of bounds."""
+    import ctypes as C
+    from pfst_b200 import _lib
+    fn = _lib.load().pfst_classmix_draw
+    n, batch = 7, 5
+    classes = np.array([0, 3, 31, 32, 100, 200, 255], dtype=np.int64)
+    rs = np.random.RandomState(123)
+    ref_state = np.random.RandomState(123)
+    want = np.zeros((batch, 8), dtype=np.uint32)
+    for b in range(batch):
+        for c in classes[ref_state.choice(n, int((n + n % 2) / 2), replace=False)]:
+            want[b, c >> 5] |= np.uint32(1) << np.uint32(c & 31)
+    out = np.zeros((batch, 8), dtype=np.uint32)
+    state = np.zeros(258, dtype=np.int32)
+    missing = np.zeros(1, dtype=np.int64)
+    bg = rs._bit_generator
+    used = 0
+    rc = fn(None, 0, classes.ctypes.data, n, batch, out.ctypes.data, state.ctypes.data, missing.ctypes.data)
+    assert rc == 0 and missing[0] == batch * (n - 1)            # nothing drawn yet: one word per swap at least
+    while missing[0]:
+        w = bg.random_raw(1)
+        used += 1
+        assert fn(w.ctypes.data, 1, classes.ctypes.data, n, batch, out.ctypes.data, state.ctypes.data,
+                  missing.ctypes.data) == 0
+    assert np.array_equal(out, want)
+    assert rs.randint(1 << 30) == ref_state.randint(1 << 30)     # both streams advanced by the same words
+    assert used >= batch * (n - 1)
+    # argument validation (negative return codes, no crash)
+    bad_cls = np.array([0, 1, 256], dtype=np.int64)
+    state[:] = 0
+    assert fn(None, 0, bad_cls.ctypes.data, 3, 1, out.ctypes.data, state.ctypes.data, missing.ctypes.data) < 0
+    assert fn(None, 0, classes.ctypes.data, 300, 1, out.ctypes.data, state.ctypes.data, missing.ctypes.data) < 0
+    state[0] = 99                                                # resume index beyond the batch
+    assert fn(None, 0, classes.ctypes.data, n, batch, out.ctypes.data, state.ctypes.data, missing.ctypes.data) < 0
+    state[:] = 0
+    w = bg.random_raw(4 * batch * n)                             # more words than the shuffles can consume
+    assert fn(w.ctypes.data, w.shape[0], classes.ctypes.data, n, batch, out.ctypes.data, state.ctypes.data,
+              missing.ctypes.data) < 0
